@@ -1,0 +1,30 @@
+"""Import the UNMODIFIED reference package `rbnet` from /root/reference (build container only).
+
+TEST INFRASTRUCTURE ONLY -- nothing under rbn_b200/ may import this.  /root/reference does not exist on the
+GPU box, so this loader is used only (a) by oracle/make_golden.py to generate the committed fixtures under
+tests/golden/ and (b) by `-m "not gpu"` tests that are skipped when /root/reference is absent.
+
+The reference cannot be imported as shipped here: `pytorch_lightning`, `matplotlib` and `triangularmap` are
+not installed.  oracle/ref_shims/ holds three stand-ins that perform no arithmetic.
+"""
+import importlib
+import os
+import sys
+
+REFERENCE_ROOT = "/root/reference"
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "rbnet"))
+
+
+def load_reference():
+    """Return the reference's modules as a dict {name: module}; raises if /root/reference is absent."""
+    if not reference_available():
+        raise RuntimeError("/root/reference is not present (GPU box?) -- use the committed fixtures instead")
+    for p in (_SHIMS, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    names = ["rbnet.base", "rbnet.util", "rbnet.sequential", "rbnet.pcfg", "rbnet.multivariate_normal"]
+    return {n.split(".")[1]: importlib.import_module(n) for n in names}
