@@ -1,0 +1,124 @@
+/*
+ * rbn_b200.h -- C ABI of the B200-native inside / outside chart pass (librbn_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of robert-lieck/RBN (`rbnet`): RBN.inside()
+ * (/root/reference/rbnet/base.py:93-121) with the discrete bricks of /root/reference/rbnet/pcfg.py, and the
+ * outside pass that the reference obtains implicitly from torch.autograd.
+ * The reference has no FFI (it is pure Python); the Python binding a maintainer adds is shown in INTEGRATION.md
+ * and shipped as rbn_b200/_lib.py (ctypes).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; every pointer except RbnDesc* / const char* is a DEVICE pointer.
+ *   - The caller allocates everything (including the workspace) and passes a CUDA stream handle (cudaStream_t
+ *     as void*; NULL = legacy default stream).  The library never allocates or frees device memory, keeps no
+ *     pointer after return and never synchronises the host: all work is stream-ordered.
+ *   - Return value 0 = success, negative = error (see RBN_E_*); rbn_last_error() gives a thread-local message.
+ *     Numeric "ungrammatical input" is not an error: log Z = -inf, Z = 0 (tests/test_base.py:293 in the reference).
+ *
+ * Grammar representation ("flat grammar"): a multi-cell RBN is collapsed host-side into one block-structured
+ * grammar with the structural probabilities folded in (rbn_b200/engine.py, restated in oracle/inside_oracle.py
+ * flatten_bricks):
+ *   W     [N][N][N] float32  W[b][c][a] = p(left=b, right=c | parent=a) * p_S(binary | a)   -- parent LAST,
+ *                            as DiscreteBinaryNonTerminalTransition stores it (pcfg.py:91-93, 289-290)
+ *   T     [V][N]    float32  T[y][a]    = p(y | a) * p_S(terminal | a)                       (pcfg.py:339, 351)
+ *   prior [N]       float32  prior[a]   = p_S(var) * p(a)                                    (pcfg.py:270-273)
+ *   tokens  [B][L][n_tvars] int32, index into the rows of T, -1 = None (pcfg.py:346-349) / padding
+ *   lengths [B] int32, 1 <= lengths[b] <= L; the root of sequence b is span (0, lengths[b]) (sequential.py:28-30)
+ */
+#ifndef RBN_B200_H
+#define RBN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBN_ABI_VERSION 1
+
+/* error codes */
+#define RBN_OK            0
+#define RBN_E_BADARG     -1   /* null pointer / non-positive size / unsupported combination */
+#define RBN_E_WORKSPACE  -2   /* workspace smaller than rbn_workspace_bytes() */
+#define RBN_E_CUDA       -3   /* a CUDA call or kernel launch failed (message in rbn_last_error) */
+#define RBN_E_UNSUPPORTED -4  /* shape outside what the selected path supports */
+
+/* RbnDesc.path */
+#define RBN_PATH_AUTO     0   /* tensor-core path when N % 64 == 0 and 64 <= N <= 256, else the shared-memory path */
+#define RBN_PATH_SIMT     1   /* shared-memory / CUDA-core path, fp32 end to end (small nonterminal counts) */
+#define RBN_PATH_TCGEN05  2   /* span-diagonal tcgen05 tensor-core path (fp16 operands, fp32 accumulate) */
+
+typedef struct RbnDesc {
+    int32_t N;            /* number of (flattened) nonterminal values */
+    int32_t V;            /* number of rows of T (flattened terminal alphabet) */
+    int32_t B;            /* sequences in the batch */
+    int32_t L;            /* padded sequence length (max over the batch) */
+    int32_t n_tvars;      /* terminal variables per position (AbstractedPCFG: 1) */
+    int32_t path;         /* RBN_PATH_* */
+    int32_t chunk_items;  /* tensor-core path: spans processed per launch group (0 = default) */
+    int32_t flags;        /* reserved, must be 0 */
+} RbnDesc;
+
+/* ABI version of the loaded library (== RBN_ABI_VERSION of the header it was built from). */
+int rbn_abi_version(void);
+
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* rbn_last_error(void);
+
+/* Which path RBN_PATH_AUTO resolves to for this descriptor (RBN_PATH_SIMT or RBN_PATH_TCGEN05), or <0. */
+int rbn_resolve_path(const RbnDesc* desc);
+
+/* Bytes of caller-allocated device workspace for one forward (+ its backward).  The workspace carries the
+ * chart between rbn_inside_forward and rbn_inside_backward / rbn_export_chart; distinct concurrent passes need
+ * distinct workspaces.  Base address must be 1024-byte aligned.  Returns 0 on a bad descriptor. */
+size_t rbn_workspace_bytes(const RbnDesc* desc);
+
+/* Inside pass.  Replaces the loop nest of RBN.inside (base.py:93-121): the width-major schedule
+ * (sequential.py:23-26), DiscreteTerminalTransition.inside_marginals (pcfg.py:344-352),
+ * DiscreteBinaryNonTerminalTransition.inside_marginals (pcfg.py:305-314), DiscreteCell.inside_mixture
+ * (pcfg.py:387-398) and DiscretePrior.marginal_likelihood (pcfg.py:270-273), batched over B sequences.
+ * Outputs (device, float32 [B] each):
+ *   logZ      natural-log marginal likelihood, -inf when Z == 0
+ *   zroot     sum_a prior[a] * mantissa(root)[a]
+ *   rootexp   power-of-two exponent of the root cell:  Z = zroot * 2^rootexp  (exact linear-space value)
+ */
+int rbn_inside_forward(const RbnDesc* desc,
+                       const float* W, const float* T, const float* prior,
+                       const int32_t* tokens, const int32_t* lengths,
+                       void* workspace, size_t workspace_bytes,
+                       float* logZ, float* zroot, float* rootexp,
+                       void* stream);
+
+/* Outside pass / expected rule counts.  Replaces the torch.autograd traversal of the reference's chart writes
+ * (sequential.py:36 CopySlices chain).  Must follow rbn_inside_forward on the same
+ * workspace and inputs.  With R_b = rootexp[b] + log2(zroot[b]) (or rootexp[b] when Z_b == 0) it accumulates
+ *   gW[b][c][a] = sum_seq coef[seq] * 2^-R_seq * dZ_seq/dW[b][c][a]      (likewise gT [V][N], gPrior [N])
+ * i.e. coef = dLoss/dlogZ gives dLoss/dW for grammatical sequences.  gW/gT/gPrior are OVERWRITTEN. */
+int rbn_inside_backward(const RbnDesc* desc,
+                        const float* W, const float* T, const float* prior,
+                        const int32_t* tokens, const int32_t* lengths,
+                        void* workspace, size_t workspace_bytes,
+                        const float* coef,
+                        float* gW, float* gT, float* gPrior,
+                        void* stream);
+
+/* Chart of one sequence in the reference's layout: rows ordered as triangularmap.TMap orders them (root first:
+ * row = d(d+1)/2 + start with d = n - (end - start); pinned by /root/reference/tests/test_pcfg.py:14-19),
+ * linear probability space, float64 [n(n+1)/2][N] with n = lengths[seq].  Serves SequentialRBN.inside_chart
+ * (sequential.py:38-40) and PCFG.map_inside_chart (pcfg.py:30-41). */
+int rbn_export_chart(const RbnDesc* desc, const int32_t* lengths,
+                     const void* workspace, size_t workspace_bytes,
+                     int32_t seq, double* out, void* stream);
+
+/* Fused constrained-parameter maintenance (the step right after the path in a training loop):
+ * LogProb.enforce_constraints (util.py:193-198): log_p[g][k] -= logsumexp_k log_p[g][k] over `groups` groups of
+ * `group_size` contiguous-with-stride entries.  Layout: element (g, k) at log_p[k * groups + g] (the reference
+ * normalises over the LEADING dims, parent last).  Returns RBN_E_BADARG if a group's normaliser is -inf
+ * is NOT detected on device; `bad` (device int32, may be NULL) is set to the number of such groups. */
+int rbn_lognormalize(float* log_p, int64_t group_size, int64_t groups, int32_t* bad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBN_B200_H */

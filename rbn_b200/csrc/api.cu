@@ -1,0 +1,175 @@
+// extern "C" entry points of librbn_b200 (see include/rbn_b200.h for the contract and the reference citations).
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace rbn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int simt_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*, const int*,
+                 float*, float*, float*, cudaStream_t);
+int simt_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
+                  const int*, const float*, float*, float*, float*, cudaStream_t);
+int export_chart(const RbnDesc*, const WsLayout&, const char*, const int*, int, double*, cudaStream_t);
+int lognormalize(float*, long long, long long, int*, cudaStream_t);
+int tc_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*, const int*,
+               float*, float*, float*, cudaStream_t);
+int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
+                const int*, const float*, float*, float*, float*, cudaStream_t);
+
+static bool desc_ok(const RbnDesc* d) {
+    if (!d) { set_error("desc is NULL"); return false; }
+    if (d->N < 1 || d->V < 1 || d->B < 1 || d->L < 1 || d->n_tvars < 1) {
+        set_error("bad descriptor: N=%d V=%d B=%d L=%d n_tvars=%d", d->N, d->V, d->B, d->L, d->n_tvars);
+        return false;
+    }
+    if (d->path < RBN_PATH_AUTO || d->path > RBN_PATH_TCGEN05 || d->flags != 0 || d->chunk_items < 0) {
+        set_error("bad descriptor: path=%d flags=%d chunk_items=%d", d->path, d->flags, d->chunk_items);
+        return false;
+    }
+    return true;
+}
+
+static bool tc_shape_ok(const RbnDesc* d) { return d->N % 64 == 0 && d->N >= 64 && d->N <= 256 && d->L >= 2; }
+
+int resolve_path(const RbnDesc* d) {
+    if (d->path == RBN_PATH_SIMT) return RBN_PATH_SIMT;
+    if (d->path == RBN_PATH_TCGEN05) {
+        if (!tc_shape_ok(d)) {
+            set_error("tensor-core path needs N in {64,128,192,256} and L >= 2 (got N=%d L=%d)", d->N, d->L);
+            return RBN_E_UNSUPPORTED;
+        }
+        return RBN_PATH_TCGEN05;
+    }
+    return tc_shape_ok(d) ? RBN_PATH_TCGEN05 : RBN_PATH_SIMT;
+}
+
+bool make_layout(const RbnDesc* d, WsLayout* o) {
+    memset(o, 0, sizeof(*o));
+    int path = resolve_path(d);
+    if (path < 0) return false;
+    size_t N = d->N, B = d->B, L = d->L, C = cells_per_seq(d->L);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t r = off; off = align_up(off + bytes, 1024); return r; };
+    o->chart_val = take(B * C * N * sizeof(float));
+    o->chart_exp = take(B * C * sizeof(int));
+    o->alpha = take(B * C * N * sizeof(float));
+    o->zroot = take(B * sizeof(float));
+    o->rootexp = take(B * sizeof(int));
+    if (path == RBN_PATH_TCGEN05) {
+        size_t Lp = align_up(L + 16, 16);
+        o->Lp = (int)Lp;
+        size_t max_items = B * (L - 1);                        // widest diagonal (w = 2)
+        size_t chunk = d->chunk_items > 0 ? (size_t)d->chunk_items : 8192;
+        if (chunk > max_items) chunk = max_items;
+        chunk = align_up(chunk, 128);
+        o->chunk = (int)chunk;
+        o->lc = take(B * L * Lp * N * sizeof(__half));
+        o->rc = take(B * (L + 1) * Lp * N * sizeof(__half));
+        o->wt = take(N * N * N * sizeof(__half));
+        o->wk = take(N * N * N * sizeof(__half));
+        o->wexp = take(N * sizeof(int));
+        o->y = take(chunk * N * N * sizeof(__half));
+        o->gy = take(chunk * N * N * sizeof(__half));
+        o->item_e = take(chunk * sizeof(int));
+        o->ghat = take(chunk * N * sizeof(__half));
+        o->gabs = take(chunk * N * sizeof(__half));
+        o->gexp = take(chunk * sizeof(int));
+    }
+    o->total = off;
+    return true;
+}
+
+}  // namespace rbn
+
+using namespace rbn;
+
+extern "C" {
+
+int rbn_abi_version(void) { return RBN_ABI_VERSION; }
+
+const char* rbn_last_error(void) { return g_err; }
+
+int rbn_resolve_path(const RbnDesc* desc) {
+    if (!desc_ok(desc)) return RBN_E_BADARG;
+    return resolve_path(desc);
+}
+
+size_t rbn_workspace_bytes(const RbnDesc* desc) {
+    WsLayout ws;
+    if (!desc_ok(desc) || !make_layout(desc, &ws)) return 0;
+    return ws.total;
+}
+
+int rbn_inside_forward(const RbnDesc* desc, const float* W, const float* T, const float* prior, const int32_t* tokens,
+                       const int32_t* lengths, void* workspace, size_t workspace_bytes, float* logZ, float* zroot,
+                       float* rootexp, void* stream) {
+    if (!desc_ok(desc)) return RBN_E_BADARG;
+    if (!W || !T || !prior || !tokens || !lengths || !workspace || !logZ || !zroot || !rootexp) {
+        set_error("rbn_inside_forward: NULL pointer argument");
+        return RBN_E_BADARG;
+    }
+    WsLayout ws;
+    if (!make_layout(desc, &ws)) return RBN_E_UNSUPPORTED;
+    if (workspace_bytes < ws.total || ((uintptr_t)workspace & 1023)) {
+        set_error("workspace too small or misaligned: have %zu need %zu (1024-byte aligned)", workspace_bytes, ws.total);
+        return RBN_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (resolve_path(desc) == RBN_PATH_TCGEN05)
+        return tc_forward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, logZ, zroot, rootexp, st);
+    return simt_forward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, logZ, zroot, rootexp, st);
+}
+
+int rbn_inside_backward(const RbnDesc* desc, const float* W, const float* T, const float* prior, const int32_t* tokens,
+                        const int32_t* lengths, void* workspace, size_t workspace_bytes, const float* coef, float* gW,
+                        float* gT, float* gPrior, void* stream) {
+    if (!desc_ok(desc)) return RBN_E_BADARG;
+    if (!W || !T || !prior || !tokens || !lengths || !workspace || !coef || !gW || !gT || !gPrior) {
+        set_error("rbn_inside_backward: NULL pointer argument");
+        return RBN_E_BADARG;
+    }
+    WsLayout ws;
+    if (!make_layout(desc, &ws)) return RBN_E_UNSUPPORTED;
+    if (workspace_bytes < ws.total || ((uintptr_t)workspace & 1023)) {
+        set_error("workspace too small or misaligned: have %zu need %zu (1024-byte aligned)", workspace_bytes, ws.total);
+        return RBN_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (resolve_path(desc) == RBN_PATH_TCGEN05)
+        return tc_backward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, coef, gW, gT, gPrior, st);
+    return simt_backward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, coef, gW, gT, gPrior, st);
+}
+
+int rbn_export_chart(const RbnDesc* desc, const int32_t* lengths, const void* workspace, size_t workspace_bytes,
+                     int32_t seq, double* out, void* stream) {
+    if (!desc_ok(desc)) return RBN_E_BADARG;
+    if (!lengths || !workspace || !out || seq < 0 || seq >= desc->B) {
+        set_error("rbn_export_chart: bad argument (seq=%d)", seq);
+        return RBN_E_BADARG;
+    }
+    WsLayout ws;
+    if (!make_layout(desc, &ws)) return RBN_E_UNSUPPORTED;
+    if (workspace_bytes < ws.total) {
+        set_error("workspace too small: have %zu need %zu", workspace_bytes, ws.total);
+        return RBN_E_WORKSPACE;
+    }
+    return export_chart(desc, ws, (const char*)workspace, lengths, seq, out, (cudaStream_t)stream);
+}
+
+int rbn_lognormalize(float* log_p, int64_t group_size, int64_t groups, int32_t* bad, void* stream) {
+    if (!log_p || group_size < 1 || groups < 1) {
+        set_error("rbn_lognormalize: bad argument");
+        return RBN_E_BADARG;
+    }
+    return lognormalize(log_p, group_size, groups, bad, (cudaStream_t)stream);
+}
+
+}  // extern "C"

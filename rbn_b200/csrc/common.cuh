@@ -1,0 +1,69 @@
+// Shared definitions for librbn_b200: error handling, chart indexing, workspace layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/rbn_b200.h"
+
+namespace rbn {
+
+// ---- error handling (C ABI never throws) --------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define RBN_CUDA_CHECK(expr)                                                                              \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess) {                                                                          \
+            rbn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);   \
+            return RBN_E_CUDA;                                                                            \
+        }                                                                                                 \
+    } while (0)
+#define RBN_LAUNCH_CHECK(name)                                                                            \
+    do {                                                                                                  \
+        cudaError_t _e = cudaGetLastError();                                                              \
+        if (_e != cudaSuccess) {                                                                          \
+            rbn::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));                      \
+            return RBN_E_CUDA;                                                                            \
+        }                                                                                                 \
+    } while (0)
+
+// ---- chart indexing ---------------------------------------------------------------------------------------------
+// Span-major ("diagonal-major") compact chart: all cells of width 1, then width 2, ...  Within a sequence the cell
+// of span (i, i+w) sits at cell_off(w, L) + i; a sequence has L(L+1)/2 cells.  The reference's root-first TMap
+// order (pcfg.py:215, test_pcfg.py:14-19) is produced on export only.
+__host__ __device__ inline int cell_off(int w, int L) { return (w - 1) * (L + 1) - ((w - 1) * w) / 2; }
+__host__ __device__ inline int cells_per_seq(int L) { return L * (L + 1) / 2; }
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- workspace layout -------------------------------------------------------------------------------------------
+struct WsLayout {
+    // common (both paths)
+    size_t chart_val;   // float  [B][C][N]   mantissas, max 1 per cell (power-of-two scaled => exact)
+    size_t chart_exp;   // int32  [B][C]      beta = mantissa * 2^exp
+    size_t alpha;       // float  [B][C][N]   scaled outside values (backward only)
+    size_t zroot;       // float  [B]
+    size_t rootexp;     // int32  [B]
+    // tensor-core path
+    size_t lc;          // half [B][L][Lp][N]    start-major operand copy: cell (i, j) at row (b*L + i)*Lp + j
+    size_t rc;          // half [B][L+1][Lp][N]  end-major operand copy:   cell (j, k) at row (b*(L+1) + k)*Lp + j
+    size_t wt;          // half [N][N*N]         Wt[a][b*N+c] = W[b][c][a] * 2^-wexp[a]
+    size_t wk;          // half [N*N][N]         Wk[b*N+c][a] = W[b][c][a] * 2^-wexp[a]
+    size_t wexp;        // int32 [N]
+    size_t y;           // half [chunk][N*N]
+    size_t gy;          // half [chunk][N*N]
+    size_t item_e;      // int32 [chunk]         E_m = max_j (e_ij + e_jk)
+    size_t ghat;        // half [chunk][N]       item-normalised upstream gradient
+    size_t gabs;        // half [chunk][N]       absolutely scaled upstream gradient (for the count GEMM)
+    size_t gexp;        // int32 [chunk]
+    size_t total;
+    int Lp;
+    int chunk;
+};
+
+int resolve_path(const RbnDesc* d);
+bool make_layout(const RbnDesc* d, WsLayout* out);
+
+}  // namespace rbn

@@ -1,0 +1,411 @@
+// Shared-memory / CUDA-core path of the inside and outside passes (fp32 end to end).
+//
+// Serves small nonterminal counts (N not a multiple of 64, e.g. the reference's own N <= 10 grammars) and is the
+// on-device cross-check for the tensor-core path.  One CTA per span (b, i, i+w); spans of one width are one
+// launch ("span diagonal"), widths ascend in the inside pass and descend in the outside pass.
+//
+// Arithmetic restated from the reference (never copied):
+//   emission   beta[i,i+1,a] = sum_t T[y_i^t, a]                       pcfg.py:344-352 (+ structural weight, folded)
+//   binary     beta[i,k,a]   = sum_j sum_{b,c} W[b,c,a] beta[i,j,b] beta[j,k,c]   pcfg.py:305-314, 387-398
+//   root       Z = sum_a prior[a] beta[0,n,a]                          pcfg.py:270-273
+// in per-cell power-of-two scaled form: beta = m * 2^e with max_a m = [0.5, 1); an all-zero cell keeps the finite
+// exponent of its best split so that derivatives w.r.t. zero-probability entries survive (oracle: flat_forward).
+#include "common.cuh"
+#include <limits.h>
+#include <math.h>
+
+namespace rbn {
+
+static constexpr int kThreads = 256;
+static constexpr int kMaxAPerThread = 4;   // N <= 1024 on this path
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int k = 1; k < (blockDim.x >> 5); ++k) r = fmaxf(r, red[k]);
+    return r;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) r += red[k];
+    return r;
+}
+
+// exponent e with mx * 2^-e in [0.5, 1); 0 for mx == 0
+__device__ __forceinline__ int norm_exp(float mx) {
+    if (!(mx > 0.f)) return 0;
+    int e;
+    frexpf(mx, &e);
+    return e;
+}
+
+// ---- width-1 cells ---------------------------------------------------------------------------------------------
+__global__ void k_emission(int N, int L, int nt, const float* __restrict__ T, const int* __restrict__ tokens,
+                           const int* __restrict__ lengths, float* __restrict__ cv, int* __restrict__ ce) {
+    __shared__ float red[32];
+    int b = blockIdx.x / L, i = blockIdx.x % L;
+    if (i >= lengths[b]) return;
+    size_t cell = (size_t)b * cells_per_seq(L) + i;
+    float v[kMaxAPerThread];
+    float mx = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxAPerThread; ++q) {
+        int a = threadIdx.x + q * kThreads;
+        float s = 0.f;
+        if (a < N)
+            for (int t = 0; t < nt; ++t) {
+                int y = tokens[((size_t)b * L + i) * nt + t];
+                if (y >= 0) s += T[(size_t)y * N + a];
+            }
+        v[q] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = block_max(mx, red);
+    int e = norm_exp(mx);
+#pragma unroll
+    for (int q = 0; q < kMaxAPerThread; ++q) {
+        int a = threadIdx.x + q * kThreads;
+        if (a < N) cv[cell * N + a] = ldexpf(v[q], -e);
+    }
+    if (threadIdx.x == 0) ce[cell] = e;
+}
+
+// split coefficients of span (i, i+w): c_u = 2^(e_left(u) + e_right(u) - E), E = max_u (...)
+__device__ __forceinline__ int split_coefs(int L, int w, int i, const int* __restrict__ ce_seq, float* cj, int* sE) {
+    if (threadIdx.x == 0) *sE = INT_MIN;
+    __syncthreads();
+    int mine = INT_MIN;
+    for (int u = 1 + threadIdx.x; u < w; u += blockDim.x) {
+        int s = ce_seq[cell_off(u, L) + i] + ce_seq[cell_off(w - u, L) + i + u];
+        mine = max(mine, s);
+    }
+    if (mine != INT_MIN) atomicMax(sE, mine);
+    __syncthreads();
+    int E = *sE;
+    for (int u = 1 + threadIdx.x; u < w; u += blockDim.x) {
+        int s = ce_seq[cell_off(u, L) + i] + ce_seq[cell_off(w - u, L) + i + u];
+        cj[u] = ldexpf(1.0f, max(s - E, -200));
+    }
+    __syncthreads();
+    return E;
+}
+
+// Y[bb][c] = sum_u c_u * left_u[b0+bb] * right_u[c]   (the split-sum, taken before the rule contraction)
+__device__ __forceinline__ void split_sum_block(int N, int L, int w, int i, int b0, int tb,
+                                                const float* __restrict__ cv_seq, const float* cj, float* Y) {
+    for (int idx = threadIdx.x; idx < tb * N; idx += blockDim.x) {
+        int bb = idx / N, c = idx - bb * N;
+        float acc = 0.f;
+        for (int u = 1; u < w; ++u) {
+            const float* l = cv_seq + (size_t)(cell_off(u, L) + i) * N;
+            const float* r = cv_seq + (size_t)(cell_off(w - u, L) + i + u) * N;
+            acc += cj[u] * l[b0 + bb] * r[c];
+        }
+        Y[idx] = acc;
+    }
+}
+
+// ---- inside: one span diagonal ----------------------------------------------------------------------------------
+__global__ void k_inside_diag(int N, int L, int w, int TB, const float* __restrict__ W,
+                              const int* __restrict__ lengths, float* __restrict__ cv, int* __restrict__ ce) {
+    extern __shared__ float sm[];
+    __shared__ float red[32];
+    __shared__ int sE;
+    int nI = L - w + 1;
+    int b = blockIdx.x / nI, i = blockIdx.x % nI;
+    if (i + w > lengths[b]) return;
+    size_t seq = (size_t)b * cells_per_seq(L);
+    const float* cv_seq = cv + seq * N;
+    const int* ce_seq = ce + seq;
+    float* cj = sm;               // [L+1]
+    float* Y = sm + (L + 1);      // [TB][N]
+    int E = split_coefs(L, w, i, ce_seq, cj, &sE);
+
+    float out[kMaxAPerThread];
+#pragma unroll
+    for (int q = 0; q < kMaxAPerThread; ++q) out[q] = 0.f;
+    for (int b0 = 0; b0 < N; b0 += TB) {
+        int tb = min(TB, N - b0);
+        split_sum_block(N, L, w, i, b0, tb, cv_seq, cj, Y);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kMaxAPerThread; ++q) {
+            int a = threadIdx.x + q * kThreads;
+            if (a < N) {
+                float acc = out[q];
+                const float* Wp = W + (size_t)b0 * N * N + a;
+                for (int idx = 0; idx < tb * N; ++idx) acc = fmaf(Y[idx], Wp[(size_t)idx * N], acc);
+                out[q] = acc;
+            }
+        }
+        __syncthreads();
+    }
+    float mx = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxAPerThread; ++q) mx = fmaxf(mx, out[q]);
+    mx = block_max(mx, red);
+    int e = norm_exp(mx);
+    size_t cell = seq + cell_off(w, L) + i;
+#pragma unroll
+    for (int q = 0; q < kMaxAPerThread; ++q) {
+        int a = threadIdx.x + q * kThreads;
+        if (a < N) cv[cell * N + a] = ldexpf(out[q], -e);
+    }
+    if (threadIdx.x == 0) ce[cell] = E + e;
+}
+
+// ---- root / prior -----------------------------------------------------------------------------------------------
+__global__ void k_root(int N, int L, const float* __restrict__ prior, const int* __restrict__ lengths,
+                       const float* __restrict__ cv, const int* __restrict__ ce,
+                       float* __restrict__ logZ, float* __restrict__ zroot, float* __restrict__ rootexp,
+                       float* __restrict__ ws_zroot, int* __restrict__ ws_rootexp) {
+    __shared__ float red[32];
+    int b = blockIdx.x;
+    int n = lengths[b];
+    size_t cell = (size_t)b * cells_per_seq(L) + cell_off(n, L);
+    float s = 0.f;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) s += prior[a] * cv[cell * N + a];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        int e = ce[cell];
+        zroot[b] = s;
+        rootexp[b] = (float)e;
+        ws_zroot[b] = s;
+        ws_rootexp[b] = e;
+        logZ[b] = (s > 0.f) ? (logf(s) + (float)e * 0.69314718055994530942f) : -INFINITY;
+    }
+}
+
+// ---- outside ------------------------------------------------------------------------------------------------------
+// scaled adjoint: alpha[cell][a] = dZ/dbeta[cell][a] * 2^(e_cell - R_seq) * coef_seq   ("scaled outside")
+__global__ void k_outside_seed(int N, int L, const float* __restrict__ prior, const int* __restrict__ lengths,
+                               const float* __restrict__ cv, const float* __restrict__ ws_zroot,
+                               const float* __restrict__ coef, float* __restrict__ alpha,
+                               float* __restrict__ gPrior) {
+    int b = blockIdx.x;
+    int n = lengths[b];
+    size_t cell = (size_t)b * cells_per_seq(L) + cell_off(n, L);
+    float z = ws_zroot[b];
+    float f = coef[b] / (z > 0.f ? z : 1.0f);
+    if (f == 0.f) return;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        alpha[cell * N + a] = f * prior[a];
+        float m = cv[cell * N + a];
+        if (m != 0.f) atomicAdd(&gPrior[a], f * m);
+    }
+}
+
+__global__ void k_outside_diag(int N, int L, int w, int TB, const float* __restrict__ W,
+                               const int* __restrict__ lengths, const float* __restrict__ cv,
+                               const int* __restrict__ ce, float* __restrict__ alpha, float* __restrict__ gW) {
+    extern __shared__ float sm[];
+    __shared__ int sE;
+    __shared__ int sAny;
+    int nI = L - w + 1;
+    int b = blockIdx.x / nI, i = blockIdx.x % nI;
+    if (i + w > lengths[b]) return;
+    size_t seq = (size_t)b * cells_per_seq(L);
+    const float* cv_seq = cv + seq * N;
+    const int* ce_seq = ce + seq;
+    float* al_seq = alpha + seq * N;
+    float* cj = sm;                     // [L+1]
+    float* G = cj + (L + 1);            // [N]
+    float* Y = G + N;                   // [TB][N]
+    float* gY = Y + (size_t)TB * N;     // [TB][N]
+    int cellw = cell_off(w, L) + i;
+    int E = split_coefs(L, w, i, ce_seq, cj, &sE);
+    int e_new = ce_seq[cellw] - E;
+    if (threadIdx.x == 0) sAny = 0;
+    __syncthreads();
+    int any = 0;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        float g = ldexpf(al_seq[(size_t)cellw * N + a], -e_new);
+        G[a] = g;
+        any |= (g != 0.f);
+    }
+    if (any) sAny = 1;
+    __syncthreads();
+    if (!sAny) return;   // span not reachable from the root (or coef == 0): contributes nothing
+
+    for (int b0 = 0; b0 < N; b0 += TB) {
+        int tb = min(TB, N - b0);
+        split_sum_block(N, L, w, i, b0, tb, cv_seq, cj, Y);
+        // gY[bb][c] = sum_a W[b0+bb][c][a] G[a]
+        for (int idx = threadIdx.x; idx < tb * N; idx += blockDim.x) {
+            const float* Wp = W + ((size_t)b0 * N + idx) * N;
+            float acc = 0.f;
+            for (int a = 0; a < N; ++a) acc = fmaf(Wp[a], G[a], acc);
+            gY[idx] = acc;
+        }
+        __syncthreads();
+        // expected rule counts: gW[b][c][a] += Y[b][c] * G[a]
+        for (int idx = 0; idx < tb * N; ++idx) {
+            float y = Y[idx];
+            if (y == 0.f) continue;
+            float* gp = gW + ((size_t)b0 * N + idx) * N;
+            for (int a = threadIdx.x; a < N; a += blockDim.x) {
+                float g = G[a];
+                if (g != 0.f) atomicAdd(&gp[a], y * g);
+            }
+        }
+        // children: alpha[i,j][b] += c_u sum_c gY[b][c] right_u[c];  alpha[j,k][c] += c_u sum_b gY[b][c] left_u[b]
+        for (int u = 1; u < w; ++u) {
+            float cu = cj[u];
+            if (cu == 0.f) continue;
+            int lcell = cell_off(u, L) + i, rcell = cell_off(w - u, L) + i + u;
+            const float* l = cv_seq + (size_t)lcell * N;
+            const float* r = cv_seq + (size_t)rcell * N;
+            for (int bb = threadIdx.x; bb < tb; bb += blockDim.x) {
+                float acc = 0.f;
+                for (int c = 0; c < N; ++c) acc = fmaf(gY[bb * N + c], r[c], acc);
+                if (acc != 0.f) atomicAdd(&al_seq[(size_t)lcell * N + b0 + bb], cu * acc);
+            }
+            for (int c = threadIdx.x; c < N; c += blockDim.x) {
+                float acc = 0.f;
+                for (int bb = 0; bb < tb; ++bb) acc = fmaf(gY[bb * N + c], l[b0 + bb], acc);
+                if (acc != 0.f) atomicAdd(&al_seq[(size_t)rcell * N + c], cu * acc);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_emission_bwd(int N, int L, int nt, const int* __restrict__ tokens, const int* __restrict__ lengths,
+                               const int* __restrict__ ce, const float* __restrict__ alpha, float* __restrict__ gT) {
+    int b = blockIdx.x / L, i = blockIdx.x % L;
+    if (i >= lengths[b]) return;
+    size_t cell = (size_t)b * cells_per_seq(L) + i;
+    int e = ce[cell];
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        float g = ldexpf(alpha[cell * N + a], -e);
+        if (g == 0.f) continue;
+        for (int t = 0; t < nt; ++t) {
+            int y = tokens[((size_t)b * L + i) * nt + t];
+            if (y >= 0) atomicAdd(&gT[(size_t)y * N + a], g);
+        }
+    }
+}
+
+// ---- chart export in the reference's TMap order, linear space, float64 ---------------------------------------------
+__global__ void k_export_chart(int N, int L, const int* __restrict__ lengths, int seq, const float* __restrict__ cv,
+                               const int* __restrict__ ce, double* __restrict__ out) {
+    // blockIdx.x = row in TMap order: row = d(d+1)/2 + start, d = n - width
+    int row = blockIdx.x;
+    int n = lengths[seq];
+    if (row >= n * (n + 1) / 2) return;
+    int d = (int)((sqrtf(8.f * row + 1.f) - 1.f) * 0.5f);
+    while ((d + 1) * (d + 2) / 2 <= row) ++d;
+    while (d * (d + 1) / 2 > row) --d;
+    int start = row - d * (d + 1) / 2;
+    int w = n - d;
+    size_t cell = (size_t)seq * cells_per_seq(L) + cell_off(w, L) + start;
+    int e = ce[cell];
+    for (int a = threadIdx.x; a < N; a += blockDim.x) out[(size_t)row * N + a] = ldexp((double)cv[cell * N + a], e);
+}
+
+// ---- log-space renormalisation (LogProb.enforce_constraints, util.py:193-198) --------------------------------------
+__global__ void k_lognormalize(float* __restrict__ lp, long long gs, long long groups, int* __restrict__ bad) {
+    // one thread per group; element (g, k) at lp[k * groups + g] => coalesced across the warp
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    float mx = -INFINITY;
+    for (long long k = 0; k < gs; ++k) mx = fmaxf(mx, lp[k * groups + g]);
+    if (mx == -INFINITY) {
+        if (bad) atomicAdd(bad, 1);
+        return;
+    }
+    float s = 0.f;
+    for (long long k = 0; k < gs; ++k) s += __expf(lp[k * groups + g] - mx);
+    float lse = mx + logf(s);
+    for (long long k = 0; k < gs; ++k) lp[k * groups + g] -= lse;
+}
+
+// ---- host-side drivers ----------------------------------------------------------------------------------------------
+static int pick_tb(int N, int n_arrays) {
+    // rows of Y (and gY) kept in shared memory at once; <= 64 KB in total for the tiles
+    int tb = (64 * 1024 / 4) / (N * n_arrays);
+    if (tb < 1) tb = 1;
+    if (tb > N) tb = N;
+    return tb;
+}
+
+int simt_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
+                 const int* tokens, const int* lengths, float* logZ, float* zroot, float* rootexp, cudaStream_t st) {
+    if (d->N > kThreads * kMaxAPerThread) {
+        set_error("shared-memory path supports N <= %d (got %d)", kThreads * kMaxAPerThread, d->N);
+        return RBN_E_UNSUPPORTED;
+    }
+    float* cv = (float*)(base + ws.chart_val);
+    int* ce = (int*)(base + ws.chart_exp);
+    int N = d->N, L = d->L, B = d->B;
+    k_emission<<<B * L, kThreads, 0, st>>>(N, L, d->n_tvars, T, tokens, lengths, cv, ce);
+    RBN_LAUNCH_CHECK("k_emission");
+    int TB = pick_tb(N, 1);
+    size_t smem = ((size_t)(L + 1) + (size_t)TB * N) * sizeof(float);
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(k_inside_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int w = 2; w <= L; ++w) {
+        k_inside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce);
+        RBN_LAUNCH_CHECK("k_inside_diag");
+    }
+    k_root<<<B, 128, 0, st>>>(N, L, prior, lengths, cv, ce, logZ, zroot, rootexp, (float*)(base + ws.zroot),
+                              (int*)(base + ws.rootexp));
+    RBN_LAUNCH_CHECK("k_root");
+    return RBN_OK;
+}
+
+int simt_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
+                  const int* tokens, const int* lengths, const float* coef, float* gW, float* gT, float* gPrior,
+                  cudaStream_t st) {
+    (void)T;
+    float* cv = (float*)(base + ws.chart_val);
+    int* ce = (int*)(base + ws.chart_exp);
+    float* alpha = (float*)(base + ws.alpha);
+    int N = d->N, L = d->L, B = d->B;
+    size_t C = cells_per_seq(L);
+    RBN_CUDA_CHECK(cudaMemsetAsync(alpha, 0, (size_t)B * C * N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(gW, 0, (size_t)N * N * N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
+    k_outside_seed<<<B, 128, 0, st>>>(N, L, prior, lengths, cv, (const float*)(base + ws.zroot), coef, alpha, gPrior);
+    RBN_LAUNCH_CHECK("k_outside_seed");
+    int TB = pick_tb(N, 2);
+    size_t smem = ((size_t)(L + 1) + N + 2 * (size_t)TB * N) * sizeof(float);
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(k_outside_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int w = L; w >= 2; --w) {
+        k_outside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce, alpha, gW);
+        RBN_LAUNCH_CHECK("k_outside_diag");
+    }
+    k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, ce, alpha, gT);
+    RBN_LAUNCH_CHECK("k_emission_bwd");
+    return RBN_OK;
+}
+
+int export_chart(const RbnDesc* d, const WsLayout& ws, const char* base, const int* lengths, int seq, double* out,
+                 cudaStream_t st) {
+    const float* cv = (const float*)(base + ws.chart_val);
+    const int* ce = (const int*)(base + ws.chart_exp);
+    k_export_chart<<<cells_per_seq(d->L), 128, 0, st>>>(d->N, d->L, lengths, seq, cv, ce, out);
+    RBN_LAUNCH_CHECK("k_export_chart");
+    return RBN_OK;
+}
+
+int lognormalize(float* lp, long long gs, long long groups, int* bad, cudaStream_t st) {
+    if (bad) RBN_CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    int threads = 128;
+    long long blocks = (groups + threads - 1) / threads;
+    k_lognormalize<<<(unsigned)blocks, threads, 0, st>>>(lp, gs, groups, bad);
+    RBN_LAUNCH_CHECK("k_lognormalize");
+    return RBN_OK;
+}
+
+}  // namespace rbn

@@ -1,0 +1,287 @@
+"""Host side of the fused chart pass: grammar flattening, token packing, the autograd boundary.
+
+`InsideEngine` turns a `SequentialRBN` made of discrete bricks into the flat grammar the C ABI takes
+(include/rbn_b200.h), with plain differentiable torch ops, so gradients flow back to the very Parameters the
+reference differentiates (and their `project_grad` hooks still fire, /root/reference/rbnet/util.py:139,179):
+
+    W[o_l+b, o_r+c, o_v+a] += S_v[tau, a] * W_tau[b, c, a]     binary transition tau of cell v
+                                                               (pcfg.py:312 weighted by pcfg.py:395-398)
+    T[q_t+y, o_v+a]        += S_v[tau, a] * T_tau[y, a]        terminal transition tau with term_idx t (pcfg.py:351)
+    prior[o_v+a]            = omega_v * pi_v[a]                (pcfg.py:270-273)
+
+The inside pass and the outside pass (expected rule counts) run in librbn_b200.so; `_InsideFn` is the
+torch.autograd.Function that joins them.  No arithmetic of the path happens on the host.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .tmap import TMap
+
+
+def _cuda_device():
+    if not torch.cuda.is_available():
+        raise _lib.RbnError("rbn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class _Pass:
+    """One forward pass on the device: inputs, workspace (holds the chart) and outputs."""
+
+    def __init__(self, W, T, prior, tokens, lengths, path=_lib.PATH_AUTO, chunk_items=0):
+        lib = _lib.load()
+        dev = W.device
+        B, L, nt = tokens.shape
+        self.desc = _lib.RbnDesc(N=W.shape[0], V=T.shape[0], B=B, L=L, n_tvars=nt, path=path,
+                                 chunk_items=chunk_items, flags=0)
+        nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
+        if nbytes == 0:
+            _lib.check(-1, "rbn_workspace_bytes")
+        self.W, self.T, self.prior, self.tokens, self.lengths = W, T, prior, tokens, lengths
+        self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        self.ws_off = (-self.workspace.data_ptr()) % 1024
+        self.ws_bytes = nbytes
+        self.logZ = torch.empty(B, dtype=torch.float32, device=dev)
+        self.zroot = torch.empty(B, dtype=torch.float32, device=dev)
+        self.rootexp = torch.empty(B, dtype=torch.float32, device=dev)
+
+    def _ws(self):
+        return ctypes.c_void_p(self.workspace.data_ptr() + self.ws_off)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.W.device).cuda_stream)
+
+    def forward(self):
+        lib = _lib.load()
+        with torch.cuda.device(self.W.device):
+            rc = lib.rbn_inside_forward(ctypes.byref(self.desc), _ptr(self.W), _ptr(self.T), _ptr(self.prior),
+                                        _ptr(self.tokens), _ptr(self.lengths), self._ws(), self.ws_bytes,
+                                        _ptr(self.logZ), _ptr(self.zroot), _ptr(self.rootexp), self._stream())
+        _lib.check(rc, "rbn_inside_forward")
+
+    def backward(self, coef):
+        lib = _lib.load()
+        dev = self.W.device
+        gW = torch.empty_like(self.W)
+        gT = torch.empty_like(self.T)
+        gP = torch.empty_like(self.prior)
+        coef = coef.to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            rc = lib.rbn_inside_backward(ctypes.byref(self.desc), _ptr(self.W), _ptr(self.T), _ptr(self.prior),
+                                         _ptr(self.tokens), _ptr(self.lengths), self._ws(), self.ws_bytes,
+                                         _ptr(coef), _ptr(gW), _ptr(gT), _ptr(gP), self._stream())
+        _lib.check(rc, "rbn_inside_backward")
+        return gW, gT, gP
+
+    def export_chart(self, seq):
+        """float64 [n(n+1)/2, N] linear-space chart of sequence `seq` in TMap row order (device tensor)."""
+        lib = _lib.load()
+        n = int(self.lengths[seq])
+        out = torch.empty((n * (n + 1) // 2, self.desc.N), dtype=torch.float64, device=self.W.device)
+        with torch.cuda.device(self.W.device):
+            rc = lib.rbn_export_chart(ctypes.byref(self.desc), _ptr(self.lengths), self._ws(), self.ws_bytes,
+                                      int(seq), _ptr(out), self._stream())
+        _lib.check(rc, "rbn_export_chart")
+        return out
+
+
+class _InsideFn(torch.autograd.Function):
+    """(W, T, prior) -> log Z [B] or Z [B]; backward = the CUDA outside pass (expected rule counts)."""
+
+    @staticmethod
+    def forward(ctx, W, T, prior, tokens, lengths, linear, holder, path, chunk_items):
+        dev = _cuda_device() if not W.is_cuda else W.device
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        p = _Pass(f32(W), f32(T), f32(prior),
+                  tokens.to(device=dev, dtype=torch.int32).contiguous(),
+                  lengths.to(device=dev, dtype=torch.int32).contiguous(), path, chunk_items)
+        p.forward()
+        holder.append(p)
+        ctx.p = p
+        ctx.linear = linear
+        ctx.in_meta = [(t.dtype, t.device) for t in (W, T, prior)]
+        z64, e64 = p.zroot.double(), p.rootexp.double()
+        if linear:
+            out = torch.ldexp(z64, e64.to(torch.int32))
+        else:
+            out = torch.where(z64 > 0, torch.log(z64) + e64 * float(np.log(2.0)), torch.full_like(z64, -np.inf))
+        ctx.save_for_backward(z64, e64)
+        return out.to(W.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        z64, e64 = ctx.saved_tensors
+        g = grad_out.to(device=z64.device, dtype=torch.float64)
+        pos = z64 > 0
+        if ctx.linear:
+            # dZ/dtheta = 2^R * (what the kernel accumulates); R = rootexp + log2(zroot) for Z > 0, rootexp otherwise
+            scale = torch.where(pos, torch.ldexp(z64, e64.to(torch.int32)), torch.ldexp(torch.ones_like(z64), e64.to(torch.int32)))
+            coef = g * scale
+        else:
+            coef = torch.where(pos, g, torch.zeros_like(g))     # log Z = -inf has no gradient
+        coef = torch.nan_to_num(coef, nan=0.0, posinf=0.0, neginf=0.0)
+        gW, gT, gP = ctx.p.backward(coef)
+        outs = [t.to(device=dv, dtype=dt) for t, (dt, dv) in zip((gW, gT, gP), ctx.in_meta)]
+        return outs[0], outs[1], outs[2], None, None, None, None, None, None
+
+
+def inside_logZ(W, T, prior, tokens, lengths=None, linear=False, path=_lib.PATH_AUTO, chunk_items=0, holder=None):
+    """Functional entry: flat grammar tensors (any float dtype / device) + integer tokens -> log Z [B] (or Z)."""
+    tokens = torch.as_tensor(tokens)
+    if tokens.dim() == 2:
+        tokens = tokens[:, :, None]
+    if lengths is None:
+        lengths = torch.full((tokens.shape[0],), tokens.shape[1], dtype=torch.int32)
+    lengths = torch.as_tensor(lengths)
+    if int(lengths.min()) < 1 or int(lengths.max()) > tokens.shape[1]:
+        raise ValueError("lengths must satisfy 1 <= lengths[b] <= tokens.shape[1]")
+    return _InsideFn.apply(W, T, prior, tokens, lengths, linear, holder if holder is not None else [], path, chunk_items)
+
+
+class LazyChart:
+    """Stands in for `SequentialRBN._inside_chart` after a fused pass: the per-variable TMap list is exported from
+    the device (rbn_export_chart) the first time somebody looks at it (sequential.py:38-40, pcfg.py:30-41)."""
+
+    def __init__(self, device_pass, seq, offsets):
+        self._pass, self._seq, self._offsets = device_pass, seq, offsets
+        self._charts = None
+
+    def materialise(self):
+        if self._charts is None:
+            flat = self._pass.export_chart(self._seq).cpu().to(torch.get_default_dtype())
+            self._charts = [TMap(flat[:, lo:hi].contiguous()) for lo, hi in zip(self._offsets[:-1], self._offsets[1:])]
+        return self._charts
+
+
+class InsideEngine:
+    """Flattens a discrete SequentialRBN and runs it through librbn_b200."""
+
+    def __init__(self, model, path=_lib.PATH_AUTO, chunk_items=0):
+        self.model = model
+        self.path = path
+        self.chunk_items = chunk_items
+        self.last_pass = None
+
+    # ---- which models the fused path covers -----------------------------------------------------------------------
+    @staticmethod
+    def supports(model):
+        from . import pcfg
+        try:
+            cells = list(model.cells())
+            ok = all(isinstance(c, pcfg.DiscreteCell) and
+                     all(isinstance(t, (pcfg.DiscreteTerminalTransition, pcfg.DiscreteBinaryNonTerminalTransition))
+                         for t in c.transitions()) for c in cells)
+            return ok and isinstance(model.prior, pcfg.DiscretePrior) and len(cells) > 0
+        except (NotImplementedError, AttributeError):
+            return False
+
+    # ---- structure (host ints only) ---------------------------------------------------------------------------------
+    def _structure(self):
+        from . import pcfg
+        cells = list(self.model.cells())
+        cards = [int(c.variable.cardinality) for c in cells]
+        off = np.concatenate([[0], np.cumsum(cards)]).astype(int)
+        tsize = {}
+        for c in cells:
+            for t in c.transitions():
+                if isinstance(t, pcfg.DiscreteTerminalTransition):
+                    V = int(t.transition_probabilities.p.shape[0])
+                    tsize[int(t.term_idx)] = max(tsize.get(int(t.term_idx), 0), V)
+        n_tvars = (max(tsize) + 1) if tsize else 1
+        toff = np.concatenate([[0], np.cumsum([tsize.get(t, 0) for t in range(n_tvars)])]).astype(int)
+        return cells, off, toff
+
+    def flatten(self):
+        """(W[N,N,N], T[Vtot,N], prior[N]) as differentiable tensors on the parameters' device and dtype."""
+        from . import pcfg
+        cells, off, toff = self._structure()
+        N = int(off[-1])
+        ref = self.model.prior.structural_distribution.p
+        W = torch.zeros((N, N, N), dtype=ref.dtype, device=ref.device)
+        T = torch.zeros((max(int(toff[-1]), 1), N), dtype=ref.dtype, device=ref.device)
+        for v, cell in enumerate(cells):
+            S = cell.transition_probabilities.p
+            pv = slice(int(off[v]), int(off[v + 1]))
+            for k, tr in enumerate(cell.transitions()):
+                P = tr.transition_probabilities.p
+                if isinstance(tr, pcfg.DiscreteTerminalTransition):
+                    t = int(tr.term_idx)
+                    rows = slice(int(toff[t]), int(toff[t]) + P.shape[0])
+                    if P.shape[1] != off[v + 1] - off[v]:
+                        raise ValueError("terminal transition does not match the cardinality of its cell's variable")
+                    T[rows, pv] = T[rows, pv] + S[k][None, :] * P
+                else:
+                    li, ri = int(tr.left_idx), int(tr.right_idx)
+                    want = (off[li + 1] - off[li], off[ri + 1] - off[ri], off[v + 1] - off[v])
+                    if tuple(P.shape) != tuple(int(x) for x in want):
+                        raise ValueError(f"binary transition of shape {tuple(P.shape)} does not match the cardinalities "
+                                         f"{tuple(int(x) for x in want)} of (left, right, parent)")
+                    sl = (slice(int(off[li]), int(off[li + 1])), slice(int(off[ri]), int(off[ri + 1])), pv)
+                    W[sl] = W[sl] + S[k][None, None, :] * P
+        omega = self.model.prior.structural_distribution.p
+        prior = torch.cat([omega[v] * d.p for v, d in enumerate(self.model.prior.prior_distributions)])
+        return W, T, prior
+
+    # ---- tokens -------------------------------------------------------------------------------------------------------
+    def pack_sequences(self, sequences):
+        """Reference-style sequences (per position: list over terminal variables of int / None, or a bare int /
+        length-1 array) -> padded int32 tokens[B, L, n_tvars] (offset into the flat alphabet, -1 = None) + lengths."""
+        _, _, toff = self._structure()
+        nt = len(toff) - 1
+        B = len(sequences)
+        L = max(len(s) for s in sequences)
+        if min(len(s) for s in sequences) < 1:
+            raise ValueError("cannot parse an empty sequence")
+        tokens = -np.ones((B, L, nt), dtype=np.int32)
+        lengths = np.zeros(B, dtype=np.int32)
+        for b, seq in enumerate(sequences):
+            lengths[b] = len(seq)
+            for i, pos in enumerate(seq):
+                vals = list(pos) if isinstance(pos, (list, tuple, np.ndarray)) else [pos]
+                for t in range(min(nt, len(vals))):
+                    if vals[t] is not None:
+                        y = int(vals[t])
+                        if not 0 <= y < toff[t + 1] - toff[t]:
+                            raise IndexError(f"terminal value {y} out of range for terminal variable {t}")
+                        tokens[b, i, t] = y + toff[t]
+        return torch.from_numpy(tokens), torch.from_numpy(lengths)
+
+    def pack_tokens(self, tokens, lengths=None):
+        """Integer tokens[B, L(, n_tvars)] with per-variable values (-1 = None) -> flat-alphabet tokens."""
+        _, _, toff = self._structure()
+        tokens = torch.as_tensor(tokens)
+        if tokens.dim() == 2:
+            tokens = tokens[:, :, None]
+        shift = torch.as_tensor(toff[:-1], dtype=tokens.dtype, device=tokens.device)
+        tokens = torch.where(tokens >= 0, tokens + shift[None, None, :], tokens)
+        if lengths is None:
+            lengths = torch.full((tokens.shape[0],), tokens.shape[1], dtype=torch.int32)
+        return tokens, torch.as_tensor(lengths)
+
+    # ---- entry points --------------------------------------------------------------------------------------------------
+    def log_inside(self, tokens, lengths=None, prepacked=True):
+        if not prepacked:
+            tokens, lengths = self.pack_tokens(tokens, lengths)
+        W, T, prior = self.flatten()
+        holder = []
+        out = inside_logZ(W, T, prior, tokens, lengths, linear=False, path=self.path, chunk_items=self.chunk_items,
+                          holder=holder)
+        self.last_pass = holder[0]
+        return out
+
+    def inside_single(self, sequence):
+        """One reference-style sequence -> (Z as 0-dim float64 tensor with grad_fn, LazyChart)."""
+        tokens, lengths = self.pack_sequences([sequence])
+        W, T, prior = self.flatten()
+        holder = []
+        Z = inside_logZ(W, T, prior, tokens, lengths, linear=True, path=self.path, chunk_items=self.chunk_items,
+                        holder=holder)[0]
+        self.last_pass = holder[0]
+        _, off, _ = self._structure()
+        return Z.to(torch.float64), LazyChart(holder[0], 0, [int(o) for o in off])

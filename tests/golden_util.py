@@ -27,3 +27,29 @@ def load_cases():
                           charts=[store[f"{key}/chart{v}"] for v in range(meta["n_cells"])],
                           grads=grads, meta=meta)
     return cases
+
+
+def build_model(case, prob_rep):
+    """An rbn_b200 SequentialRBN with exactly the (normalised) brick probabilities of a golden case."""
+    from rbn_b200 import pcfg, sequential
+    cells = []
+    for c in case["cells"]:
+        trs = []
+        for tr in c["transitions"]:
+            if tr[0] == "term":
+                trs.append(pcfg.DiscreteTerminalTransition(weights=tr[1], term_idx=tr[2], prob_rep=prob_rep))
+            else:
+                trs.append(pcfg.DiscreteBinaryNonTerminalTransition(weights=tr[1], left_idx=tr[2], right_idx=tr[3],
+                                                                    prob_rep=prob_rep))
+        cells.append(pcfg.DiscreteCell(variable=pcfg.DiscreteNonTermVar(c["cardinality"]), weights=c["struct"],
+                                       transitions=trs, prob_rep=prob_rep))
+    prior = pcfg.DiscretePrior(struc_weights=case["prior"]["struct"], prior_weights=case["prior"]["dists"],
+                               prob_rep=prob_rep)
+    return sequential.SequentialRBN(cells=cells, prior=prior)
+
+
+def case_prob_rep(case):
+    from rbn_b200 import util
+    if any(k.endswith("log_p") for k in case["grads"]):
+        return util.LogProb
+    return util.Prob
