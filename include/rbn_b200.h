@@ -118,6 +118,13 @@ int rbn_export_chart(const RbnDesc* desc, const int32_t* lengths,
  * is NOT detected on device; `bad` (device int32, may be NULL) is set to the number of such groups. */
 int rbn_lognormalize(float* log_p, int64_t group_size, int64_t groups, int32_t* bad, void* stream);
 
+/* Diagnostics: D[M][N] (float32) = A * B through the same tcgen05 GEMM kernel template the chart pass uses
+ * (N must be 256, K a multiple of 64; fp16 operands).  a_mn / b_mn select the operand layout: 0 = K-major
+ * (A[M][K], B[N][K]), 1 = MN-major (A[K][M], B[K][N]).  segmented != 0 selects the segmented-accumulation variant
+ * (K chains of 4096 folded with round-to-nearest adds; DESIGN.md "accumulator truncation").  Tests only. */
+int rbn_debug_gemm(int32_t M, int32_t N, int32_t K, const void* A, const void* B, float* D, int32_t a_mn, int32_t b_mn,
+                   int32_t segmented, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

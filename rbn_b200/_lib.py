@@ -40,6 +40,8 @@ _SIGNATURES = {
                                            _P, _P, _P, _P, _P]),
     "rbn_export_chart": (ctypes.c_int, [ctypes.POINTER(RbnDesc), _P, _P, ctypes.c_size_t, ctypes.c_int32, _P, _P]),
     "rbn_lognormalize": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, _P, _P]),
+    "rbn_debug_gemm": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_int32,
+                                      ctypes.c_int32, ctypes.c_int32, _P]),
 }
 
 

@@ -23,6 +23,7 @@ int tc_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float
                float*, float*, float*, cudaStream_t);
 int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
                 const int*, const float*, float*, float*, float*, cudaStream_t);
+int debug_gemm(int, int, int, const __half*, const __half*, float*, int, int, int, cudaStream_t);
 
 static bool desc_ok(const RbnDesc* d) {
     if (!d) { set_error("desc is NULL"); return false; }
@@ -76,6 +77,8 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->wt = take(N * N * N * sizeof(__half));
         o->wk = take(N * N * N * sizeof(__half));
         o->wexp = take(N * sizeof(int));
+        o->wscale = take(N * sizeof(float));
+        o->wbits = take(N * sizeof(int));
         o->y = take(chunk * N * N * sizeof(__half));
         o->gy = take(chunk * N * N * sizeof(__half));
         o->item_e = take(chunk * sizeof(int));
@@ -170,6 +173,15 @@ int rbn_lognormalize(float* log_p, int64_t group_size, int64_t groups, int32_t* 
         return RBN_E_BADARG;
     }
     return lognormalize(log_p, group_size, groups, bad, (cudaStream_t)stream);
+}
+
+int rbn_debug_gemm(int32_t M, int32_t N, int32_t K, const void* A, const void* B, float* D, int32_t a_mn, int32_t b_mn,
+                   int32_t segmented, void* stream) {
+    if (!A || !B || !D || M < 1 || N < 1 || K < 1) {
+        set_error("rbn_debug_gemm: bad argument");
+        return RBN_E_BADARG;
+    }
+    return debug_gemm(M, N, K, (const __half*)A, (const __half*)B, D, a_mn, b_mn, segmented, (cudaStream_t)stream);
 }
 
 }  // extern "C"

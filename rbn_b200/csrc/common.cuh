@@ -51,7 +51,9 @@ struct WsLayout {
     size_t rc;          // half [B][L+1][Lp][N]  end-major operand copy:   cell (j, k) at row (b*(L+1) + k)*Lp + j
     size_t wt;          // half [N][N*N]         Wt[a][b*N+c] = W[b][c][a] * 2^-wexp[a]
     size_t wk;          // half [N*N][N]         Wk[b*N+c][a] = W[b][c][a] * 2^-wexp[a]
-    size_t wexp;        // int32 [N]
+    size_t wexp;        // int32 [N]   W = W16 * 2^wexp[a]
+    size_t wscale;      // float [N]   2^wexp[a]
+    size_t wbits;       // int32 [N]   scratch: float bits of max_{b,c} W[b][c][a]
     size_t y;           // half [chunk][N*N]
     size_t gy;          // half [chunk][N*N]
     size_t item_e;      // int32 [chunk]         E_m = max_j (e_ij + e_jk)

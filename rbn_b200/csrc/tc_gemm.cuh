@@ -1,0 +1,231 @@
+// Generic warp-specialised tcgen05 GEMM used by the rule contraction (K2), its two adjoints (K3, K4) and the
+// diagnostics entry point.  D[128 x BLOCK_N] tiles, fp16 operands staged by TMA (128-byte swizzle) into a
+// STAGES-deep mbarrier ring, fp32 accumulators double-buffered in tensor memory, epilogue in 4 warps.
+//   warp 0 : TMA producer (one lane)        warp 1 : tcgen05.mma issuer (one lane)
+//   warp 2 : TMEM allocator                 warps 4-7 : epilogue (TMEM -> registers -> global), one row per thread
+// Operand "major-ness":
+//   K-major  X[rows][K]  : smem tile = rows x 64 halves, 128 B per row, 8-row swizzle groups of 1024 B
+//   MN-major X[K][rows]  : smem tile = (rows/64) atoms, each 64 k-rows x 128 B (64 row-elements), atoms 8192 B apart
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace rbn {
+
+static constexpr int kBM = 128;      // tile rows (TMEM lanes)
+static constexpr int kBK = 64;       // halves per k-block = one 128-byte swizzle span
+
+struct GemmShape {
+    int m_tiles, n_tiles, k_blocks;
+};
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = kBM * kBK * 2;
+    static constexpr int B_BYTES = BLOCK_N * kBK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // + barriers + alignment slack
+};
+
+__host__ __device__ constexpr uint32_t tmem_cols_pow2(int c) {
+    return c <= 32 ? 32u : c <= 64 ? 64u : c <= 128 ? 128u : c <= 256 ? 256u : 512u;
+}
+
+// SEG > 0: segmented accumulation.  tcgen05.mma adds into its fp32 accumulator with truncation; over a K-chain of
+// 65536 that is a systematic -3.9e-4 relative bias (measured).  With SEG k-blocks per segment, segment 0
+// accumulates into accumulator B, every later segment into accumulator A (fresh), and the epilogue warps fold A
+// into B with round-to-nearest adds (tcgen05.ld / tcgen05.st) between segments; the last segment is folded in the
+// final epilogue read.  SEG == 0: plain accumulation, the two accumulators double-buffer consecutive tiles.
+template <bool A_MN, bool B_MN, int BLOCK_N, int STAGES, int SEG, class Epi>
+__global__ void __launch_bounds__(256, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape, Epi epi) {
+    using S = GemmSmem<BLOCK_N, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* segfull = tempty + 2;
+    uint64_t* segfree = segfull + 1;
+    uint32_t* tmem_slot = (uint32_t*)(segfree + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * BLOCK_N);
+    constexpr int SEGD = SEG > 0 ? SEG : 1;   // divisor that is never zero (SEG == 0 branches are dead)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], 128);
+        }
+        ptx::mbar_init(segfull, 1);
+        ptx::mbar_init(segfree, 128);
+        ptx::fence_barrier_init();
+        ptx::tma_prefetch_desc(&tmA);
+        ptx::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = shape.m_tiles * shape.n_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile / shape.m_tiles, mt = tile - nt * shape.m_tiles;
+                for (int kb = 0; kb < shape.k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * S::STAGE_BYTES;
+                    uint8_t* sB = sA + S::A_BYTES;
+                    ptx::mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+                    if (!A_MN) {
+                        ptx::tma_load_2d(sA, &tmA, &full[stage], kb * kBK, mt * kBM);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < kBM / 64; ++a)
+                            ptx::tma_load_2d(sA + a * 8192, &tmA, &full[stage], mt * kBM + a * 64, kb * kBK);
+                    }
+                    if (!B_MN) {
+                        ptx::tma_load_2d(sB, &tmB, &full[stage], kb * kBK, nt * BLOCK_N);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BLOCK_N / 64; ++a)
+                            ptx::tma_load_2d(sB + a * 8192, &tmB, &full[stage], nt * BLOCK_N + a * 64, kb * kBK);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, BLOCK_N, A_MN, B_MN, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            uint32_t flush_waits = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < shape.k_blocks; ++kb) {
+                    uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                    bool seg_start = (kb == 0);
+                    if (SEG > 0) {
+                        const int seg = kb / SEGD;
+                        seg_start = (kb - seg * SEGD) == 0;
+                        d_tmem = tmem_base + (seg == 0 ? 0 : BLOCK_N);
+                        if (seg_start && seg >= 2) {           // accumulator A must have been folded into B
+                            ptx::mbar_wait(segfree, flush_waits & 1);
+                            ++flush_waits;
+                            ptx::tc_fence_after();
+                        }
+                    }
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sA = ptx::smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint32_t sB = sA + S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t ad = A_MN ? ptx::make_smem_desc(sA + k * 2048, 8192, 1024)
+                                                 : ptx::make_smem_desc(sA + k * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? ptx::make_smem_desc(sB + k * 2048, 8192, 1024)
+                                                 : ptx::make_smem_desc(sB + k * 32, 16, 1024);
+                        ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (uint32_t)(!(seg_start && k == 0)));
+                    }
+                    ptx::mma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (SEG > 0) {
+                        const int seg = kb / SEGD;
+                        const bool seg_end = ((kb + 1) % SEGD == 0) && (kb + 1 < shape.k_blocks);
+                        if (seg_end && seg >= 1) ptx::mma_commit(segfull);   // a non-final segment in A: fold it
+                    }
+                }
+                ptx::mma_commit(&tfull[acc]);
+                if (SEG == 0) {
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                } else {
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t flushes = 0;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile / shape.m_tiles, mt = tile - nt * shape.m_tiles;
+            uint32_t t0 = tmem_base + acc * BLOCK_N + lane_off, t1 = 0;
+            if (SEG > 0) {
+                const int nseg = (shape.k_blocks + SEGD - 1) / SEGD;
+                t0 = tmem_base + lane_off;
+                const uint32_t tA = tmem_base + BLOCK_N + lane_off;
+                for (int sg = 1; sg + 1 < nseg; ++sg) {       // fold every non-final segment held in A into B
+                    ptx::mbar_wait(segfull, flushes & 1);
+                    ++flushes;
+                    ptx::tc_fence_after();
+                    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                        float v[32];
+                        ptx::tmem_ld32_sum(t0, tA, c0, v);
+                        ptx::tmem_st32(t0 + c0, v);
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(segfree);
+                }
+                if (nseg >= 2) t1 = tA;
+            }
+            ptx::mbar_wait(&tfull[acc], acc_phase);
+            ptx::tc_fence_after();
+            epi(mt, nt, q * 32 + lane, t0, t1);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty[acc]);
+            if (SEG == 0) {
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            } else {
+                acc_phase ^= 1;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- host: TMA descriptor encoding (driver entry point fetched at run time; libcuda is never linked) --------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn();
+
+// 2-D fp16 tensor [outer][inner] (inner contiguous), box = {64, box_outer}, 128-byte swizzle, OOB reads give zeros.
+int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_outer);
+
+template <bool A_MN, bool B_MN, int BLOCK_N, int STAGES, int SEG, class Epi>
+int launch_tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape shape, const Epi& epi, int num_sms,
+                   cudaStream_t st, const char* name) {
+    using S = GemmSmem<BLOCK_N, STAGES>;
+    auto kern = k_tc_gemm<A_MN, B_MN, BLOCK_N, STAGES, SEG, Epi>;
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    int tiles = shape.m_tiles * shape.n_tiles;
+    int grid = tiles < num_sms ? tiles : num_sms;
+    if (grid < 1) return RBN_OK;
+    kern<<<grid, 256, S::TOTAL, st>>>(tmA, tmB, shape, epi);
+    RBN_LAUNCH_CHECK(name);
+    return RBN_OK;
+}
+
+}  // namespace rbn

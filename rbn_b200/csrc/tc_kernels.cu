@@ -1,8 +1,814 @@
-// placeholder until the tcgen05 path lands (next commit)
+// Span-diagonal tensor-core path (tcgen05 + TMEM + TMA) of the inside and outside passes.
+//
+// Per span diagonal (width w), spans ("items", m = b * (L-w+1) + i) are processed in chunks:
+//   inside :  K1 split-sum    Y[m][b,c]  = sum_j c_j * Lhat_j[b] * Rhat_j[c]          (per-item GEMM, K = w-1)
+//             K2 rule GEMM    out[m][a]  = sum_{b,c} Y[m][b,c] * Wt[a][b,c]           (items x N^2 x N) + max-shift epilogue
+//   outside:  K1 recompute Y, prepG (scaled upstream gradient), then
+//             K3 gY[m][b,c]   = sum_a Ghat[m][a] * Wk[b,c][a]                        (items x N x N^2)
+//             K4 gW[b,c][a]  += sum_m Y[m][b,c] * Gabs[m][a]                         (N^2 x items x N) expected rule counts
+//             K5 alpha[i,j][b]+= c_j 2^eG sum_c gY[m][b,c] Rhat_j[c]; alpha[j,k][c] += c_j 2^eG sum_b gY[m][b,c] Lhat_j[b]
+// Reference arithmetic being replaced: /root/reference/rbnet/pcfg.py:305-314 (per-split contraction), 387-398
+// (structural mixture) and the autograd traversal of sequential.py:36.
+// Scaling: every chart cell is mantissa (max in [0.5,1)) x 2^exp; operands are fp16 copies of the mantissas in a
+// start-major (LC) and an end-major (RC) layout; W is pre-scaled per parent (wexp) so its fp16 copy keeps 11 bits.
 #include "common.cuh"
+#include "tc_gemm.cuh"
+#include <limits.h>
+#include <mutex>
+
 namespace rbn {
-int tc_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*, const int*,
-               float*, float*, float*, cudaStream_t) { set_error("tensor-core path not built"); return RBN_E_UNSUPPORTED; }
-int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
-                const int*, const float*, float*, float*, float*, cudaStream_t) { set_error("tensor-core path not built"); return RBN_E_UNSUPPORTED; }
+
+// kernels shared with the CUDA-core path (same chart layout)
+__global__ void k_emission(int, int, int, const float*, const int*, const int*, float*, int*);
+__global__ void k_root(int, int, const float*, const int*, const float*, const int*, float*, float*, float*, float*, int*);
+__global__ void k_outside_seed(int, int, const float*, const int*, const float*, const float*, const float*, float*, float*);
+__global__ void k_emission_bwd(int, int, int, const int*, const int*, const int*, const float*, float*);
+
+// ---- TMA descriptor encoding ------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    });
+    return fn;
 }
+
+int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_outer) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return RBN_E_CUDA;
+    }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {64, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu stride=%llu box_outer=%u", (int)r,
+                  (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_outer);
+        return RBN_E_CUDA;
+    }
+    return RBN_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// =======================================================================================================================
+// epilogues of the generic GEMM
+// =======================================================================================================================
+struct EpiStoreF32 {   // diagnostics: D -> float [M][N]
+    float* D;
+    int M, N, block_n;
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1) const {
+        int r = mt * kBM + row;
+        for (int c0 = 0; c0 < block_n; c0 += 32) {
+            float v[32];
+            ptx::tmem_ld32_sum(t0, t1, c0, v);
+            if (r < M)
+                for (int j = 0; j < 32; ++j) {
+                    int c = nt * block_n + c0 + j;
+                    if (c < N) D[(size_t)r * N + c] = v[j];
+                }
+        }
+    }
+};
+
+// K2: out[m][a] -> chart mantissas (fp32), exponents, fp16 operand copies
+struct EpiRule {
+    int N, L, Lp, w, m0, cnt;
+    const int* lengths;
+    const float* wscale; // W = Wt * wscale[a], wscale[a] = 2^wexp[a]
+    const int* item_e;   // E_m
+    float* cv;
+    int* ce;
+    __half* lc;
+    __half* rc;
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1) const {
+        (void)nt;
+        const int t = mt * kBM + row;
+        const int nI = L - w + 1;
+        const int m = m0 + t;
+        const int b = m / nI, i = m - b * nI, k = i + w;
+        const bool valid = (t < cnt) && (k <= lengths[t < cnt ? b : 0]);
+        float mx = 0.f;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            ptx::tmem_ld32_sum(t0, t1, c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j] * wscale[c0 + j]);
+        }
+        int e_new = 0;
+        if (mx > 0.f) frexpf(mx, &e_new);
+        const float rs = ldexpf(1.0f, -e_new);
+        const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
+        float* cvp = cv + cell * N;
+        __half* lcp = lc + ((size_t)((size_t)b * L + i) * Lp + k) * N;
+        __half* rcp = rc + ((size_t)((size_t)b * (L + 1) + k) * Lp + i) * N;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            ptx::tmem_ld32_sum(t0, t1, c0, v);
+            if (valid) {
+                __align__(16) __half h[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = v[j] * wscale[c0 + j] * rs;
+                    h[j] = __float2half_rn(v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cvp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    *reinterpret_cast<uint4*>(lcp + c0 + j) = *reinterpret_cast<const uint4*>(h + j);
+                    *reinterpret_cast<uint4*>(rcp + c0 + j) = *reinterpret_cast<const uint4*>(h + j);
+                }
+            }
+        }
+        if (valid) ce[cell] = item_e[t] + e_new;
+    }
+};
+
+// K3: gY (fp16) [items][N*N]
+struct EpiGY {
+    __half* gy;
+    int cnt;
+    size_t ld;   // N*N
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1) const {
+        const int t = mt * kBM + row;
+        __half* dst = gy + (size_t)t * ld + (size_t)nt * 256;
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+            float v[32];
+            ptx::tmem_ld32_sum(t0, t1, c0, v);
+            if (t < cnt) {
+                __align__(16) __half h[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) h[j] = __float2half_rn(v[j]);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dst + c0 + j) = *reinterpret_cast<const uint4*>(h + j);
+            }
+        }
+    }
+};
+
+// K4: gW[(b,c)][a] += D * 2^kGabsShift
+static constexpr int kGabsShift = 8;
+static constexpr int kSegBlocks = 64;   // k-blocks (of 64) per accumulation segment: K chain of 4096 -> bias ~2e-5
+struct EpiCounts {
+    float* gW;
+    int N;
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1) const {
+        (void)nt;
+        float* dst = gW + ((size_t)mt * kBM + row) * N;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            ptx::tmem_ld32_sum(t0, t1, c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 o = *reinterpret_cast<float4*>(dst + c0 + j);
+                o.x += ldexpf(v[j], kGabsShift);
+                o.y += ldexpf(v[j + 1], kGabsShift);
+                o.z += ldexpf(v[j + 2], kGabsShift);
+                o.w += ldexpf(v[j + 3], kGabsShift);
+                *reinterpret_cast<float4*>(dst + c0 + j) = o;
+            }
+        }
+    }
+};
+
+// =======================================================================================================================
+// K1: split-sum, one span per CTA iteration; operands loaded by 4 producer warps (scale folding + swizzled store)
+// =======================================================================================================================
+// smem operand tile, MN-major: atom a (64 nonterminals) = Kpad rows x 128 B; row r holds splits' values, 16-byte chunk
+// ch of row r is stored at chunk position ch ^ (r & 7)  (the 128-byte swizzle the UMMA descriptor expects)
+static constexpr int kK1Threads = 288;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer / TMEM owner
+
+__global__ void __launch_bounds__(kK1Threads, 1)
+k_tc_splitsum(int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths,
+              const int* __restrict__ ce, const __half* __restrict__ lc, const __half* __restrict__ rc,
+              __half* __restrict__ Y, int* __restrict__ item_e) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int Kpad = ((w - 1) + 15) & ~15;
+    const int halves = (N + 127) / 128;
+    const int a_atoms = halves * 2;            // A operand covers halves * 128 rows (zero beyond N)
+    const int b_atoms = N / 64;
+    const uint32_t atom_bytes = (uint32_t)Kpad * 128;
+    uint8_t* sL = smem;
+    uint8_t* sR = sL + (size_t)a_atoms * atom_bytes;
+    uint8_t* tail = sR + (size_t)b_atoms * atom_bytes;
+    uint64_t* sm_full = (uint64_t*)tail;
+    uint64_t* sm_empty = sm_full + 1;
+    uint64_t* acc_full = sm_empty + 1;     // [2]
+    uint64_t* acc_empty = acc_full + 2;    // [2]
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    int* red = (int*)(tmem_slot + 1);      // [4]
+    float* cj = (float*)(red + 4);         // [128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t TMEM_COLS = tmem_cols_pow2(halves * N);
+    const int nI = L - w + 1;
+    const size_t C = cells_per_seq(L);
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(sm_full, 128);
+        ptx::mbar_init(sm_empty, 1);
+        for (int h = 0; h < 2; ++h) {
+            ptx::mbar_init(&acc_full[h], 1);
+            ptx::mbar_init(&acc_empty[h], 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    // zero the A atoms that lie beyond N (N = 64 or 192): never written by the producers
+    for (uint32_t off = (uint32_t)b_atoms * atom_bytes + threadIdx.x * 16; off < (uint32_t)a_atoms * atom_bytes; off += kK1Threads * 16)
+        *reinterpret_cast<uint4*>(sL + off) = make_uint4(0, 0, 0, 0);
+    if (warp == 8) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    uint32_t it_phase = 0;          // phase of sm_full / sm_empty / acc_* (one completion per processed item)
+    for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+        const int m = m0 + t;
+        const int b = m / nI, i = m - b * nI, k = i + w;
+        if (k > lengths[b]) continue;                       // uniform across the CTA
+        if (warp >= 4 && warp < 8) {
+            // ---------------- producers ----------------
+            const int p = threadIdx.x - 128;                // 0..127
+            const int* ce_seq = ce + (size_t)b * C;
+            int s = INT_MIN;
+            if (p < w - 1) {
+                const int u = p + 1;
+                s = ce_seq[cell_off(u, L) + i] + ce_seq[cell_off(w - u, L) + i + u];
+            }
+            int mxs = s;
+            for (int o = 16; o > 0; o >>= 1) mxs = max(mxs, __shfl_xor_sync(0xffffffffu, mxs, o));
+            ptx::mbar_wait(sm_empty, it_phase ^ 1);          // previous item's MMAs have consumed the tiles (and cj/red)
+            if (lane == 0) red[warp - 4] = mxs;
+            ptx::named_bar_sync(1, 128);
+            const int E = max(max(red[0], red[1]), max(red[2], red[3]));
+            if (p < w - 1) cj[p] = ldexpf(1.0f, max(s - E, -60));
+            if (p == 0) item_e[t] = E;
+            ptx::named_bar_sync(1, 128);
+            const __half* lrow0 = lc + ((size_t)((size_t)b * L + i) * Lp + (i + 1)) * N;
+            const __half* rrow0 = rc + ((size_t)((size_t)b * (L + 1) + k) * Lp + (i + 1)) * N;
+            for (int r = warp - 4; r < Kpad; r += 4) {
+                const bool live = r < w - 1;
+                const __half2 sc = __float2half2_rn(live ? cj[r] : 0.f);
+                for (int c16 = lane; c16 < N / 8; c16 += 32) {
+                    uint4 lv = make_uint4(0, 0, 0, 0), rv = make_uint4(0, 0, 0, 0);
+                    if (live) {
+                        lv = *reinterpret_cast<const uint4*>(lrow0 + (size_t)r * N + c16 * 8);
+                        rv = *reinterpret_cast<const uint4*>(rrow0 + (size_t)r * N + c16 * 8);
+                        __half2* lh = reinterpret_cast<__half2*>(&lv);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) lh[q] = __hmul2(lh[q], sc);
+                    }
+                    const uint32_t off = (uint32_t)(c16 >> 3) * atom_bytes + (uint32_t)r * 128 + (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
+                    *reinterpret_cast<uint4*>(sL + off) = lv;
+                    *reinterpret_cast<uint4*>(sR + off) = rv;
+                }
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(sm_full);
+        } else if (warp == 8) {
+            // ---------------- MMA issuer ----------------
+            if (lane == 0) {
+                const uint32_t idesc = ptx::make_idesc_f16(128, N, true, true, 0);
+                ptx::mbar_wait(sm_full, it_phase);
+                ptx::tc_fence_after();
+                const uint32_t aL = ptx::smem_u32(sL), aR = ptx::smem_u32(sR);
+                for (int h = 0; h < halves; ++h) {
+                    ptx::mbar_wait(&acc_empty[h], it_phase ^ 1);
+                    ptx::tc_fence_after();
+                    for (int k16 = 0; k16 < Kpad / 16; ++k16) {
+                        const uint64_t ad = ptx::make_smem_desc(aL + (uint32_t)(h * 2) * atom_bytes + k16 * 2048, atom_bytes, 1024);
+                        const uint64_t bd = ptx::make_smem_desc(aR + k16 * 2048, atom_bytes, 1024);
+                        ptx::mma_f16_ss(tmem_base + h * N, ad, bd, idesc, (uint32_t)(k16 != 0));
+                    }
+                    ptx::mma_commit(&acc_full[h]);
+                }
+                ptx::mma_commit(sm_empty);
+            }
+        } else {
+            // ---------------- epilogue: TMEM -> fp16 -> Y[t][b][c] ----------------
+            for (int h = 0; h < halves; ++h) {
+                ptx::mbar_wait(&acc_full[h], it_phase);
+                ptx::tc_fence_after();
+                const int brow = h * 128 + warp * 32 + lane;
+                const uint32_t taddr = tmem_base + h * N + ((uint32_t)(warp * 32) << 16);
+                __half* dst = Y + ((size_t)t * N + brow) * N;
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    float v[32];
+                    ptx::tmem_ld32(taddr + c0, v);
+                    ptx::tmem_ld_wait();
+                    if (brow < N) {
+                        __align__(16) __half hv[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) hv[j] = __float2half_rn(v[j]);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dst + c0 + j) = *reinterpret_cast<const uint4*>(hv + j);
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&acc_empty[h]);
+            }
+        }
+        it_phase ^= 1;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+static size_t k1_smem_bytes(int N, int w) {
+    int Kpad = ((w - 1) + 15) & ~15;
+    int halves = (N + 127) / 128;
+    return (size_t)(halves * 2 + N / 64) * Kpad * 128 + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
+}
+
+// =======================================================================================================================
+// K5: child gradients, one span per CTA iteration, TMA-fed
+// =======================================================================================================================
+static constexpr int kK5Stages = 4;
+static constexpr int kK5StageBytes = 32768;   // A 16 KB + B 16 KB
+
+__global__ void __launch_bounds__(256, 1)
+k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)][c], box {64,128}: A of the left-child GEMM
+               const __grid_constant__ CUtensorMap tmGYm,   // same array, box {64,64}: MN-major A of the right-child GEMM
+               const __grid_constant__ CUtensorMap tmRC,    // RC rows, box {64, Npad}
+               const __grid_constant__ CUtensorMap tmLC,    // LC rows, box {64, Npad}
+               int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths,
+               const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp,
+               float* __restrict__ alpha) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + kK5Stages * kK5StageBytes);
+    uint64_t* empty = full + kK5Stages;
+    uint64_t* afull = empty + kK5Stages;     // [4]
+    uint64_t* aempty = afull + 4;            // [4]
+    uint32_t* tmem_slot = (uint32_t*)(aempty + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Npad = ((w - 1) + 15) & ~15;
+    const int halves = (N + 127) / 128;
+    const int units = 2 * halves;            // unit = kind * halves + h ; kind 0 = left-child, 1 = right-child gradient
+    const int kblocks = N / 64;
+    const int nI = L - w + 1;
+    const size_t C = cells_per_seq(L);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kK5Stages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 4; ++s) {
+            ptx::mbar_init(&afull[s], 1);
+            ptx::mbar_init(&aempty[s], 128);
+        }
+        ptx::fence_barrier_init();
+        ptx::tma_prefetch_desc(&tmGYk);
+        ptx::tma_prefetch_desc(&tmGYm);
+        ptx::tma_prefetch_desc(&tmRC);
+        ptx::tma_prefetch_desc(&tmLC);
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t b_bytes = (uint32_t)Npad * 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+                const int m = m0 + t;
+                const int b = m / nI, i = m - b * nI, k = i + w;
+                if (k > lengths[b]) continue;
+                const int rc_row = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
+                const int lc_row = (int)(((size_t)b * L + i) * Lp + (i + 1));
+                for (int u = 0; u < units; ++u) {
+                    const int kind = u / halves, h = u - kind * halves;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        ptx::mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * kK5StageBytes;
+                        uint8_t* sB = sA + 16384;
+                        ptx::mbar_expect_tx(&full[stage], 16384 + b_bytes);
+                        if (kind == 0) {
+                            ptx::tma_load_2d(sA, &tmGYk, &full[stage], kb * 64, t * N + h * 128);
+                            ptx::tma_load_2d(sB, &tmRC, &full[stage], kb * 64, rc_row);
+                        } else {
+                            ptx::tma_load_2d(sA, &tmGYm, &full[stage], h * 128, t * N + kb * 64);
+                            ptx::tma_load_2d(sA + 8192, &tmGYm, &full[stage], h * 128 + 64, t * N + kb * 64);
+                            ptx::tma_load_2d(sB, &tmLC, &full[stage], kb * 64, lc_row);
+                        }
+                        if (++stage == kK5Stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_k = ptx::make_idesc_f16(128, Npad, false, false, 0);
+            const uint32_t idesc_m = ptx::make_idesc_f16(128, Npad, true, false, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t slot_phase = 0;      // all four slots complete once per processed item (unused slots are skipped)
+            for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+                const int m = m0 + t;
+                const int b = m / nI, i = m - b * nI;
+                if (i + w > lengths[b]) continue;
+                for (int u = 0; u < units; ++u) {
+                    const int kind = u / halves;
+                    ptx::mbar_wait(&aempty[u], slot_phase ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + u * 128;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        ptx::mbar_wait(&full[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t sA = ptx::smem_u32(smem + stage * kK5StageBytes);
+                        const uint32_t sB = sA + 16384;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t ad = kind ? ptx::make_smem_desc(sA + kk * 2048, 8192, 1024)
+                                                     : ptx::make_smem_desc(sA + kk * 32, 16, 1024);
+                            const uint64_t bd = ptx::make_smem_desc(sB + kk * 32, 16, 1024);
+                            ptx::mma_f16_ss(d_tmem, ad, bd, kind ? idesc_m : idesc_k, (uint32_t)((kb | kk) != 0));
+                        }
+                        ptx::mma_commit(&empty[stage]);
+                        if (++stage == kK5Stages) { stage = 0; phase ^= 1; }
+                    }
+                    ptx::mma_commit(&afull[u]);
+                }
+                slot_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        uint32_t slot_phase = 0;
+        for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+            const int m = m0 + t;
+            const int b = m / nI, i = m - b * nI, k = i + w;
+            if (k > lengths[b]) continue;
+            const int* ce_seq = ce + (size_t)b * C;
+            float* al_seq = alpha + (size_t)b * C * N;
+            const int E = item_e[t];
+            const int eg = gexp[t];
+            for (int u = 0; u < units; ++u) {
+                const int kind = u / halves, h = u - kind * halves;
+                ptx::mbar_wait(&afull[u], slot_phase);
+                ptx::tc_fence_after();
+                const int x = h * 128 + q * 32 + lane;          // nonterminal index of this thread's row
+                const uint32_t taddr = tmem_base + u * 128 + ((uint32_t)(q * 32) << 16);
+                for (int c0 = 0; c0 < Npad; c0 += 16) {
+                    float v[16];
+                    ptx::tmem_ld16(taddr + c0, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int us = c0 + j + 1;               // left width of this split
+                        if (us < w && x < N) {
+                            const int lcell = cell_off(us, L) + i, rcell = cell_off(w - us, L) + i + us;
+                            const int sft = ce_seq[lcell] + ce_seq[rcell] - E + eg;
+                            const float g = ldexpf(v[j], max(sft, -120));
+                            if (g != 0.f) atomicAdd(al_seq + (size_t)(kind ? rcell : lcell) * N + x, g);
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&aempty[u]);
+            }
+            slot_phase ^= 1;
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// =======================================================================================================================
+// element-wise helpers of the tensor-core path
+// =======================================================================================================================
+// per-parent exponent of max_{b,c} W[b][c][a]
+__global__ void k_w_colmax(int N, const float* __restrict__ W, int* __restrict__ wmax_bits) {
+    // grid over (b,c) rows in slabs; thread a
+    size_t rows = (size_t)N * N;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        float mx = 0.f;
+        for (size_t r = blockIdx.x; r < rows; r += gridDim.x) mx = fmaxf(mx, W[r * N + a]);
+        atomicMax(&wmax_bits[a], __float_as_int(mx));     // non-negative floats order like ints
+    }
+}
+__global__ void k_w_exp(int N, const int* __restrict__ wmax_bits, int* __restrict__ wexp, float* __restrict__ wscale) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= N) return;
+    float mx = __int_as_float(wmax_bits[a]);
+    int e = 0;
+    if (mx > 0.f) frexpf(mx, &e);
+    wexp[a] = e;
+    wscale[a] = ldexpf(1.0f, e);
+}
+// Wk[(b,c)][a] = W * 2^-wexp[a]  and its transpose Wt[a][(b,c)]  (32x32 tiles through shared memory)
+__global__ void k_w_copies(int N, const float* __restrict__ W, const int* __restrict__ wexp, __half* __restrict__ wk,
+                           __half* __restrict__ wt) {
+    __shared__ __half tile[32][33];
+    size_t rows = (size_t)N * N;
+    size_t r0 = (size_t)blockIdx.x * 32;
+    int a0 = blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        size_t r = r0 + rr;
+        int a = a0 + threadIdx.x;
+        __half h = __float2half_rn(ldexpf(W[r * N + a], -wexp[a]));
+        wk[r * N + a] = h;
+        tile[rr][threadIdx.x] = h;
+    }
+    __syncthreads();
+    for (int aa = threadIdx.y; aa < 32; aa += blockDim.y) wt[(size_t)(a0 + aa) * rows + r0 + threadIdx.x] = tile[threadIdx.x][aa];
+}
+// fp16 operand copies of the width-1 cells
+__global__ void k_copy_width1(int N, int L, int Lp, const int* __restrict__ lengths, const float* __restrict__ cv,
+                              __half* __restrict__ lc, __half* __restrict__ rc) {
+    int b = blockIdx.x / L, i = blockIdx.x % L;
+    if (i >= lengths[b]) return;
+    const float* src = cv + ((size_t)b * cells_per_seq(L) + i) * N;
+    __half* l = lc + ((size_t)((size_t)b * L + i) * Lp + (i + 1)) * N;
+    __half* r = rc + ((size_t)((size_t)b * (L + 1) + (i + 1)) * Lp + i) * N;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        __half h = __float2half_rn(src[a]);
+        l[a] = h;
+        r[a] = h;
+    }
+}
+// upstream gradient of one chunk:  G = alpha * 2^-e_new ;  Ghat = G * 2^wexp[a] normalised per item ; Gabs = G * 2^-8
+__global__ void k_prep_g(int N, int L, int w, int m0, int cnt, const int* __restrict__ lengths, const int* __restrict__ ce,
+                         const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
+                         __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
+    __shared__ float red[32];
+    const int t = blockIdx.x;
+    const int nI = L - w + 1;
+    const int m = m0 + t;
+    const int b = m / nI, i = m - b * nI;
+    const bool valid = (t < cnt) && (i + w <= lengths[b]);
+    float g = 0.f, gs = 0.f;
+    const int a = threadIdx.x;     // blockDim.x == N (<= 256)
+    if (valid) {
+        const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
+        const int e_new = ce[cell] - item_e[t];
+        g = ldexpf(alpha[cell * N + a], -e_new);
+        gs = ldexpf(g, wexp[a]);
+    }
+    float mx = fabsf(gs);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int q = 1; q < (blockDim.x >> 5); ++q) mx = fmaxf(mx, red[q]);
+    int eg = 0;
+    if (mx > 0.f) frexpf(mx, &eg);
+    ghat[(size_t)t * N + a] = __float2half_rn(ldexpf(gs, -eg));
+    float ga = ldexpf(g, -kGabsShift);
+    ga = fminf(fmaxf(ga, -65504.f), 65504.f);
+    gabs[(size_t)t * N + a] = __float2half_rn(ga);
+    if (a == 0) gexp[t] = eg;
+}
+
+// =======================================================================================================================
+// drivers
+// =======================================================================================================================
+struct TcCtx {
+    const RbnDesc* d;
+    const WsLayout* ws;
+    char* base;
+    int N, L, B, Lp, chunk, sms;
+    float* cv;
+    int* ce;
+    float* alpha;
+    __half *lc, *rc, *wt, *wk, *y, *gy, *ghat, *gabs;
+    int *wexp, *wbits, *item_e, *gexp;
+    float* wscale;
+    const int* lengths;
+    cudaStream_t st;
+};
+
+static void fill_ctx(TcCtx& c, const RbnDesc* d, const WsLayout& ws, char* base, const int* lengths, cudaStream_t st) {
+    c.d = d; c.ws = &ws; c.base = base; c.N = d->N; c.L = d->L; c.B = d->B; c.Lp = ws.Lp; c.chunk = ws.chunk;
+    c.sms = sm_count();
+    c.cv = (float*)(base + ws.chart_val); c.ce = (int*)(base + ws.chart_exp); c.alpha = (float*)(base + ws.alpha);
+    c.lc = (__half*)(base + ws.lc); c.rc = (__half*)(base + ws.rc); c.wt = (__half*)(base + ws.wt);
+    c.wk = (__half*)(base + ws.wk); c.y = (__half*)(base + ws.y); c.gy = (__half*)(base + ws.gy);
+    c.ghat = (__half*)(base + ws.ghat); c.gabs = (__half*)(base + ws.gabs);
+    c.wexp = (int*)(base + ws.wexp); c.wbits = (int*)(base + ws.wbits); c.wscale = (float*)(base + ws.wscale); c.item_e = (int*)(base + ws.item_e); c.gexp = (int*)(base + ws.gexp);
+    c.lengths = lengths; c.st = st;
+}
+
+static int prep_weights(TcCtx& c, const float* W) {
+    int N = c.N;
+    int* bits = c.wbits;
+    RBN_CUDA_CHECK(cudaMemsetAsync(bits, 0, (size_t)N * sizeof(int), c.st));
+    k_w_colmax<<<256, 256, 0, c.st>>>(N, W, bits);
+    RBN_LAUNCH_CHECK("k_w_colmax");
+    k_w_exp<<<(N + 127) / 128, 128, 0, c.st>>>(N, bits, c.wexp, c.wscale);
+    RBN_LAUNCH_CHECK("k_w_exp");
+    dim3 grid((unsigned)((size_t)N * N / 32), (unsigned)(N / 32));
+    k_w_copies<<<grid, dim3(32, 8), 0, c.st>>>(N, W, c.wexp, c.wk, c.wt);
+    RBN_LAUNCH_CHECK("k_w_copies");
+    return RBN_OK;
+}
+
+static int launch_k1(TcCtx& c, int w, int m0, int cnt) {
+    size_t smem = k1_smem_bytes(c.N, w);
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_splitsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = cnt < 2 * c.sms ? cnt : 2 * c.sms;
+    if (smem > 110 * 1024 || grid > c.sms) grid = cnt < c.sms ? cnt : c.sms;
+    k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.lc, c.rc, c.y, c.item_e);
+    RBN_LAUNCH_CHECK("k_tc_splitsum");
+    return RBN_OK;
+}
+
+template <int BN>
+static int launch_k2_bn(TcCtx& c, int w, int m0, int cnt) {
+    size_t NN = (size_t)c.N * c.N;
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_2d(&tmA, c.y, NN, (uint64_t)cnt, NN * 2, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmB, c.wt, NN, (uint64_t)c.N, NN * 2, BN);
+    if (rc) return rc;
+    EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.item_e, c.cv, c.ce, c.lc, c.rc};
+    GemmShape shape{(cnt + 127) / 128, 1, (int)(NN / 64)};
+    return launch_tc_gemm<false, false, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiRule>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<rule>");
+}
+static int launch_k2(TcCtx& c, int w, int m0, int cnt) {
+    switch (c.N) {
+        case 64: return launch_k2_bn<64>(c, w, m0, cnt);
+        case 128: return launch_k2_bn<128>(c, w, m0, cnt);
+        case 192: return launch_k2_bn<192>(c, w, m0, cnt);
+        default: return launch_k2_bn<256>(c, w, m0, cnt);
+    }
+}
+
+static int launch_k3(TcCtx& c, int cnt) {
+    size_t NN = (size_t)c.N * c.N;
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_2d(&tmA, c.ghat, (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmB, c.wk, (uint64_t)c.N, NN, (uint64_t)c.N * 2, 256);
+    if (rc) return rc;
+    EpiGY epi{c.gy, cnt, NN};
+    GemmShape shape{(cnt + 127) / 128, (int)(NN / 256), c.N / 64};
+    return launch_tc_gemm<false, false, 256, 4, 0, EpiGY>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<gY>");
+}
+
+template <int BN>
+static int launch_k4_bn(TcCtx& c, int cnt, float* gW) {
+    size_t NN = (size_t)c.N * c.N;
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_2d(&tmA, c.y, NN, (uint64_t)cnt, NN * 2, 64);            // MN-major A: [K=items][M=(b,c)]
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmB, c.gabs, (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 64);   // MN-major B: [K=items][N=a]
+    if (rc) return rc;
+    EpiCounts epi{gW, c.N};
+    GemmShape shape{(int)(NN / 128), 1, (cnt + 63) / 64};
+    return launch_tc_gemm<true, true, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiCounts>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<counts>");
+}
+static int launch_k4(TcCtx& c, int cnt, float* gW) {
+    switch (c.N) {
+        case 64: return launch_k4_bn<64>(c, cnt, gW);
+        case 128: return launch_k4_bn<128>(c, cnt, gW);
+        case 192: return launch_k4_bn<192>(c, cnt, gW);
+        default: return launch_k4_bn<256>(c, cnt, gW);
+    }
+}
+
+static int launch_k5(TcCtx& c, int w, int m0, int cnt) {
+    int N = c.N, L = c.L, B = c.B;
+    int Npad = ((w - 1) + 15) & ~15;
+    CUtensorMap tmGYk, tmGYm, tmRC, tmLC;
+    int rc = make_tmap_2d(&tmGYk, c.gy, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmGYm, c.gy, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmRC, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, (uint32_t)Npad);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, (uint32_t)Npad);
+    if (rc) return rc;
+    size_t smem = (size_t)kK5Stages * kK5StageBytes + 256 + 1024;
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = cnt < c.sms ? cnt : c.sms;
+    k_tc_childgrad<<<grid, 256, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.item_e,
+                                              c.gexp, c.alpha);
+    RBN_LAUNCH_CHECK("k_tc_childgrad");
+    return RBN_OK;
+}
+
+int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
+               const int* tokens, const int* lengths, float* logZ, float* zroot, float* rootexp, cudaStream_t st) {
+    TcCtx c;
+    fill_ctx(c, d, ws, base, lengths, st);
+    int N = c.N, L = c.L, B = c.B;
+    int rc = prep_weights(c, W);
+    if (rc) return rc;
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.y, 0, (size_t)c.chunk * N * N * sizeof(__half), st));
+    k_emission<<<B * L, 256, 0, st>>>(N, L, d->n_tvars, T, tokens, lengths, c.cv, c.ce);
+    RBN_LAUNCH_CHECK("k_emission");
+    k_copy_width1<<<B * L, 128, 0, st>>>(N, L, c.Lp, lengths, c.cv, c.lc, c.rc);
+    RBN_LAUNCH_CHECK("k_copy_width1");
+    for (int w = 2; w <= L; ++w) {
+        int items = B * (L - w + 1);
+        for (int m0 = 0; m0 < items; m0 += c.chunk) {
+            int cnt = items - m0 < c.chunk ? items - m0 : c.chunk;
+            if ((rc = launch_k1(c, w, m0, cnt))) return rc;
+            if ((rc = launch_k2(c, w, m0, cnt))) return rc;
+        }
+    }
+    k_root<<<B, 128, 0, st>>>(N, L, prior, lengths, c.cv, c.ce, logZ, zroot, rootexp, (float*)(base + ws.zroot),
+                              (int*)(base + ws.rootexp));
+    RBN_LAUNCH_CHECK("k_root");
+    return RBN_OK;
+}
+
+int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
+                const int* tokens, const int* lengths, const float* coef, float* gW, float* gT, float* gPrior,
+                cudaStream_t st) {
+    (void)W; (void)T;
+    TcCtx c;
+    fill_ctx(c, d, ws, base, lengths, st);
+    int N = c.N, L = c.L, B = c.B;
+    size_t C = cells_per_seq(L);
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha, 0, (size_t)B * C * N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(gW, 0, (size_t)N * N * N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.y, 0, (size_t)c.chunk * N * N * sizeof(__half), st));
+    k_outside_seed<<<B, 128, 0, st>>>(N, L, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior);
+    RBN_LAUNCH_CHECK("k_outside_seed");
+    int rc;
+    for (int w = L; w >= 2; --w) {
+        int items = B * (L - w + 1);
+        for (int m0 = 0; m0 < items; m0 += c.chunk) {
+            int cnt = items - m0 < c.chunk ? items - m0 : c.chunk;
+            if ((rc = launch_k1(c, w, m0, cnt))) return rc;
+            int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
+            k_prep_g<<<pg, N, 0, st>>>(N, L, w, m0, cnt, lengths, c.ce, c.item_e, c.wexp, c.alpha, c.ghat, c.gabs, c.gexp);
+            RBN_LAUNCH_CHECK("k_prep_g");
+            if ((rc = launch_k3(c, cnt))) return rc;
+            if ((rc = launch_k4(c, cnt, gW))) return rc;
+            if ((rc = launch_k5(c, w, m0, cnt))) return rc;
+        }
+    }
+    k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, c.ce, c.alpha, gT);
+    RBN_LAUNCH_CHECK("k_emission_bwd");
+    return RBN_OK;
+}
+
+// ---- diagnostics: plain GEMM through the same kernel template (tests/test_gpu_tc.py) -----------------------------------
+int debug_gemm(int M, int N, int K, const __half* A, const __half* Bm, float* D, int a_mn, int b_mn, int seg, cudaStream_t st) {
+    if (N != 256 || K % 64 != 0) {
+        set_error("debug gemm: N must be 256 and K a multiple of 64");
+        return RBN_E_BADARG;
+    }
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (!a_mn) rc = make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 128);
+    else rc = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)M * 2, 64);
+    if (rc) return rc;
+    if (!b_mn) rc = make_tmap_2d(&tmB, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 256);
+    else rc = make_tmap_2d(&tmB, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)N * 2, 64);
+    if (rc) return rc;
+    EpiStoreF32 epi{D, M, N, 256};
+    GemmShape shape{(M + 127) / 128, 1, K / 64};
+    int sms = sm_count();
+#define RBN_DBG(AM, BM_, SG) return launch_tc_gemm<AM, BM_, 256, 4, SG, EpiStoreF32>(tmA, tmB, shape, epi, sms, st, "debug_gemm")
+    if (seg) {
+        if (!a_mn && !b_mn) RBN_DBG(false, false, kSegBlocks);
+        if (a_mn && b_mn) RBN_DBG(true, true, kSegBlocks);
+        if (a_mn) RBN_DBG(true, false, kSegBlocks);
+        RBN_DBG(false, true, kSegBlocks);
+    }
+    if (!a_mn && !b_mn) RBN_DBG(false, false, 0);
+    if (a_mn && b_mn) RBN_DBG(true, true, 0);
+    if (a_mn) RBN_DBG(true, false, 0);
+    RBN_DBG(false, true, 0);
+#undef RBN_DBG
+}
+
+}  // namespace rbn

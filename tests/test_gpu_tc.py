@@ -1,0 +1,78 @@
+"""Tensor-core (tcgen05) path: the GEMM kernel template against torch, and the full chart pass against the fp64
+oracle and against the CUDA-core path."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LOGZ_RTOL = 1e-4
+GRAD_RTOL = 1e-3
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 1), (1, 0), (0, 1)])
+@pytest.mark.parametrize("M,K,seg", [(128, 64, 0), (304, 192, 0), (1000, 1024, 0), (200, 4096 * 3 + 128, 1), (128, 65536, 1)])
+def test_tcgen05_gemm_template_vs_torch(a_mn, b_mn, M, K, seg):
+    from rbn_b200 import _lib
+    lib = _lib.load()
+    N = 256
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + K + a_mn * 2 + b_mn)
+    A = torch.rand((M, K), device="cuda", generator=g).half()
+    Bm = torch.rand((N, K), device="cuda", generator=g).half()
+    ref = (A.double() @ Bm.double().t()).float()
+    Ain = A.t().contiguous() if a_mn else A.contiguous()
+    Bin = Bm.t().contiguous() if b_mn else Bm.contiguous()
+    D = torch.full((M, N), float("nan"), device="cuda")
+    rc = lib.rbn_debug_gemm(M, N, K, ctypes.c_void_p(Ain.data_ptr()), ctypes.c_void_p(Bin.data_ptr()),
+                            ctypes.c_void_p(D.data_ptr()), a_mn, b_mn, seg,
+                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "rbn_debug_gemm")
+    torch.cuda.synchronize()
+    err = float((D - ref).abs().max() / ref.abs().max())
+    bias = float(((D - ref) / ref).mean())
+    assert err < 4e-5 and abs(bias) < 3e-5, (a_mn, b_mn, M, K, err, bias)
+
+
+def _run(N, V, L, B, ragged, seed, path, chunk=0):
+    from oracle import inside_oracle as O
+    from rbn_b200 import inside_logZ
+    W, T, pr = O.synthetic_grammar(N, V, seed=seed)
+    tok, lengths = O.synthetic_tokens(B, L, V, seed=seed + 1, ragged=ragged)
+    coef = np.random.default_rng(seed + 2).uniform(0.5, 1.5, B)
+    Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+    lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), path=path, chunk_items=chunk)
+    (lz * torch.tensor(coef, device="cuda")).sum().backward()
+    return (W, T, pr, tok, lengths, coef), lz.detach().cpu().numpy(), Wt.grad.cpu().numpy(), Tt.grad.cpu().numpy(), pt.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize("N,V,L,B,ragged,chunk", [(64, 16, 8, 3, False, 0), (64, 16, 12, 5, True, 128), (128, 8, 9, 3, True, 0),
+                                                  (192, 8, 6, 2, False, 0), (256, 32, 7, 2, True, 0), (256, 32, 20, 2, False, 0)])
+def test_tc_path_vs_fp64_oracle(N, V, L, B, ragged, chunk):
+    from oracle import inside_oracle as O
+    from rbn_b200 import _lib
+    inp, lz, gW, gT, gP = _run(N, V, L, B, ragged, seed=100 + N + L, path=_lib.PATH_TCGEN05, chunk=chunk)
+    W, T, pr, tok, lengths, coef = inp
+    lz_ref, gW_ref, gT_ref, gP_ref = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths, grad_logZ=coef)
+    assert np.abs(lz - lz_ref.numpy()).max() <= LOGZ_RTOL * np.abs(lz_ref.numpy()).max(), (lz, lz_ref)
+    errs = (_rel(gW, gW_ref.numpy()), _rel(gT, gT_ref.numpy()), _rel(gP, gP_ref.numpy()))
+    assert max(errs) <= GRAD_RTOL, errs
+
+
+def test_tc_path_vs_cuda_core_path_long():
+    """L = 64 (beyond what linear space can hold): tensor-core path against the fp32 CUDA-core path + count identities."""
+    from rbn_b200 import _lib
+    N, V, L, B = 64, 32, 64, 4
+    _, lz_s, gW_s, gT_s, gP_s = _run(N, V, L, B, True, seed=7, path=_lib.PATH_SIMT)
+    inp, lz_t, gW_t, gT_t, gP_t = _run(N, V, L, B, True, seed=7, path=_lib.PATH_TCGEN05, chunk=256)
+    assert np.abs(lz_t - lz_s).max() <= LOGZ_RTOL * np.abs(lz_s).max()
+    assert max(_rel(gW_t, gW_s), _rel(gT_t, gT_s), _rel(gP_t, gP_s)) <= GRAD_RTOL
+    W, T, pr, tok, lengths, coef = inp
+    assert abs((gW_t * W).sum() - (coef * (lengths - 1)).sum()) <= 1e-3 * (coef * lengths).sum()
+    assert abs((gT_t * T).sum() - (coef * lengths).sum()) <= 1e-3 * (coef * lengths).sum()
