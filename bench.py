@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched inside + outside (expected rule counts) chart pass.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one JSON line on rank 0)
+    python bench.py --impl reference --gpus N ...            # the reference's algorithm on the host cores (CPU)
+
+Workload (BASELINE.json configs[2], the configuration the metric's target is quoted on): PCFG with N = 256
+nonterminals, V = 32 terminals, sequences of length 128, batch 512 per GPU, inside + outside.  A "step" is one
+pass of the hot path over one batch: inside pass (log Z for every sequence) followed by the outside pass
+(gradients of sum log Z = expected rule counts) and, for N > 1 GPUs, the NCCL all-reduce of the count tensors.
+Weak scaling: every rank owns its own batch of 512 sequences; no collective touches chart data.
+
+Metric: inside+outside sequences / second (whole job).  `value` times the device-resident path (inputs in HBM),
+`e2e` the public API (`SequentialRBN.log_inside_batch` on a model whose Parameters live on the GPU) with the token
+batch in pinned host memory and the loss read back to the host every step.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, V, L, B per GPU, with outside pass)
+    "c3": dict(N=256, V=32, L=128, B=512, outside=True,
+               name="PCFG N=256 L=128 batch 512/GPU inside+outside (BASELINE configs[2])"),
+    "c2": dict(N=64, V=32, L=64, B=1024, outside=False,
+               name="discrete RBN N=64 L=64 batch 1024/GPU inside only (BASELINE configs[1])"),
+    "tiny": dict(N=64, V=32, L=16, B=8, outside=True, name="tiny self-test"),
+}
+
+
+def flops_per_sequence(N, L, outside):
+    """Algorithmic FLOPs: split-sum 2 N^2 (L^3-L)/6, rule contraction N^3 L (L-1);
+    inside+outside = 3x inside."""
+    f_split = 2.0 * N * N * (L ** 3 - L) / 6.0
+    f_rule = float(N) ** 3 * L * (L - 1)
+    mult = 3.0 if outside else 1.0
+    return mult * (f_split + f_rule), mult * f_rule, f_rule
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=p.get("bf16_tflops_sustained", 1394.7), burst=p.get("bf16_tflops", 1670.0),
+                    hbm=p.get("hbm_gbs", 6553.0), source="measured")
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_sample(wl, seconds_budget=25.0):
+    """Time the fp64 oracle (oracle/inside_oracle.py, a restatement of rbnet's inside pass + autograd outside) on a
+    bounded sample of the workload: whole sequences of the workload's N, with the length truncated so that one
+    sequence fits the time budget; the per-sequence time at full length is extrapolated with the algorithmic FLOP
+    ratio and stated as such."""
+    import torch
+    from oracle import inside_oracle as O
+    N, V, L = wl["N"], wl["V"], wl["L"]
+    W, T, pr = O.synthetic_grammar(N, V, seed=0)
+    # pick the sample length from a quick probe at L/4
+    Lp = max(4, L // 4)
+    tok, le = O.synthetic_tokens(1, Lp, V, seed=1)
+    t0 = time.perf_counter()
+    run = (lambda tk, ln: O.flat_inside_with_grads(W, T, pr, tk[:, :, None], ln)) if wl["outside"] else \
+          (lambda tk, ln: O.flat_inside(torch.as_tensor(W), torch.as_tensor(T), torch.as_tensor(pr), torch.as_tensor(tk)[:, :, None], ln))
+    run(tok, le)
+    t_probe = time.perf_counter() - t0
+    f_probe = flops_per_sequence(N, Lp, wl["outside"])[0]
+    Ls = Lp
+    for cand in (L, (3 * L) // 4, L // 2, (3 * L) // 8):
+        if t_probe * flops_per_sequence(N, cand, wl["outside"])[0] / f_probe <= seconds_budget:
+            Ls = cand
+            break
+    if Ls != Lp:
+        tok, le = O.synthetic_tokens(1, Ls, V, seed=1)
+        t0 = time.perf_counter()
+        run(tok, le)
+        t_s = time.perf_counter() - t0
+    else:
+        t_s = t_probe
+    scale = flops_per_sequence(N, L, wl["outside"])[0] / flops_per_sequence(N, Ls, wl["outside"])[0]
+    t_full = t_s * scale
+    sample = (f"1 sequence, N={N}, L={Ls}" + ("" if Ls == L else f" (of {L}; time scaled x{scale:.2f} by algorithmic FLOPs)")
+              + f", fp64 torch restatement of rbnet inside{'+autograd outside' if wl['outside'] else ''}, "
+              f"{t_s:.2f}s measured")
+    return 1.0 / t_full, t_full, sample, torch.get_num_threads()
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    vals = []
+    sample, cores = "", torch.get_num_threads()
+    for s in range(args.warmup + args.steps):
+        v, t_full, sample, cores = cpu_sample(wl, seconds_budget=20.0)
+        if s >= args.warmup:
+            vals.append((v, t_full))
+        if s == 0 and args.warmup > 0 and t_full > 0:
+            pass
+    v = sum(x[0] for x in vals) / len(vals)
+    t = sum(x[1] for x in vals) / len(vals)
+    line = dict(metric="inside+outside sequences/sec" if wl["outside"] else "inside sequences/sec", value=v,
+                unit="seq/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                impl="reference", config=dict(workload=wl["name"], N=wl["N"], V=wl["V"], L=wl["L"]),
+                cpu_baseline=dict(value=v, unit="seq/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=v, unit="seq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                note="the reference (pure Python rbnet) cannot travel to the GPU box; this arm times oracle/ (its "
+                     "vectorised fp64 restatement) on the host cores, one sequence per step")
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------------------------------------
+def build_model(N, V, seed, device):
+    """A single-cell discrete RBN of the AbstractedPCFG shape with random dense weights (the public API object)."""
+    import numpy as np
+    from rbn_b200 import pcfg, sequential
+    rng = np.random.default_rng(seed)
+    cell = pcfg.DiscreteCell(variable=pcfg.DiscreteNonTermVar(N), weights=rng.random((2, N)),
+                             transitions=[pcfg.DiscreteTerminalTransition(weights=rng.random((V, N))),
+                                          pcfg.DiscreteBinaryNonTerminalTransition(weights=rng.random((N, N, N)))])
+    prior = pcfg.DiscretePrior(struc_weights=np.ones(1), prior_weights=[rng.random(N)])
+    return sequential.SequentialRBN(cells=[cell], prior=prior).to(device)
+
+
+def run_ours(args, wl):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import inside_oracle as O     # synthetic workload generator only (shared with the tests)
+    from rbn_b200 import _lib, inside_logZ
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    N, V, L, B = wl["N"], wl["V"], wl["L"], args.batch or wl["B"]
+    W, T, pr = O.synthetic_grammar(N, V, seed=0)
+    tok_np, len_np = O.synthetic_tokens(B, L, V, seed=1 + rank)
+    Wd = torch.tensor(W, dtype=torch.float32, device=dev, requires_grad=wl["outside"])
+    Td = torch.tensor(T, dtype=torch.float32, device=dev, requires_grad=wl["outside"])
+    pd = torch.tensor(pr, dtype=torch.float32, device=dev, requires_grad=wl["outside"])
+    tok_d = torch.tensor(tok_np, dtype=torch.int32, device=dev)
+    len_d = torch.tensor(len_np, dtype=torch.int32, device=dev)
+
+    def allreduce_grads(tensors):
+        if world > 1:
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def device_step():
+        lz = inside_logZ(Wd, Td, pd, tok_d, len_d, chunk_items=args.chunk)
+        if wl["outside"]:
+            for t in (Wd, Td, pd):
+                t.grad = None
+            lz.sum().backward()
+            allreduce_grads([Wd.grad, Td.grad, pd.grad])
+        return lz
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, out
+
+    # ---- device-resident arm -------------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    _lib.profile_read(reset=True)
+    _lib.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step, lz = timed(device_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = _lib.profile_read(reset=True)
+    _lib.profile_enable(False)
+    lz_host = lz.detach().double().cpu().numpy()
+
+    # ---- end-to-end arm: public API, host tokens in pinned memory, loss back to the host --------------------------------
+    model = build_model(N, V, seed=0, device=dev)
+    tok_pin = torch.tensor(tok_np, dtype=torch.int32).pin_memory()
+    len_pin = torch.tensor(len_np, dtype=torch.int32).pin_memory()
+    params = [p for p in model.parameters()]
+
+    def e2e_step():
+        tk = tok_pin.to(dev, non_blocking=True)
+        ln = len_pin.to(dev, non_blocking=True)
+        lz = model.log_inside_batch(tokens=tk, lengths=ln)
+        loss = -lz.sum()
+        if wl["outside"]:
+            for p in params:
+                p.grad = None
+            loss.backward()
+            allreduce_grads([p.grad for p in params])
+        return float(loss)          # device -> host read of the step's result
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    h2d = tok_pin.numel() * 4 + len_pin.numel() * 4
+    d2h = 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    f_step, f_rule_step, f_rule_fwd = (x * B for x in flops_per_sequence(N, L, wl["outside"]))
+    peaks = load_peaks()
+    rule_ms, rule_launches = prof["rule_gemm"]
+    achieved = (f_rule_fwd * args.steps / (rule_ms * 1e-3) / 1e12) if rule_ms > 0 else None
+    roofline = dict(bound="tensor", kernel="k_tc_gemm<rule> (rule contraction, tcgen05)",
+                    achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
+                    frac=(achieved / peaks["tflops"]) if achieved else None, traffic=None,
+                    peak_source=f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                    launches=int(rule_launches), avg_launch_ms=(rule_ms / rule_launches) if rule_launches else None,
+                    algorithmic_flops_per_step=f_rule_fwd,
+                    step_tflops=f_step / (ms_step * 1e-3) / 1e12, step_frac=f_step / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
+                    kernels_ms_per_step={k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]})
+    launches = int(sum(v[1] for v in prof.values()))
+    cpu_v, cpu_t, cpu_samp, cores = cpu_sample(wl) if world == 1 else (None, None, None, None)
+    line = dict(metric="inside+outside sequences/sec" if wl["outside"] else "inside sequences/sec",
+                value=world * B / (ms_step * 1e-3), unit="seq/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
+                data="synthetic",
+                config=dict(workload=wl["name"], N=N, V=V, L=L, batch_per_gpu=B, global_batch=world * B,
+                            parallelism=f"dp{world}", l2="inputs larger than L2 (chart + split-sum buffers are GBs)",
+                            accumulate="fp32 (tcgen05, segmented)", operands="fp16 mantissas + per-cell exponents"),
+                e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="seq/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=d2h),
+                gpu_launches=launches, roofline=roofline, clocks=clocks,
+                logZ_mean=float(np.mean(lz_host)))
+    if cpu_v is not None:
+        line["cpu_baseline"] = dict(value=cpu_v, unit="seq/s", cores=cores, kind="port", sample=cpu_samp)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU (default: the workload's)")
+    ap.add_argument("--chunk", type=int, default=0, help="spans per launch group (0 = library default)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,15 @@ int rbn_export_chart(const RbnDesc* desc, const int32_t* lengths,
  * is NOT detected on device; `bad` (device int32, may be NULL) is set to the number of such groups. */
 int rbn_lognormalize(float* log_p, int64_t group_size, int64_t groups, int32_t* bad, void* stream);
 
+/* Launch accounting and optional per-kernel timing.  The library counts every kernel it launches, by class; with
+ * rbn_profile_enable(1) it also brackets each launch with CUDA events on the caller's stream.  rbn_profile_read
+ * synchronises the device and returns, per class, the summed event time (ms) and the launch count since the last
+ * reset.  Classes (RBN_KC_*): 0 emission, 1 split-sum, 2 rule GEMM, 3 gY GEMM, 4 count GEMM, 5 child-gradient,
+ * 6 gradient prep, 7 CUDA-core inside, 8 CUDA-core outside, 9 other.  n must be >= RBN_KC_NUM. */
+#define RBN_KC_NUM 10
+int rbn_profile_enable(int32_t on);
+int rbn_profile_read(double* ms, int64_t* launches, int32_t n, int32_t reset);
+
 /* Diagnostics: D[M][N] (float32) = A * B through the same tcgen05 GEMM kernel template the chart pass uses
  * (N must be 256, K a multiple of 64; fp16 operands).  a_mn / b_mn select the operand layout: 0 = K-major
  * (A[M][K], B[N][K]), 1 = MN-major (A[K][M], B[K][N]).  segmented != 0 selects the segmented-accumulation variant

@@ -10,6 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librbn_b200.so")
 
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+KERNEL_CLASSES = ["emission", "split_sum", "rule_gemm", "gy_gemm", "count_gemm", "child_grad", "grad_prep",
+                  "simt_inside", "simt_outside", "other"]
 
 
 class RbnDesc(ctypes.Structure):
@@ -40,6 +42,8 @@ _SIGNATURES = {
                                            _P, _P, _P, _P, _P]),
     "rbn_export_chart": (ctypes.c_int, [ctypes.POINTER(RbnDesc), _P, _P, ctypes.c_size_t, ctypes.c_int32, _P, _P]),
     "rbn_lognormalize": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, _P, _P]),
+    "rbn_profile_enable": (ctypes.c_int, [ctypes.c_int32]),
+    "rbn_profile_read": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
     "rbn_debug_gemm": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_int32,
                                       ctypes.c_int32, ctypes.c_int32, _P]),
 }
@@ -78,3 +82,16 @@ def check(code, what):
     if code != 0:
         msg = load().rbn_last_error().decode("utf-8", "replace")
         raise RbnError(f"{what} failed with code {code}: {msg}")
+
+
+def profile_enable(on):
+    check(load().rbn_profile_enable(1 if on else 0), "rbn_profile_enable")
+
+
+def profile_read(reset=True):
+    """{class: (ms, launches)} since the last reset (synchronises the device)."""
+    n = len(KERNEL_CLASSES)
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    check(load().rbn_profile_read(ms, cnt, n, 1 if reset else 0), "rbn_profile_read")
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(KERNEL_CLASSES)}

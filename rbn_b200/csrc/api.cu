@@ -1,6 +1,8 @@
 // extern "C" entry points of librbn_b200 (see include/rbn_b200.h for the contract and the reference citations).
 #include "common.cuh"
 #include <stdarg.h>
+#include <mutex>
+#include <vector>
 
 namespace rbn {
 
@@ -24,6 +26,33 @@ int tc_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float
 int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
                 const int*, const float*, float*, float*, float*, cudaStream_t);
 int debug_gemm(int, int, int, const __half*, const __half*, float*, int, int, int, cudaStream_t);
+
+// ---- profiling -------------------------------------------------------------------------------------------------------
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static long long g_launches[KC_NUM] = {0};
+static double g_ms[KC_NUM] = {0};
+struct EvPair { cudaEvent_t a, b; int cls; };
+static std::vector<EvPair> g_pending;
+static std::vector<EvPair> g_free;
+
+ProfScope::ProfScope(int c, cudaStream_t s) : cls(c), st(s), slot(-1) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_launches[cls]++;
+    if (!g_prof_on) return;
+    EvPair e;
+    if (!g_free.empty()) { e = g_free.back(); g_free.pop_back(); }
+    else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
+    e.cls = cls;
+    cudaEventRecord(e.a, st);
+    g_pending.push_back(e);
+    slot = (int)g_pending.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_pending[slot].b, st);
+}
 
 static bool desc_ok(const RbnDesc* d) {
     if (!d) { set_error("desc is NULL"); return false; }
@@ -68,7 +97,11 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         size_t Lp = align_up(L + 16, 16);
         o->Lp = (int)Lp;
         size_t max_items = B * (L - 1);                        // widest diagonal (w = 2)
-        size_t chunk = d->chunk_items > 0 ? (size_t)d->chunk_items : 8192;
+        // default: whole waves of 128-span tiles on 148 SMs, split-sum buffer Y of at most ~6 GB
+        size_t wave = 148 * 128;
+        size_t chunk = (size_t)(6.0e9 / (2.0 * N * N)) / wave * wave;
+        if (chunk < wave) chunk = wave;
+        if (d->chunk_items > 0) chunk = (size_t)d->chunk_items;
         if (chunk > max_items) chunk = max_items;
         chunk = align_up(chunk, 128);
         o->chunk = (int)chunk;
@@ -182,6 +215,30 @@ int rbn_debug_gemm(int32_t M, int32_t N, int32_t K, const void* A, const void* B
         return RBN_E_BADARG;
     }
     return debug_gemm(M, N, K, (const __half*)A, (const __half*)B, D, a_mn, b_mn, segmented, (cudaStream_t)stream);
+}
+
+int rbn_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return RBN_OK;
+}
+
+int rbn_profile_read(double* ms, int64_t* launches, int32_t n, int32_t reset) {
+    if (!ms || !launches || n < KC_NUM) {
+        set_error("rbn_profile_read: need arrays of at least %d entries", (int)KC_NUM);
+        return RBN_E_BADARG;
+    }
+    RBN_CUDA_CHECK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& e : g_pending) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) g_ms[e.cls] += t;
+        g_free.push_back(e);
+    }
+    g_pending.clear();
+    for (int i = 0; i < KC_NUM; ++i) { ms[i] = g_ms[i]; launches[i] = g_launches[i]; }
+    if (reset) for (int i = 0; i < KC_NUM; ++i) { g_ms[i] = 0; g_launches[i] = 0; }
+    return RBN_OK;
 }
 
 }  // extern "C"

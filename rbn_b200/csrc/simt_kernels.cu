@@ -348,17 +348,17 @@ int simt_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* 
     float* cv = (float*)(base + ws.chart_val);
     int* ce = (int*)(base + ws.chart_exp);
     int N = d->N, L = d->L, B = d->B;
-    k_emission<<<B * L, kThreads, 0, st>>>(N, L, d->n_tvars, T, tokens, lengths, cv, ce);
+    { ProfScope ps(KC_EMISSION, st); k_emission<<<B * L, kThreads, 0, st>>>(N, L, d->n_tvars, T, tokens, lengths, cv, ce); }
     RBN_LAUNCH_CHECK("k_emission");
     int TB = pick_tb(N, 1);
     size_t smem = ((size_t)(L + 1) + (size_t)TB * N) * sizeof(float);
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_inside_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int w = 2; w <= L; ++w) {
-        k_inside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce);
+        { ProfScope ps(KC_SIMT_INSIDE, st); k_inside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce); }
         RBN_LAUNCH_CHECK("k_inside_diag");
     }
-    k_root<<<B, 128, 0, st>>>(N, L, prior, lengths, cv, ce, logZ, zroot, rootexp, (float*)(base + ws.zroot),
-                              (int*)(base + ws.rootexp));
+    { ProfScope ps(KC_OTHER, st); k_root<<<B, 128, 0, st>>>(N, L, prior, lengths, cv, ce, logZ, zroot, rootexp, (float*)(base + ws.zroot),
+                              (int*)(base + ws.rootexp)); }
     RBN_LAUNCH_CHECK("k_root");
     return RBN_OK;
 }
@@ -376,16 +376,16 @@ int simt_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float*
     RBN_CUDA_CHECK(cudaMemsetAsync(gW, 0, (size_t)N * N * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
-    k_outside_seed<<<B, 128, 0, st>>>(N, L, prior, lengths, cv, (const float*)(base + ws.zroot), coef, alpha, gPrior);
+    { ProfScope ps(KC_OTHER, st); k_outside_seed<<<B, 128, 0, st>>>(N, L, prior, lengths, cv, (const float*)(base + ws.zroot), coef, alpha, gPrior); }
     RBN_LAUNCH_CHECK("k_outside_seed");
     int TB = pick_tb(N, 2);
     size_t smem = ((size_t)(L + 1) + N + 2 * (size_t)TB * N) * sizeof(float);
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_outside_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int w = L; w >= 2; --w) {
-        k_outside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce, alpha, gW);
+        { ProfScope ps(KC_SIMT_OUTSIDE, st); k_outside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce, alpha, gW); }
         RBN_LAUNCH_CHECK("k_outside_diag");
     }
-    k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, ce, alpha, gT);
+    { ProfScope ps(KC_EMISSION, st); k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, ce, alpha, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");
     return RBN_OK;
 }

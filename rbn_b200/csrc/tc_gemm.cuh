@@ -216,14 +216,14 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t out
 
 template <bool A_MN, bool B_MN, int BLOCK_N, int STAGES, int SEG, class Epi>
 int launch_tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape shape, const Epi& epi, int num_sms,
-                   cudaStream_t st, const char* name) {
+                   cudaStream_t st, const char* name, int kclass) {
     using S = GemmSmem<BLOCK_N, STAGES>;
     auto kern = k_tc_gemm<A_MN, B_MN, BLOCK_N, STAGES, SEG, Epi>;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     int tiles = shape.m_tiles * shape.n_tiles;
     int grid = tiles < num_sms ? tiles : num_sms;
     if (grid < 1) return RBN_OK;
-    kern<<<grid, 256, S::TOTAL, st>>>(tmA, tmB, shape, epi);
+    { ProfScope ps(kclass, st); kern<<<grid, 256, S::TOTAL, st>>>(tmA, tmB, shape, epi); }
     RBN_LAUNCH_CHECK(name);
     return RBN_OK;
 }

@@ -625,12 +625,12 @@ static int prep_weights(TcCtx& c, const float* W) {
     int N = c.N;
     int* bits = c.wbits;
     RBN_CUDA_CHECK(cudaMemsetAsync(bits, 0, (size_t)N * sizeof(int), c.st));
-    k_w_colmax<<<256, 256, 0, c.st>>>(N, W, bits);
+    { ProfScope ps(KC_OTHER, c.st); k_w_colmax<<<256, 256, 0, c.st>>>(N, W, bits); }
     RBN_LAUNCH_CHECK("k_w_colmax");
-    k_w_exp<<<(N + 127) / 128, 128, 0, c.st>>>(N, bits, c.wexp, c.wscale);
+    { ProfScope ps(KC_OTHER, c.st); k_w_exp<<<(N + 127) / 128, 128, 0, c.st>>>(N, bits, c.wexp, c.wscale); }
     RBN_LAUNCH_CHECK("k_w_exp");
     dim3 grid((unsigned)((size_t)N * N / 32), (unsigned)(N / 32));
-    k_w_copies<<<grid, dim3(32, 8), 0, c.st>>>(N, W, c.wexp, c.wk, c.wt);
+    { ProfScope ps(KC_OTHER, c.st); k_w_copies<<<grid, dim3(32, 8), 0, c.st>>>(N, W, c.wexp, c.wk, c.wt); }
     RBN_LAUNCH_CHECK("k_w_copies");
     return RBN_OK;
 }
@@ -640,7 +640,7 @@ static int launch_k1(TcCtx& c, int w, int m0, int cnt) {
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_splitsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < 2 * c.sms ? cnt : 2 * c.sms;
     if (smem > 110 * 1024 || grid > c.sms) grid = cnt < c.sms ? cnt : c.sms;
-    k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.lc, c.rc, c.y, c.item_e);
+    { ProfScope ps(KC_SPLITSUM, c.st); k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.lc, c.rc, c.y, c.item_e); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
 }
@@ -655,7 +655,7 @@ static int launch_k2_bn(TcCtx& c, int w, int m0, int cnt) {
     if (rc) return rc;
     EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.item_e, c.cv, c.ce, c.lc, c.rc};
     GemmShape shape{(cnt + 127) / 128, 1, (int)(NN / 64)};
-    return launch_tc_gemm<false, false, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiRule>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<rule>");
+    return launch_tc_gemm<false, false, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiRule>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<rule>", KC_RULE);
 }
 static int launch_k2(TcCtx& c, int w, int m0, int cnt) {
     switch (c.N) {
@@ -675,7 +675,7 @@ static int launch_k3(TcCtx& c, int cnt) {
     if (rc) return rc;
     EpiGY epi{c.gy, cnt, NN};
     GemmShape shape{(cnt + 127) / 128, (int)(NN / 256), c.N / 64};
-    return launch_tc_gemm<false, false, 256, 4, 0, EpiGY>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<gY>");
+    return launch_tc_gemm<false, false, 256, 4, 0, EpiGY>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<gY>", KC_GY);
 }
 
 template <int BN>
@@ -688,7 +688,7 @@ static int launch_k4_bn(TcCtx& c, int cnt, float* gW) {
     if (rc) return rc;
     EpiCounts epi{gW, c.N};
     GemmShape shape{(int)(NN / 128), 1, (cnt + 63) / 64};
-    return launch_tc_gemm<true, true, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiCounts>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<counts>");
+    return launch_tc_gemm<true, true, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiCounts>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<counts>", KC_COUNTS);
 }
 static int launch_k4(TcCtx& c, int cnt, float* gW) {
     switch (c.N) {
@@ -714,8 +714,8 @@ static int launch_k5(TcCtx& c, int w, int m0, int cnt) {
     size_t smem = (size_t)kK5Stages * kK5StageBytes + 256 + 1024;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < c.sms ? cnt : c.sms;
-    k_tc_childgrad<<<grid, 256, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.item_e,
-                                              c.gexp, c.alpha);
+    { ProfScope ps(KC_CHILD, c.st); k_tc_childgrad<<<grid, 256, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.item_e,
+                                              c.gexp, c.alpha); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;
 }
@@ -728,9 +728,9 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
     int rc = prep_weights(c, W);
     if (rc) return rc;
     RBN_CUDA_CHECK(cudaMemsetAsync(c.y, 0, (size_t)c.chunk * N * N * sizeof(__half), st));
-    k_emission<<<B * L, 256, 0, st>>>(N, L, d->n_tvars, T, tokens, lengths, c.cv, c.ce);
+    { ProfScope ps(KC_EMISSION, st); k_emission<<<B * L, 256, 0, st>>>(N, L, d->n_tvars, T, tokens, lengths, c.cv, c.ce); }
     RBN_LAUNCH_CHECK("k_emission");
-    k_copy_width1<<<B * L, 128, 0, st>>>(N, L, c.Lp, lengths, c.cv, c.lc, c.rc);
+    { ProfScope ps(KC_EMISSION, st); k_copy_width1<<<B * L, 128, 0, st>>>(N, L, c.Lp, lengths, c.cv, c.lc, c.rc); }
     RBN_LAUNCH_CHECK("k_copy_width1");
     for (int w = 2; w <= L; ++w) {
         int items = B * (L - w + 1);
@@ -740,8 +740,8 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
             if ((rc = launch_k2(c, w, m0, cnt))) return rc;
         }
     }
-    k_root<<<B, 128, 0, st>>>(N, L, prior, lengths, c.cv, c.ce, logZ, zroot, rootexp, (float*)(base + ws.zroot),
-                              (int*)(base + ws.rootexp));
+    { ProfScope ps(KC_OTHER, st); k_root<<<B, 128, 0, st>>>(N, L, prior, lengths, c.cv, c.ce, logZ, zroot, rootexp, (float*)(base + ws.zroot),
+                              (int*)(base + ws.rootexp)); }
     RBN_LAUNCH_CHECK("k_root");
     return RBN_OK;
 }
@@ -759,7 +759,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(c.y, 0, (size_t)c.chunk * N * N * sizeof(__half), st));
-    k_outside_seed<<<B, 128, 0, st>>>(N, L, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior);
+    { ProfScope ps(KC_OTHER, st); k_outside_seed<<<B, 128, 0, st>>>(N, L, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior); }
     RBN_LAUNCH_CHECK("k_outside_seed");
     int rc;
     for (int w = L; w >= 2; --w) {
@@ -768,14 +768,14 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
             int cnt = items - m0 < c.chunk ? items - m0 : c.chunk;
             if ((rc = launch_k1(c, w, m0, cnt))) return rc;
             int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
-            k_prep_g<<<pg, N, 0, st>>>(N, L, w, m0, cnt, lengths, c.ce, c.item_e, c.wexp, c.alpha, c.ghat, c.gabs, c.gexp);
+            { ProfScope ps(KC_PREP, st); k_prep_g<<<pg, N, 0, st>>>(N, L, w, m0, cnt, lengths, c.ce, c.item_e, c.wexp, c.alpha, c.ghat, c.gabs, c.gexp); }
             RBN_LAUNCH_CHECK("k_prep_g");
             if ((rc = launch_k3(c, cnt))) return rc;
             if ((rc = launch_k4(c, cnt, gW))) return rc;
             if ((rc = launch_k5(c, w, m0, cnt))) return rc;
         }
     }
-    k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, c.ce, c.alpha, gT);
+    { ProfScope ps(KC_EMISSION, st); k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, c.ce, c.alpha, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");
     return RBN_OK;
 }
@@ -797,7 +797,7 @@ int debug_gemm(int M, int N, int K, const __half* A, const __half* Bm, float* D,
     EpiStoreF32 epi{D, M, N, 256};
     GemmShape shape{(M + 127) / 128, 1, K / 64};
     int sms = sm_count();
-#define RBN_DBG(AM, BM_, SG) return launch_tc_gemm<AM, BM_, 256, 4, SG, EpiStoreF32>(tmA, tmB, shape, epi, sms, st, "debug_gemm")
+#define RBN_DBG(AM, BM_, SG) return launch_tc_gemm<AM, BM_, 256, 4, SG, EpiStoreF32>(tmA, tmB, shape, epi, sms, st, "debug_gemm", KC_OTHER)
     if (seg) {
         if (!a_mn && !b_mn) RBN_DBG(false, false, kSegBlocks);
         if (a_mn && b_mn) RBN_DBG(true, true, kSegBlocks);
