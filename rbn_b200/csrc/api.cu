@@ -105,6 +105,7 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         if (chunk > max_items) chunk = max_items;
         chunk = align_up(chunk, 128);
         o->chunk = (int)chunk;
+        o->alpha2 = take(B * C * N * sizeof(float));
         o->lc = take(B * L * Lp * N * sizeof(__half));
         o->rc = take(B * (L + 1) * Lp * N * sizeof(__half));
         o->wt = take(N * N * N * sizeof(__half));

@@ -44,6 +44,7 @@ struct WsLayout {
     size_t chart_val;   // float  [B][C][N]   mantissas, max 1 per cell (power-of-two scaled => exact)
     size_t chart_exp;   // int32  [B][C]      beta = mantissa * 2^exp
     size_t alpha;       // float  [B][C][N]   scaled outside values (backward only)
+    size_t alpha2;      // float  [B][C][N]   tensor-core path: right-child contributions (alpha holds left-child ones)
     size_t zroot;       // float  [B]
     size_t rootexp;     // int32  [B]
     // tensor-core path

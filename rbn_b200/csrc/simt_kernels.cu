@@ -281,13 +281,14 @@ __global__ void k_outside_diag(int N, int L, int w, int TB, const float* __restr
 }
 
 __global__ void k_emission_bwd(int N, int L, int nt, const int* __restrict__ tokens, const int* __restrict__ lengths,
-                               const int* __restrict__ ce, const float* __restrict__ alpha, float* __restrict__ gT) {
+                               const int* __restrict__ ce, const float* __restrict__ alpha,
+                               const float* __restrict__ alpha2, float* __restrict__ gT) {
     int b = blockIdx.x / L, i = blockIdx.x % L;
     if (i >= lengths[b]) return;
     size_t cell = (size_t)b * cells_per_seq(L) + i;
     int e = ce[cell];
     for (int a = threadIdx.x; a < N; a += blockDim.x) {
-        float g = ldexpf(alpha[cell * N + a], -e);
+        float g = ldexpf(alpha[cell * N + a] + (alpha2 ? alpha2[cell * N + a] : 0.f), -e);
         if (g == 0.f) continue;
         for (int t = 0; t < nt; ++t) {
             int y = tokens[((size_t)b * L + i) * nt + t];
@@ -385,7 +386,7 @@ int simt_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float*
         { ProfScope ps(KC_SIMT_OUTSIDE, st); k_outside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce, alpha, gW); }
         RBN_LAUNCH_CHECK("k_outside_diag");
     }
-    { ProfScope ps(KC_EMISSION, st); k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, ce, alpha, gT); }
+    { ProfScope ps(KC_EMISSION, st); k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, ce, alpha, nullptr, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");
     return RBN_OK;
 }

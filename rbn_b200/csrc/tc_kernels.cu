@@ -22,7 +22,7 @@ namespace rbn {
 __global__ void k_emission(int, int, int, const float*, const int*, const int*, float*, int*);
 __global__ void k_root(int, int, const float*, const int*, const float*, const int*, float*, float*, float*, float*, int*);
 __global__ void k_outside_seed(int, int, const float*, const int*, const float*, const float*, const float*, float*, float*);
-__global__ void k_emission_bwd(int, int, int, const int*, const int*, const int*, const float*, float*);
+__global__ void k_emission_bwd(int, int, int, const int*, const int*, const int*, const float*, const float*, float*);
 
 // ---- TMA descriptor encoding ------------------------------------------------------------------------------------------
 PFN_encodeTiled get_encode_fn() {
@@ -193,33 +193,35 @@ struct EpiCounts {
 };
 
 // =======================================================================================================================
-// K1: split-sum, one span per CTA iteration; operands loaded by 4 producer warps (scale folding + swizzled store)
+// K1: split-sum, one span per CTA iteration
 // =======================================================================================================================
-// smem operand tile, MN-major: atom a (64 nonterminals) = Kpad rows x 128 B; row r holds splits' values, 16-byte chunk
-// ch of row r is stored at chunk position ch ^ (r & 7)  (the 128-byte swizzle the UMMA descriptor expects)
-static constexpr int kK1Threads = 288;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer / TMEM owner
+// Operands are K-slabs of up to 64 splits: TMA boxes of 64 chart rows x 64 nonterminals land as MN-major atoms
+// (64 k-rows x 128 B, 128-byte swizzle).  Four "fix-up" warps fold the per-split scale c_j = 2^(e_ij + e_jk - E)
+// into the left-child slab in shared memory (and zero the rows past the last split); one thread issues the MMAs.
+//   warps 0-3 epilogue (TMEM -> fp16 -> Y)   warps 4-7 fix-up   warp 8 TMA producer   warp 9 MMA issuer / TMEM owner
+static constexpr int kK1Threads = 320;
 
 __global__ void __launch_bounds__(kK1Threads, 1)
-k_tc_splitsum(int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths,
-              const int* __restrict__ ce, const __half* __restrict__ lc, const __half* __restrict__ rc,
-              __half* __restrict__ Y, int* __restrict__ item_e) {
+k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ CUtensorMap tmRC,
+              int N, int L, int Lp, int w, int m0, int cnt, int stages, const int* __restrict__ lengths,
+              const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int Kpad = ((w - 1) + 15) & ~15;
+    const int parts = (Kpad + 63) / 64;
     const int halves = (N + 127) / 128;
     const int a_atoms = halves * 2;            // A operand covers halves * 128 rows (zero beyond N)
     const int b_atoms = N / 64;
-    const uint32_t atom_bytes = (uint32_t)Kpad * 128;
-    uint8_t* sL = smem;
-    uint8_t* sR = sL + (size_t)a_atoms * atom_bytes;
-    uint8_t* tail = sR + (size_t)b_atoms * atom_bytes;
-    uint64_t* sm_full = (uint64_t*)tail;
-    uint64_t* sm_empty = sm_full + 1;
-    uint64_t* acc_full = sm_empty + 1;     // [2]
-    uint64_t* acc_empty = acc_full + 2;    // [2]
+    const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * 8192;
+    uint8_t* tail = smem + (size_t)stages * stage_bytes;
+    uint64_t* tma_full = (uint64_t*)tail;         // [stages]
+    uint64_t* fix_full = tma_full + stages;       // [stages]
+    uint64_t* empty = fix_full + stages;          // [stages]
+    uint64_t* acc_full = empty + stages;          // [2]
+    uint64_t* acc_empty = acc_full + 2;           // [2]
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
-    int* red = (int*)(tmem_slot + 1);      // [4]
-    float* cj = (float*)(red + 4);         // [128]
+    int* red = (int*)(tmem_slot + 2);             // [4]
+    float* cj = (float*)(red + 4);                // [128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t TMEM_COLS = tmem_cols_pow2(halves * N);
@@ -227,89 +229,146 @@ k_tc_splitsum(int N, int L, int Lp, int w, int m0, int cnt, const int* __restric
     const size_t C = cells_per_seq(L);
 
     if (threadIdx.x == 0) {
-        ptx::mbar_init(sm_full, 128);
-        ptx::mbar_init(sm_empty, 1);
+        for (int s = 0; s < stages; ++s) {
+            ptx::mbar_init(&tma_full[s], 1);
+            ptx::mbar_init(&fix_full[s], 128);
+            ptx::mbar_init(&empty[s], 1);
+        }
         for (int h = 0; h < 2; ++h) {
             ptx::mbar_init(&acc_full[h], 1);
             ptx::mbar_init(&acc_empty[h], 128);
         }
         ptx::fence_barrier_init();
+        ptx::tma_prefetch_desc(&tmLC);
+        ptx::tma_prefetch_desc(&tmRC);
     }
-    // zero the A atoms that lie beyond N (N = 64 or 192): never written by the producers
-    for (uint32_t off = (uint32_t)b_atoms * atom_bytes + threadIdx.x * 16; off < (uint32_t)a_atoms * atom_bytes; off += kK1Threads * 16)
-        *reinterpret_cast<uint4*>(sL + off) = make_uint4(0, 0, 0, 0);
-    if (warp == 8) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    // zero the A atoms that lie beyond N (N = 64 or 192) in every stage: TMA never writes them
+    if (a_atoms > b_atoms)
+        for (int sidx = 0; sidx < stages; ++sidx)
+            for (uint32_t off = (uint32_t)b_atoms * 8192 + threadIdx.x * 16; off < (uint32_t)a_atoms * 8192; off += kK1Threads * 16)
+                *reinterpret_cast<uint4*>(smem + (size_t)sidx * stage_bytes + off) = make_uint4(0, 0, 0, 0);
+    if (warp == 9) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    uint32_t it_phase = 0;          // phase of sm_full / sm_empty / acc_* (one completion per processed item)
-    for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
-        const int m = m0 + t;
-        const int b = m / nI, i = m - b * nI, k = i + w;
-        if (k > lengths[b]) continue;                       // uniform across the CTA
-        if (warp >= 4 && warp < 8) {
-            // ---------------- producers ----------------
-            const int p = threadIdx.x - 128;                // 0..127
+    if (warp == 8) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+                const int m = m0 + t;
+                const int b = m / nI, i = m - b * nI, k = i + w;
+                if (k > lengths[b]) continue;
+                const int lc_row = (int)(((size_t)b * L + i) * Lp + (i + 1));
+                const int rc_row = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
+                for (int part = 0; part < parts; ++part) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sL = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sR = sL + (size_t)a_atoms * 8192;
+                    ptx::mbar_expect_tx(&tma_full[stage], (uint32_t)b_atoms * 2 * 8192);
+                    for (int a = 0; a < b_atoms; ++a) {
+                        ptx::tma_load_2d(sL + a * 8192, &tmLC, &tma_full[stage], a * 64, lc_row + part * 64);
+                        ptx::tma_load_2d(sR + a * 8192, &tmRC, &tma_full[stage], a * 64, rc_row + part * 64);
+                    }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ---------------- fix-up: fold c_j into the left-child slab ----------------
+        const int p = threadIdx.x - 128;                // 0..127
+        int stage = 0;
+        uint32_t phase = 0;
+        const int chunks_per_row = N / 8;               // 16-byte chunks per chart row
+        for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+            const int m = m0 + t;
+            const int b = m / nI, i = m - b * nI, k = i + w;
+            if (k > lengths[b]) continue;
             const int* ce_seq = ce + (size_t)b * C;
-            int s = INT_MIN;
+            int sft = INT_MIN;
             if (p < w - 1) {
                 const int u = p + 1;
-                s = ce_seq[cell_off(u, L) + i] + ce_seq[cell_off(w - u, L) + i + u];
+                sft = ce_seq[cell_off(u, L) + i] + ce_seq[cell_off(w - u, L) + i + u];
             }
-            int mxs = s;
+            int mxs = sft;
             for (int o = 16; o > 0; o >>= 1) mxs = max(mxs, __shfl_xor_sync(0xffffffffu, mxs, o));
-            ptx::mbar_wait(sm_empty, it_phase ^ 1);          // previous item's MMAs have consumed the tiles (and cj/red)
+            ptx::named_bar_sync(1, 128);                // every fix-up thread is done with the previous span's cj / red
             if (lane == 0) red[warp - 4] = mxs;
             ptx::named_bar_sync(1, 128);
             const int E = max(max(red[0], red[1]), max(red[2], red[3]));
-            if (p < w - 1) cj[p] = ldexpf(1.0f, max(s - E, -60));
+            cj[p] = (p < w - 1) ? ldexpf(1.0f, max(sft - E, -60)) : 0.f;
             if (p == 0) item_e[t] = E;
             ptx::named_bar_sync(1, 128);
-            const __half* lrow0 = lc + ((size_t)((size_t)b * L + i) * Lp + (i + 1)) * N;
-            const __half* rrow0 = rc + ((size_t)((size_t)b * (L + 1) + k) * Lp + (i + 1)) * N;
-            for (int r = warp - 4; r < Kpad; r += 4) {
-                const bool live = r < w - 1;
-                const __half2 sc = __float2half2_rn(live ? cj[r] : 0.f);
-                for (int c16 = lane; c16 < N / 8; c16 += 32) {
-                    uint4 lv = make_uint4(0, 0, 0, 0), rv = make_uint4(0, 0, 0, 0);
-                    if (live) {
-                        lv = *reinterpret_cast<const uint4*>(lrow0 + (size_t)r * N + c16 * 8);
-                        rv = *reinterpret_cast<const uint4*>(rrow0 + (size_t)r * N + c16 * 8);
-                        __half2* lh = reinterpret_cast<__half2*>(&lv);
+            for (int part = 0; part < parts; ++part) {
+                const int Ks = min(64, Kpad - part * 64);
+                ptx::mbar_wait(&tma_full[stage], phase);
+                uint8_t* sL = smem + (size_t)stage * stage_bytes;
+                for (int idx = p; idx < Ks * chunks_per_row; idx += 128) {
+                    const int r = idx / chunks_per_row, c16 = idx - r * chunks_per_row;
+                    const float c = cj[part * 64 + r];
+                    if (c == 1.0f) continue;
+                    uint4* ptr = reinterpret_cast<uint4*>(sL + (uint32_t)(c16 >> 3) * 8192 + (uint32_t)r * 128 +
+                                                         (uint32_t)(((c16 & 7) ^ (r & 7)) << 4));
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (c != 0.f) {
+                        v = *ptr;
+                        const __half2 sc = __float2half2_rn(c);
+                        __half2* hv = reinterpret_cast<__half2*>(&v);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) lh[q] = __hmul2(lh[q], sc);
+                        for (int qd = 0; qd < 4; ++qd) hv[qd] = __hmul2(hv[qd], sc);
                     }
-                    const uint32_t off = (uint32_t)(c16 >> 3) * atom_bytes + (uint32_t)r * 128 + (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
-                    *reinterpret_cast<uint4*>(sL + off) = lv;
-                    *reinterpret_cast<uint4*>(sR + off) = rv;
+                    *ptr = v;
                 }
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(&fix_full[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
-            ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(sm_full);
-        } else if (warp == 8) {
-            // ---------------- MMA issuer ----------------
-            if (lane == 0) {
-                const uint32_t idesc = ptx::make_idesc_f16(128, N, true, true, 0);
-                ptx::mbar_wait(sm_full, it_phase);
-                ptx::tc_fence_after();
-                const uint32_t aL = ptx::smem_u32(sL), aR = ptx::smem_u32(sR);
-                for (int h = 0; h < halves; ++h) {
-                    ptx::mbar_wait(&acc_empty[h], it_phase ^ 1);
+        }
+    } else if (warp == 9) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_f16(128, N, true, true, 0);
+            int stage = 0;
+            uint32_t phase = 0, it_phase = 0;
+            for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+                const int m = m0 + t;
+                const int b = m / nI, i = m - b * nI;
+                if (i + w > lengths[b]) continue;
+                for (int part = 0; part < parts; ++part) {
+                    const int Ks = min(64, Kpad - part * 64);
+                    ptx::mbar_wait(&fix_full[stage], phase);
                     ptx::tc_fence_after();
-                    for (int k16 = 0; k16 < Kpad / 16; ++k16) {
-                        const uint64_t ad = ptx::make_smem_desc(aL + (uint32_t)(h * 2) * atom_bytes + k16 * 2048, atom_bytes, 1024);
-                        const uint64_t bd = ptx::make_smem_desc(aR + k16 * 2048, atom_bytes, 1024);
-                        ptx::mma_f16_ss(tmem_base + h * N, ad, bd, idesc, (uint32_t)(k16 != 0));
+                    const uint32_t aL = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t aR = aL + (uint32_t)a_atoms * 8192;
+                    for (int h = 0; h < halves; ++h) {
+                        if (part == 0) {
+                            ptx::mbar_wait(&acc_empty[h], it_phase ^ 1);
+                            ptx::tc_fence_after();
+                        }
+                        for (int k16 = 0; k16 < Ks / 16; ++k16) {
+                            const uint64_t ad = ptx::make_smem_desc(aL + (uint32_t)(h * 2) * 8192 + k16 * 2048, 8192, 1024);
+                            const uint64_t bd = ptx::make_smem_desc(aR + k16 * 2048, 8192, 1024);
+                            ptx::mma_f16_ss(tmem_base + h * N, ad, bd, idesc, (uint32_t)!(part == 0 && k16 == 0));
+                        }
+                        if (part == parts - 1) ptx::mma_commit(&acc_full[h]);
                     }
-                    ptx::mma_commit(&acc_full[h]);
+                    ptx::mma_commit(&empty[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                ptx::mma_commit(sm_empty);
+                it_phase ^= 1;
             }
-        } else {
-            // ---------------- epilogue: TMEM -> fp16 -> Y[t][b][c] ----------------
+        }
+    } else if (warp < 4) {
+        // ---------------- epilogue: TMEM -> fp16 -> Y[t][b][c] ----------------
+        uint32_t it_phase = 0;
+        for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+            const int m = m0 + t;
+            const int b = m / nI, i = m - b * nI;
+            if (i + w > lengths[b]) continue;
             for (int h = 0; h < halves; ++h) {
                 ptx::mbar_wait(&acc_full[h], it_phase);
                 ptx::tc_fence_after();
@@ -331,18 +390,12 @@ k_tc_splitsum(int N, int L, int Lp, int w, int m0, int cnt, const int* __restric
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&acc_empty[h]);
             }
+            it_phase ^= 1;
         }
-        it_phase ^= 1;
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 8) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-static size_t k1_smem_bytes(int N, int w) {
-    int Kpad = ((w - 1) + 15) & ~15;
-    int halves = (N + 127) / 128;
-    return (size_t)(halves * 2 + N / 64) * Kpad * 128 + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
+    if (warp == 9) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // =======================================================================================================================
@@ -358,7 +411,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                const __grid_constant__ CUtensorMap tmLC,    // LC rows, box {64, Npad}
                int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths,
                const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp,
-               float* __restrict__ alpha) {
+               float* __restrict__ alphaL, float* __restrict__ alphaR) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + kK5Stages * kK5StageBytes);
@@ -366,6 +419,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
     uint64_t* afull = empty + kK5Stages;     // [4]
     uint64_t* aempty = afull + 4;            // [4]
     uint32_t* tmem_slot = (uint32_t*)(aempty + 4);
+    float* fac = (float*)(tmem_slot + 2);    // [2][128] split factors c_j * 2^eG of the current / next span
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Npad = ((w - 1) + 15) & ~15;
@@ -464,41 +518,55 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
             }
         }
     } else if (warp >= 4) {
+        // Epilogue.  Within one launch every child row receives exactly one left-child contribution (from the span
+        // that starts where it starts) and one right-child contribution (from the span that ends where it ends);
+        // the two kinds go to separate charts, so plain read-modify-write is race-free: no atomics.
         const int q = warp & 3;
+        const int p = threadIdx.x - 128;
         uint32_t slot_phase = 0;
+        int fbuf = 0;
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI, k = i + w;
             if (k > lengths[b]) continue;
             const int* ce_seq = ce + (size_t)b * C;
-            float* al_seq = alpha + (size_t)b * C * N;
-            const int E = item_e[t];
-            const int eg = gexp[t];
+            float* facb = fac + fbuf * 128;
+            if (p < w - 1) {
+                const int us = p + 1;
+                const int sft = ce_seq[cell_off(us, L) + i] + ce_seq[cell_off(w - us, L) + i + us] - item_e[t] + gexp[t];
+                facb[p] = ldexpf(1.0f, min(max(sft, -126), 126));
+            }
+            ptx::named_bar_sync(2, 128);
             for (int u = 0; u < units; ++u) {
                 const int kind = u / halves, h = u - kind * halves;
                 ptx::mbar_wait(&afull[u], slot_phase);
                 ptx::tc_fence_after();
                 const int x = h * 128 + q * 32 + lane;          // nonterminal index of this thread's row
                 const uint32_t taddr = tmem_base + u * 128 + ((uint32_t)(q * 32) << 16);
+                float* al_seq = (kind ? alphaR : alphaL) + (size_t)b * C * N + x;
                 for (int c0 = 0; c0 < Npad; c0 += 16) {
                     float v[16];
                     ptx::tmem_ld16(taddr + c0, v);
-                    ptx::tmem_ld_wait();
+                    float* ptr[16];
+                    float old[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int us = c0 + j + 1;               // left width of this split
-                        if (us < w && x < N) {
-                            const int lcell = cell_off(us, L) + i, rcell = cell_off(w - us, L) + i + us;
-                            const int sft = ce_seq[lcell] + ce_seq[rcell] - E + eg;
-                            const float g = ldexpf(v[j], max(sft, -120));
-                            if (g != 0.f) atomicAdd(al_seq + (size_t)(kind ? rcell : lcell) * N + x, g);
-                        }
+                        const int cell = kind ? (cell_off(w - us, L) + i + us) : (cell_off(us, L) + i);
+                        const bool ok = (us < w) && (x < N);
+                        ptr[j] = ok ? al_seq + (size_t)cell * N : nullptr;
+                        old[j] = ok ? *ptr[j] : 0.f;
                     }
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (ptr[j]) *ptr[j] = fmaf(v[j], facb[c0 + j], old[j]);
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&aempty[u]);
             }
             slot_phase ^= 1;
+            fbuf ^= 1;
         }
     }
     ptx::tc_fence_before();
@@ -562,7 +630,7 @@ __global__ void k_copy_width1(int N, int L, int Lp, const int* __restrict__ leng
 // upstream gradient of one chunk:  G = alpha * 2^-e_new ;  Ghat = G * 2^wexp[a] normalised per item ; Gabs = G * 2^-8
 __global__ void k_prep_g(int N, int L, int w, int m0, int cnt, const int* __restrict__ lengths, const int* __restrict__ ce,
                          const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
-                         __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
+                         const float* __restrict__ alpha2, __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
     __shared__ float red[32];
     const int t = blockIdx.x;
     const int nI = L - w + 1;
@@ -574,7 +642,7 @@ __global__ void k_prep_g(int N, int L, int w, int m0, int cnt, const int* __rest
     if (valid) {
         const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
         const int e_new = ce[cell] - item_e[t];
-        g = ldexpf(alpha[cell * N + a], -e_new);
+        g = ldexpf(alpha[cell * N + a] + alpha2[cell * N + a], -e_new);
         gs = ldexpf(g, wexp[a]);
     }
     float mx = fabsf(gs);
@@ -602,7 +670,8 @@ struct TcCtx {
     int N, L, B, Lp, chunk, sms;
     float* cv;
     int* ce;
-    float* alpha;
+    float* alpha;    // left-child contributions (+ root seed)
+    float* alpha2;   // right-child contributions
     __half *lc, *rc, *wt, *wk, *y, *gy, *ghat, *gabs;
     int *wexp, *wbits, *item_e, *gexp;
     float* wscale;
@@ -613,7 +682,7 @@ struct TcCtx {
 static void fill_ctx(TcCtx& c, const RbnDesc* d, const WsLayout& ws, char* base, const int* lengths, cudaStream_t st) {
     c.d = d; c.ws = &ws; c.base = base; c.N = d->N; c.L = d->L; c.B = d->B; c.Lp = ws.Lp; c.chunk = ws.chunk;
     c.sms = sm_count();
-    c.cv = (float*)(base + ws.chart_val); c.ce = (int*)(base + ws.chart_exp); c.alpha = (float*)(base + ws.alpha);
+    c.cv = (float*)(base + ws.chart_val); c.ce = (int*)(base + ws.chart_exp); c.alpha = (float*)(base + ws.alpha); c.alpha2 = (float*)(base + ws.alpha2);
     c.lc = (__half*)(base + ws.lc); c.rc = (__half*)(base + ws.rc); c.wt = (__half*)(base + ws.wt);
     c.wk = (__half*)(base + ws.wk); c.y = (__half*)(base + ws.y); c.gy = (__half*)(base + ws.gy);
     c.ghat = (__half*)(base + ws.ghat); c.gabs = (__half*)(base + ws.gabs);
@@ -636,11 +705,21 @@ static int prep_weights(TcCtx& c, const float* W) {
 }
 
 static int launch_k1(TcCtx& c, int w, int m0, int cnt) {
-    size_t smem = k1_smem_bytes(c.N, w);
+    int N = c.N, L = c.L, B = c.B;
+    CUtensorMap tmLC, tmRC;
+    int rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmRC, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, 64);
+    if (rc) return rc;
+    int halves = (N + 127) / 128;
+    size_t stage_bytes = (size_t)(halves * 2 + N / 64) * 8192;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 6) stages = 6;
+    size_t smem = stages * stage_bytes + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_splitsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = cnt < 2 * c.sms ? cnt : 2 * c.sms;
-    if (smem > 110 * 1024 || grid > c.sms) grid = cnt < c.sms ? cnt : c.sms;
-    { ProfScope ps(KC_SPLITSUM, c.st); k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.lc, c.rc, c.y, c.item_e); }
+    int grid = cnt < c.sms ? cnt : c.sms;
+    { ProfScope ps(KC_SPLITSUM, c.st);
+      k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(tmLC, tmRC, N, L, c.Lp, w, m0, cnt, stages, c.lengths, c.ce, c.y, c.item_e); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
 }
@@ -711,11 +790,11 @@ static int launch_k5(TcCtx& c, int w, int m0, int cnt) {
     if (rc) return rc;
     rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, (uint32_t)Npad);
     if (rc) return rc;
-    size_t smem = (size_t)kK5Stages * kK5StageBytes + 256 + 1024;
+    size_t smem = (size_t)kK5Stages * kK5StageBytes + 256 + 1024 + 1024;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < c.sms ? cnt : c.sms;
     { ProfScope ps(KC_CHILD, c.st); k_tc_childgrad<<<grid, 256, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.item_e,
-                                              c.gexp, c.alpha); }
+                                              c.gexp, c.alpha, c.alpha2); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;
 }
@@ -728,6 +807,9 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
     int rc = prep_weights(c, W);
     if (rc) return rc;
     RBN_CUDA_CHECK(cudaMemsetAsync(c.y, 0, (size_t)c.chunk * N * N * sizeof(__half), st));
+    // TMA slabs over-read rows of cells that are never written (start >= end, beyond a sequence's length): keep them 0
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.lc, 0, (size_t)B * L * c.Lp * N * sizeof(__half), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.rc, 0, (size_t)B * (L + 1) * c.Lp * N * sizeof(__half), st));
     { ProfScope ps(KC_EMISSION, st); k_emission<<<B * L, 256, 0, st>>>(N, L, d->n_tvars, T, tokens, lengths, c.cv, c.ce); }
     RBN_LAUNCH_CHECK("k_emission");
     { ProfScope ps(KC_EMISSION, st); k_copy_width1<<<B * L, 128, 0, st>>>(N, L, c.Lp, lengths, c.cv, c.lc, c.rc); }
@@ -755,6 +837,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     int N = c.N, L = c.L, B = c.B;
     size_t C = cells_per_seq(L);
     RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha, 0, (size_t)B * C * N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha2, 0, (size_t)B * C * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gW, 0, (size_t)N * N * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
@@ -768,14 +851,14 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
             int cnt = items - m0 < c.chunk ? items - m0 : c.chunk;
             if ((rc = launch_k1(c, w, m0, cnt))) return rc;
             int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
-            { ProfScope ps(KC_PREP, st); k_prep_g<<<pg, N, 0, st>>>(N, L, w, m0, cnt, lengths, c.ce, c.item_e, c.wexp, c.alpha, c.ghat, c.gabs, c.gexp); }
+            { ProfScope ps(KC_PREP, st); k_prep_g<<<pg, N, 0, st>>>(N, L, w, m0, cnt, lengths, c.ce, c.item_e, c.wexp, c.alpha, c.alpha2, c.ghat, c.gabs, c.gexp); }
             RBN_LAUNCH_CHECK("k_prep_g");
             if ((rc = launch_k3(c, cnt))) return rc;
             if ((rc = launch_k4(c, cnt, gW))) return rc;
             if ((rc = launch_k5(c, w, m0, cnt))) return rc;
         }
     }
-    { ProfScope ps(KC_EMISSION, st); k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, c.ce, c.alpha, gT); }
+    { ProfScope ps(KC_EMISSION, st); k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, c.ce, c.alpha, c.alpha2, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");
     return RBN_OK;
 }
