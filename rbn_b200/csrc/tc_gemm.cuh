@@ -19,13 +19,14 @@ struct GemmShape {
     int m_tiles, n_tiles, k_blocks;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int EPI_SMEM>
 struct GemmSmem {
     static constexpr int A_BYTES = kBM * kBK * 2;
     static constexpr int B_BYTES = BLOCK_N * kBK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // + barriers + alignment slack
+    static constexpr int EPI_OFF = STAGES * STAGE_BYTES;          // staging tiles of a TMA-store epilogue
+    static constexpr int BAR_OFF = EPI_OFF + EPI_SMEM;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;            // + barriers + alignment slack
 };
 
 __host__ __device__ constexpr uint32_t tmem_cols_pow2(int c) {
@@ -39,8 +40,9 @@ __host__ __device__ constexpr uint32_t tmem_cols_pow2(int c) {
 // final epilogue read.  SEG == 0: plain accumulation, the two accumulators double-buffer consecutive tiles.
 template <bool A_MN, bool B_MN, int BLOCK_N, int STAGES, int SEG, class Epi>
 __global__ void __launch_bounds__(256, 1)
-k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape, Epi epi) {
-    using S = GemmSmem<BLOCK_N, STAGES>;
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape,
+          const __grid_constant__ Epi epi) {
+    using S = GemmSmem<BLOCK_N, STAGES, Epi::kSmem>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
@@ -163,7 +165,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int q = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        uint32_t flushes = 0;
+        uint32_t flushes = 0, nstore = 0;
+        uint8_t* epi_smem = smem + S::EPI_OFF;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile / shape.m_tiles, mt = tile - nt * shape.m_tiles;
@@ -189,7 +192,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
-            epi(mt, nt, q * 32 + lane, t0, t1);
+            epi(mt, nt, q * 32 + lane, t0, t1, epi_smem, nstore);
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[acc]);
             if (SEG == 0) {
@@ -198,6 +201,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 acc_phase ^= 1;
             }
         }
+        if (Epi::kSmem > 0 && threadIdx.x == 128) ptx::bulk_wait_all();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -217,7 +221,7 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t out
 template <bool A_MN, bool B_MN, int BLOCK_N, int STAGES, int SEG, class Epi>
 int launch_tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape shape, const Epi& epi, int num_sms,
                    cudaStream_t st, const char* name, int kclass) {
-    using S = GemmSmem<BLOCK_N, STAGES>;
+    using S = GemmSmem<BLOCK_N, STAGES, Epi::kSmem>;
     auto kern = k_tc_gemm<A_MN, B_MN, BLOCK_N, STAGES, SEG, Epi>;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     int tiles = shape.m_tiles * shape.n_tiles;

@@ -75,9 +75,11 @@ static int sm_count() {
 // epilogues of the generic GEMM
 // =======================================================================================================================
 struct EpiStoreF32 {   // diagnostics: D -> float [M][N]
+    static constexpr int kSmem = 0;
     float* D;
     int M, N, block_n;
-    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1) const {
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore) const {
+        (void)es; (void)nstore;
         int r = mt * kBM + row;
         for (int c0 = 0; c0 < block_n; c0 += 32) {
             float v[32];
@@ -93,6 +95,7 @@ struct EpiStoreF32 {   // diagnostics: D -> float [M][N]
 
 // K2: out[m][a] -> chart mantissas (fp32), exponents, fp16 operand copies
 struct EpiRule {
+    static constexpr int kSmem = 0;
     int N, L, Lp, w, m0, cnt;
     const int* lengths;
     const float* wscale; // W = Wt * wscale[a], wscale[a] = 2^wexp[a]
@@ -101,7 +104,8 @@ struct EpiRule {
     int* ce;
     __half* lc;
     __half* rc;
-    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1) const {
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore) const {
+        (void)es; (void)nstore;
         (void)nt;
         const int t = mt * kBM + row;
         const int nI = L - w + 1;
@@ -145,24 +149,17 @@ struct EpiRule {
     }
 };
 
-// K3: gY (fp16) [items][N*N]
+// K3: gY (fp16) [items][N*N], written as full 128-byte lines by TMA stores of smem-staged [128 x 64] tiles
 struct EpiGY {
-    __half* gy;
-    int cnt;
-    size_t ld;   // N*N
-    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1) const {
-        const int t = mt * kBM + row;
-        __half* dst = gy + (size_t)t * ld + (size_t)nt * 256;
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-            float v[32];
+    static constexpr int kSmem = 32768;
+    CUtensorMap tm;      // gY as [cnt rows][N*N cols], box {64, 128}
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore) const {
+        for (int c0 = 0; c0 < 256; c0 += 64) {
+            float v[64];
             ptx::tmem_ld32_sum(t0, t1, c0, v);
-            if (t < cnt) {
-                __align__(16) __half h[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) h[j] = __float2half_rn(v[j]);
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dst + c0 + j) = *reinterpret_cast<const uint4*>(h + j);
-            }
+            ptx::tmem_ld32_sum(t0, t1, c0 + 32, v + 32);
+            ptx::stage_store_tile(es, &tm, nt * 256 + c0, mt * kBM, row, v, nstore, 3, threadIdx.x == 128, true);
+            ++nstore;
         }
     }
 };
@@ -171,9 +168,11 @@ struct EpiGY {
 static constexpr int kGabsShift = 8;
 static constexpr int kSegBlocks = 64;   // k-blocks (of 64) per accumulation segment: K chain of 4096 -> bias ~2e-5
 struct EpiCounts {
+    static constexpr int kSmem = 0;
     float* gW;
     int N;
-    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1) const {
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore) const {
+        (void)es; (void)nstore;
         (void)nt;
         float* dst = gW + ((size_t)mt * kBM + row) * N;
         for (int c0 = 0; c0 < N; c0 += 32) {
@@ -203,6 +202,7 @@ static constexpr int kK1Threads = 320;
 
 __global__ void __launch_bounds__(kK1Threads, 1)
 k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ CUtensorMap tmRC,
+              const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYtail,
               int N, int L, int Lp, int w, int m0, int cnt, int stages, const int* __restrict__ lengths,
               const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e) {
     extern __shared__ uint8_t smem_raw[];
@@ -213,7 +213,8 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     const int a_atoms = halves * 2;            // A operand covers halves * 128 rows (zero beyond N)
     const int b_atoms = N / 64;
     const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * 8192;
-    uint8_t* tail = smem + (size_t)stages * stage_bytes;
+    uint8_t* ybuf = smem + (size_t)stages * stage_bytes;       // 2 x 16 KB staging tiles for the Y stores
+    uint8_t* tail = ybuf + 32768;
     uint64_t* tma_full = (uint64_t*)tail;         // [stages]
     uint64_t* fix_full = tma_full + stages;       // [stages]
     uint64_t* empty = fix_full + stages;          // [stages]
@@ -363,8 +364,10 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
             }
         }
     } else if (warp < 4) {
-        // ---------------- epilogue: TMEM -> fp16 -> Y[t][b][c] ----------------
-        uint32_t it_phase = 0;
+        // ---------------- epilogue: TMEM -> fp16 -> smem tile -> TMA store into Y[t][b][c] ----------------
+        uint32_t it_phase = 0, nstore = 0;
+        const int row = warp * 32 + lane;
+        const bool issuer = (threadIdx.x == 0);
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI;
@@ -372,26 +375,22 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
             for (int h = 0; h < halves; ++h) {
                 ptx::mbar_wait(&acc_full[h], it_phase);
                 ptx::tc_fence_after();
-                const int brow = h * 128 + warp * 32 + lane;
                 const uint32_t taddr = tmem_base + h * N + ((uint32_t)(warp * 32) << 16);
-                __half* dst = Y + ((size_t)t * N + brow) * N;
-                for (int c0 = 0; c0 < N; c0 += 32) {
-                    float v[32];
+                const bool tail_half = (h * 128 + 128 > N);          // only 64 valid rows (N = 64 or 192)
+                for (int c0 = 0; c0 < N; c0 += 64) {
+                    float v[64];
                     ptx::tmem_ld32(taddr + c0, v);
+                    ptx::tmem_ld32(taddr + c0 + 32, v + 32);
                     ptx::tmem_ld_wait();
-                    if (brow < N) {
-                        __align__(16) __half hv[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) hv[j] = __float2half_rn(v[j]);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dst + c0 + j) = *reinterpret_cast<const uint4*>(hv + j);
-                    }
+                    ptx::stage_store_tile(ybuf, tail_half ? &tmYtail : &tmY, c0, t * N + h * 128, row, v, nstore, 3, issuer, true);
+                    ++nstore;
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&acc_empty[h]);
             }
             it_phase ^= 1;
         }
+        if (issuer) ptx::bulk_wait_all();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -404,7 +403,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
 static constexpr int kK5Stages = 4;
 static constexpr int kK5StageBytes = 32768;   // A 16 KB + B 16 KB
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)][c], box {64,128}: A of the left-child GEMM
                const __grid_constant__ CUtensorMap tmGYm,   // same array, box {64,64}: MN-major A of the right-child GEMM
                const __grid_constant__ CUtensorMap tmRC,    // RC rows, box {64, Npad}
@@ -419,7 +418,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
     uint64_t* afull = empty + kK5Stages;     // [4]
     uint64_t* aempty = afull + 4;            // [4]
     uint32_t* tmem_slot = (uint32_t*)(aempty + 4);
-    float* fac = (float*)(tmem_slot + 2);    // [2][128] split factors c_j * 2^eG of the current / next span
+    float* fac = (float*)(tmem_slot + 2);    // [2 groups][2][128] split factors c_j * 2^eG of the current / next span
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Npad = ((w - 1) + 15) & ~15;
@@ -521,8 +520,10 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
         // Epilogue.  Within one launch every child row receives exactly one left-child contribution (from the span
         // that starts where it starts) and one right-child contribution (from the span that ends where it ends);
         // the two kinds go to separate charts, so plain read-modify-write is race-free: no atomics.
+        // Two groups of four warps (4-7, 8-11) take alternate units, so two read-modify-write streams are in flight.
         const int q = warp & 3;
-        const int p = threadIdx.x - 128;
+        const int grp = (warp - 4) >> 2;
+        const int p = (threadIdx.x - 128) & 127;
         uint32_t slot_phase = 0;
         int fbuf = 0;
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
@@ -530,37 +531,36 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
             const int b = m / nI, i = m - b * nI, k = i + w;
             if (k > lengths[b]) continue;
             const int* ce_seq = ce + (size_t)b * C;
-            float* facb = fac + fbuf * 128;
+            float* facb = fac + (grp * 2 + fbuf) * 128;
             if (p < w - 1) {
                 const int us = p + 1;
                 const int sft = ce_seq[cell_off(us, L) + i] + ce_seq[cell_off(w - us, L) + i + us] - item_e[t] + gexp[t];
                 facb[p] = ldexpf(1.0f, min(max(sft, -126), 126));
             }
-            ptx::named_bar_sync(2, 128);
-            for (int u = 0; u < units; ++u) {
+            ptx::named_bar_sync(2 + grp, 128);
+            for (int u = grp; u < units; u += 2) {
                 const int kind = u / halves, h = u - kind * halves;
                 ptx::mbar_wait(&afull[u], slot_phase);
                 ptx::tc_fence_after();
                 const int x = h * 128 + q * 32 + lane;          // nonterminal index of this thread's row
                 const uint32_t taddr = tmem_base + u * 128 + ((uint32_t)(q * 32) << 16);
                 float* al_seq = (kind ? alphaR : alphaL) + (size_t)b * C * N + x;
-                for (int c0 = 0; c0 < Npad; c0 += 16) {
-                    float v[16];
-                    ptx::tmem_ld16(taddr + c0, v);
-                    float* ptr[16];
-                    float old[16];
+                for (int c0 = 0; c0 < Npad; c0 += 32) {
+                    float v[32];
+                    ptx::tmem_ld32(taddr + c0, v);               // Npad is a multiple of 16: columns past it are never used
+                    int cell[32];
+                    float old[32];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 32; ++j) {
                         const int us = c0 + j + 1;               // left width of this split
-                        const int cell = kind ? (cell_off(w - us, L) + i + us) : (cell_off(us, L) + i);
                         const bool ok = (us < w) && (x < N);
-                        ptr[j] = ok ? al_seq + (size_t)cell * N : nullptr;
-                        old[j] = ok ? *ptr[j] : 0.f;
+                        cell[j] = ok ? (kind ? (cell_off(w - us, L) + i + us) : (cell_off(us, L) + i)) : -1;
+                        old[j] = ok ? al_seq[(size_t)cell[j] * N] : 0.f;
                     }
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (ptr[j]) *ptr[j] = fmaf(v[j], facb[c0 + j], old[j]);
+                    for (int j = 0; j < 32; ++j)
+                        if (cell[j] >= 0) al_seq[(size_t)cell[j] * N] = fmaf(v[j], facb[c0 + j], old[j]);
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&aempty[u]);
@@ -711,15 +711,20 @@ static int launch_k1(TcCtx& c, int w, int m0, int cnt) {
     if (rc) return rc;
     rc = make_tmap_2d(&tmRC, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, 64);
     if (rc) return rc;
+    CUtensorMap tmY, tmYtail;
+    rc = make_tmap_2d(&tmY, c.y, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmYtail, c.y, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
+    if (rc) return rc;
     int halves = (N + 127) / 128;
     size_t stage_bytes = (size_t)(halves * 2 + N / 64) * 8192;
-    int stages = (int)((200 * 1024) / stage_bytes);
+    int stages = (int)((232448 - 2048 - 32768) / stage_bytes);
     if (stages > 6) stages = 6;
-    size_t smem = stages * stage_bytes + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
+    size_t smem = stages * stage_bytes + 32768 /*Y staging*/ + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_splitsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < c.sms ? cnt : c.sms;
     { ProfScope ps(KC_SPLITSUM, c.st);
-      k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(tmLC, tmRC, N, L, c.Lp, w, m0, cnt, stages, c.lengths, c.ce, c.y, c.item_e); }
+      k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(tmLC, tmRC, tmY, tmYtail, N, L, c.Lp, w, m0, cnt, stages, c.lengths, c.ce, c.y, c.item_e); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
 }
@@ -752,7 +757,9 @@ static int launch_k3(TcCtx& c, int cnt) {
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, c.wk, (uint64_t)c.N, NN, (uint64_t)c.N * 2, 256);
     if (rc) return rc;
-    EpiGY epi{c.gy, cnt, NN};
+    EpiGY epi;
+    rc = make_tmap_2d(&epi.tm, c.gy, NN, (uint64_t)cnt, NN * 2, 128);
+    if (rc) return rc;
     GemmShape shape{(cnt + 127) / 128, (int)(NN / 256), c.N / 64};
     return launch_tc_gemm<false, false, 256, 4, 0, EpiGY>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<gY>", KC_GY);
 }
@@ -790,10 +797,10 @@ static int launch_k5(TcCtx& c, int w, int m0, int cnt) {
     if (rc) return rc;
     rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, (uint32_t)Npad);
     if (rc) return rc;
-    size_t smem = (size_t)kK5Stages * kK5StageBytes + 256 + 1024 + 1024;
+    size_t smem = (size_t)kK5Stages * kK5StageBytes + 256 + 2048 + 1024;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < c.sms ? cnt : c.sms;
-    { ProfScope ps(KC_CHILD, c.st); k_tc_childgrad<<<grid, 256, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.item_e,
+    { ProfScope ps(KC_CHILD, c.st); k_tc_childgrad<<<grid, 384, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.item_e,
                                               c.gexp, c.alpha, c.alpha2); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;

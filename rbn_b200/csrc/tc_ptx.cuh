@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace rbn {
@@ -48,6 +49,39 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+
+// smem (128-byte swizzled tile) -> global, bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Epilogue helper: 128 threads (thread <-> tile row) stage a [128 x 64] fp16 tile (64 fp32 values per thread) in a
+// 16 KB 128-byte-swizzled buffer and one of them TMA-stores it: every global write is a full 128-byte line.
+// `nstore` counts the stores issued so far by this CTA (selects the ping-pong buffer).
+__device__ __forceinline__ void stage_store_tile(uint8_t* bufs, const CUtensorMap* tm, int x, int y, int row,
+                                                 const float* v, uint32_t nstore, uint32_t bar_id, bool issuer, bool active) {
+    uint8_t* buf = bufs + (nstore & 1) * 16384;
+    if (issuer) bulk_wait_read<1>();                 // the store that used this buffer two tiles ago has been read
+    named_bar_sync(bar_id, 128);
+    uint4 pk[8];
+    __half2* h = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(buf + row * 128 + ((c ^ (row & 7)) << 4)) = pk[c];
+    fence_proxy_async_smem();
+    named_bar_sync(bar_id, 128);
+    if (issuer && active) {
+        tma_store_2d(tm, buf, x, y);
+        bulk_commit();
+    }
 }
 
 // ---- tcgen05: tensor memory -------------------------------------------------------------------------------------------
