@@ -280,9 +280,12 @@ def run_ours(args, wl):
             allreduce_grads([p.grad for p in params])
         return float(loss)          # device -> host read of the step's result
 
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    ms_e2e, _ = timed(e2e_step, args.steps)
+    if args.skip_e2e:
+        ms_e2e = float('nan')
+    else:
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        ms_e2e, _ = timed(e2e_step, args.steps)
     h2d = tok_pin.numel() * 4 + len_pin.numel() * 4
     d2h = 8
 
@@ -304,7 +307,7 @@ def run_ours(args, wl):
                     step_tflops=f_step / (ms_step * 1e-3) / 1e12, step_frac=f_step / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
                     kernels_ms_per_step={k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]})
     launches = int(sum(v[1] for v in prof.values()))
-    cpu_v, cpu_t, cpu_samp, cores = cpu_sample(wl) if world == 1 else (None, None, None, None)
+    cpu_v, cpu_t, cpu_samp, cores = cpu_sample(wl) if (world == 1 and not args.skip_cpu) else (None, None, None, None)
     line = dict(metric="inside+outside sequences/sec" if wl["outside"] else "inside sequences/sec",
                 value=world * B / (ms_step * 1e-3), unit="seq/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
@@ -332,6 +335,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="sequences per GPU (default: the workload's)")
     ap.add_argument("--chunk", type=int, default=0, help="spans per launch group (0 = library default)")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the end-to-end arm")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the CPU baseline")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -202,6 +202,7 @@ static constexpr int kK1Threads = 320;
 
 __global__ void __launch_bounds__(kK1Threads, 1)
 k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ CUtensorMap tmRC,
+              const __grid_constant__ CUtensorMap tmLC1, const __grid_constant__ CUtensorMap tmRC1,   // second K-slab (rows = Kpad - 64)
               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYtail,
               int N, int L, int Lp, int w, int m0, int cnt, int stages, const int* __restrict__ lengths,
               const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e) {
@@ -270,10 +271,12 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sL = smem + (size_t)stage * stage_bytes;
                     uint8_t* sR = sL + (size_t)a_atoms * 8192;
-                    ptx::mbar_expect_tx(&tma_full[stage], (uint32_t)b_atoms * 2 * 8192);
+                    // the box of this slab holds exactly Ks = min(64, Kpad - 64 part) chart rows (its atom stays 8 KB apart)
+                    const int Ks = min(64, Kpad - part * 64);
+                    ptx::mbar_expect_tx(&tma_full[stage], (uint32_t)b_atoms * 2 * (uint32_t)Ks * 128);
                     for (int a = 0; a < b_atoms; ++a) {
-                        ptx::tma_load_2d(sL + a * 8192, &tmLC, &tma_full[stage], a * 64, lc_row + part * 64);
-                        ptx::tma_load_2d(sR + a * 8192, &tmRC, &tma_full[stage], a * 64, rc_row + part * 64);
+                        ptx::tma_load_2d(sL + a * 8192, part ? &tmLC1 : &tmLC, &tma_full[stage], a * 64, lc_row + part * 64);
+                        ptx::tma_load_2d(sR + a * 8192, part ? &tmRC1 : &tmRC, &tma_full[stage], a * 64, rc_row + part * 64);
                     }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -478,6 +481,23 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                         if (++stage == kK5Stages) { stage = 0; phase ^= 1; }
                     }
                 }
+            }
+        }
+    } else if (warp == 3) {
+        // L2 prefetch of the chart rows the epilogue will read-modify-write, one span ahead of it
+        for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+            const int m = m0 + t;
+            const int b = m / nI, i = m - b * nI, k = i + w;
+            if (k > lengths[b]) continue;
+            const int lines_per_row = N / 32;                    // 128-byte lines per chart row
+            const int total = 2 * (w - 1) * lines_per_row;
+            for (int idx = lane; idx < total; idx += 32) {
+                const int kind = idx / ((w - 1) * lines_per_row);
+                const int rem = idx - kind * (w - 1) * lines_per_row;
+                const int us = rem / lines_per_row + 1, ln = rem - (us - 1) * lines_per_row;
+                const int cell = kind ? (cell_off(w - us, L) + i + us) : (cell_off(us, L) + i);
+                const float* ptr = (kind ? alphaR : alphaL) + ((size_t)b * C + cell) * N + ln * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
             }
         }
     } else if (warp == 1) {
@@ -706,10 +726,16 @@ static int prep_weights(TcCtx& c, const float* W) {
 
 static int launch_k1(TcCtx& c, int w, int m0, int cnt) {
     int N = c.N, L = c.L, B = c.B;
-    CUtensorMap tmLC, tmRC;
-    int rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, 64);
+    const int Kpad = ((w - 1) + 15) & ~15;
+    const uint32_t rows0 = (uint32_t)(Kpad < 64 ? Kpad : 64), rows1 = (uint32_t)(Kpad > 64 ? Kpad - 64 : 16);
+    CUtensorMap tmLC, tmRC, tmLC1, tmRC1;
+    int rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, rows0);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmRC, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, 64);
+    rc = make_tmap_2d(&tmRC, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, rows0);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmLC1, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, rows1);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmRC1, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, rows1);
     if (rc) return rc;
     CUtensorMap tmY, tmYtail;
     rc = make_tmap_2d(&tmY, c.y, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
@@ -724,7 +750,7 @@ static int launch_k1(TcCtx& c, int w, int m0, int cnt) {
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_splitsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < c.sms ? cnt : c.sms;
     { ProfScope ps(KC_SPLITSUM, c.st);
-      k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(tmLC, tmRC, tmY, tmYtail, N, L, c.Lp, w, m0, cnt, stages, c.lengths, c.ce, c.y, c.item_e); }
+      k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L, c.Lp, w, m0, cnt, stages, c.lengths, c.ce, c.y, c.item_e); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
 }
