@@ -118,6 +118,23 @@ int rbn_export_chart(const RbnDesc* desc, const int32_t* lengths,
  * is NOT detected on device; `bad` (device int32, may be NULL) is set to the number of such groups. */
 int rbn_lognormalize(float* log_p, int64_t group_size, int64_t groups, int32_t* bad, void* stream);
 
+/* ---- continuous RBN with multivariate-normal transitions (BASELINE config 4) ------------------------------------
+ * beta_{i:k}(x) = exp(logc) N(x; mu, Sigma).  Terminal p(y|x) = N(y; x, cov_term); binary transition
+ * p(x_l, x_r | x) = N(x_l; x, cov_left) N(x_r; x, cov_right); per split the children are multiplied as
+ * rbnet.multivariate_normal.PairwiseProduct does (/root/reference/rbnet/multivariate_normal.py:339-396), the splits
+ * of a span are moment-matched as ApproximateMixture does (:502-550); prior N(x; prior_mean, prior_cov).  The
+ * reference ships only these primitives, not the RBN bricks; the composition is the one of
+ * oracle/gauss_oracle.py.  All arrays float64 on the device; y [B][L][D]; covariances [D][D] row-major symmetric;
+ * log_struct[2] = {log p_S(terminal), log p_S(binary)}; D in {1,2,3,4,8}. */
+typedef struct RbnGaussDesc {
+    int32_t D, B, L, flags;
+} RbnGaussDesc;
+size_t rbn_gauss_workspace_bytes(const RbnGaussDesc* desc);
+int rbn_gauss_inside_forward(const RbnGaussDesc* desc, const double* y, const int32_t* lengths, const double* cov_term,
+                             const double* cov_left, const double* cov_right, const double* prior_mean,
+                             const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
+                             double* logZ, void* stream);
+
 /* Launch accounting and optional per-kernel timing.  The library counts every kernel it launches, by class; with
  * rbn_profile_enable(1) it also brackets each launch with CUDA events on the caller's stream.  rbn_profile_read
  * synchronises the device and returns, per class, the summed event time (ms) and the launch count since the last

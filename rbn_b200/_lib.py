@@ -42,6 +42,9 @@ _SIGNATURES = {
                                            _P, _P, _P, _P, _P]),
     "rbn_export_chart": (ctypes.c_int, [ctypes.POINTER(RbnDesc), _P, _P, ctypes.c_size_t, ctypes.c_int32, _P, _P]),
     "rbn_lognormalize": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, _P, _P]),
+    "rbn_gauss_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(GaussDesc)]),
+    "rbn_gauss_inside_forward": (ctypes.c_int, [ctypes.POINTER(GaussDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                                ctypes.c_size_t, _P, _P]),
     "rbn_profile_enable": (ctypes.c_int, [ctypes.c_int32]),
     "rbn_profile_read": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
     "rbn_debug_gemm": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_int32,

@@ -26,6 +26,9 @@ int tc_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float
 int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
                 const int*, const float*, float*, float*, float*, cudaStream_t);
 int debug_gemm(int, int, int, const __half*, const __half*, float*, int, int, int, cudaStream_t);
+size_t gauss_workspace_bytes(int, int, int);
+int gauss_forward(int, int, int, const double*, const int*, const double*, const double*, const double*, const double*,
+                  const double*, const double*, double*, double*, cudaStream_t);
 
 // ---- profiling -------------------------------------------------------------------------------------------------------
 static std::mutex g_prof_mu;
@@ -216,6 +219,36 @@ int rbn_debug_gemm(int32_t M, int32_t N, int32_t K, const void* A, const void* B
         return RBN_E_BADARG;
     }
     return debug_gemm(M, N, K, (const __half*)A, (const __half*)B, D, a_mn, b_mn, segmented, (cudaStream_t)stream);
+}
+
+static bool gdesc_ok(const RbnGaussDesc* d) {
+    if (!d || d->D < 1 || d->D > 8 || d->B < 1 || d->L < 1 || d->flags != 0) {
+        set_error("bad Gaussian descriptor");
+        return false;
+    }
+    return true;
+}
+
+size_t rbn_gauss_workspace_bytes(const RbnGaussDesc* desc) {
+    if (!gdesc_ok(desc)) return 0;
+    return 2 * gauss_workspace_bytes(desc->D, desc->B, desc->L);     // chart + adjoint chart
+}
+
+int rbn_gauss_inside_forward(const RbnGaussDesc* desc, const double* y, const int32_t* lengths, const double* cov_term,
+                             const double* cov_left, const double* cov_right, const double* prior_mean,
+                             const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
+                             double* logZ, void* stream) {
+    if (!gdesc_ok(desc)) return RBN_E_BADARG;
+    if (!y || !lengths || !cov_term || !cov_left || !cov_right || !prior_mean || !prior_cov || !log_struct || !workspace || !logZ) {
+        set_error("rbn_gauss_inside_forward: NULL pointer argument");
+        return RBN_E_BADARG;
+    }
+    if (workspace_bytes < rbn_gauss_workspace_bytes(desc)) {
+        set_error("Gaussian workspace too small");
+        return RBN_E_WORKSPACE;
+    }
+    return gauss_forward(desc->D, desc->B, desc->L, y, lengths, cov_term, cov_left, cov_right, prior_mean, prior_cov,
+                         log_struct, (double*)workspace, logZ, (cudaStream_t)stream);
 }
 
 int rbn_profile_enable(int32_t on) {
