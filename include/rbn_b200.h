@@ -135,6 +135,16 @@ int rbn_gauss_inside_forward(const RbnGaussDesc* desc, const double* y, const in
                              const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
                              double* logZ, void* stream);
 
+/* Outside pass of the Gaussian RBN (reverse mode through the moment matching and the pairwise products; the reference
+ * would obtain it from torch.autograd).  Must follow rbn_gauss_inside_forward on the same workspace.  Outputs are
+ * OVERWRITTEN with d(sum_b coef[b] log Z_b)/d(argument); covariance gradients are symmetrised. g_y is [B][L][D]. */
+int rbn_gauss_inside_backward(const RbnGaussDesc* desc, const double* y, const int32_t* lengths, const double* cov_term,
+                              const double* cov_left, const double* cov_right, const double* prior_mean,
+                              const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
+                              const double* coef, double* g_y, double* g_cov_term, double* g_cov_left,
+                              double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
+                              void* stream);
+
 /* Launch accounting and optional per-kernel timing.  The library counts every kernel it launches, by class; with
  * rbn_profile_enable(1) it also brackets each launch with CUDA events on the caller's stream.  rbn_profile_read
  * synchronises the device and returns, per class, the summed event time (ms) and the launch count since the last

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "rbn_gauss_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(GaussDesc)]),
     "rbn_gauss_inside_forward": (ctypes.c_int, [ctypes.POINTER(GaussDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                                 ctypes.c_size_t, _P, _P]),
+    "rbn_gauss_inside_backward": (ctypes.c_int, [ctypes.POINTER(GaussDesc)] + [_P] * 9 + [ctypes.c_size_t] + [_P] * 9),
     "rbn_profile_enable": (ctypes.c_int, [ctypes.c_int32]),
     "rbn_profile_read": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
     "rbn_debug_gemm": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_int32,

@@ -27,6 +27,8 @@ int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const floa
                 const int*, const float*, float*, float*, float*, cudaStream_t);
 int debug_gemm(int, int, int, const __half*, const __half*, float*, int, int, int, cudaStream_t);
 size_t gauss_workspace_bytes(int, int, int);
+int gauss_backward(int, int, int, const int*, const double*, const double*, const double*, const double*, const double*,
+                   double*, const double*, double*, double*, double*, double*, double*, double*, double*, cudaStream_t);
 int gauss_forward(int, int, int, const double*, const int*, const double*, const double*, const double*, const double*,
                   const double*, const double*, double*, double*, cudaStream_t);
 
@@ -249,6 +251,30 @@ int rbn_gauss_inside_forward(const RbnGaussDesc* desc, const double* y, const in
     }
     return gauss_forward(desc->D, desc->B, desc->L, y, lengths, cov_term, cov_left, cov_right, prior_mean, prior_cov,
                          log_struct, (double*)workspace, logZ, (cudaStream_t)stream);
+}
+
+int rbn_gauss_inside_backward(const RbnGaussDesc* desc, const double* y, const int32_t* lengths, const double* cov_term,
+                              const double* cov_left, const double* cov_right, const double* prior_mean,
+                              const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
+                              const double* coef, double* g_y, double* g_cov_term, double* g_cov_left,
+                              double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
+                              void* stream) {
+    (void)y; (void)cov_term; (void)log_struct;
+    if (!gdesc_ok(desc)) return RBN_E_BADARG;
+    if (!lengths || !cov_left || !cov_right || !prior_mean || !prior_cov || !workspace || !coef || !g_y || !g_cov_term ||
+        !g_cov_left || !g_cov_right || !g_prior_mean || !g_prior_cov || !g_log_struct) {
+        set_error("rbn_gauss_inside_backward: NULL pointer argument");
+        return RBN_E_BADARG;
+    }
+    if (workspace_bytes < rbn_gauss_workspace_bytes(desc)) {
+        set_error("Gaussian workspace too small");
+        return RBN_E_WORKSPACE;
+    }
+    double* chart = (double*)workspace;
+    double* adj = (double*)((char*)workspace + gauss_workspace_bytes(desc->D, desc->B, desc->L));
+    return gauss_backward(desc->D, desc->B, desc->L, lengths, cov_left, cov_right, prior_mean, prior_cov, chart, adj, coef,
+                          g_y, g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct,
+                          (cudaStream_t)stream);
 }
 
 int rbn_profile_enable(int32_t on) {

@@ -260,3 +260,331 @@ int gauss_forward(int D, int B, int L, const double* y, const int* lengths, cons
 }
 
 }  // namespace rbn
+
+// =====================================================================================================================
+// outside pass of the Gaussian RBN: reverse-mode through moment matching and the pairwise products
+// =====================================================================================================================
+// Adjoint chart cell = [a_bar | mu_bar[D] | Sigma_bar[D][D]] of sum_b coef_b log Z_b.  One warp per span, one lane per
+// split; the D x D work matrices of a lane live in shared memory, lane-interleaved (entry e of lane t at [e*32 + t]).
+namespace rbn {
+
+#define SMAT(M, r, c) M[((r) * D + (c)) * 32 + lane]
+
+template <int D>
+__global__ void k_gauss_bwd_root(int L, int B, const int* __restrict__ lengths, const double* __restrict__ prior_mean,
+                                 const double* __restrict__ prior_cov, const double* __restrict__ chart,
+                                 const double* __restrict__ coef, double* __restrict__ adj,
+                                 double* __restrict__ g_prior_mean, double* __restrict__ g_prior_cov) {
+    constexpr int G = GCell<D>::kStride;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double c = coef[b];
+    if (c == 0.0) return;
+    const int n = lengths[b];
+    const size_t cidx = (size_t)b * cells_per_seq(L) + cell_off(n, L);
+    const double* cell = chart + cidx * G;
+    double* out = adj + cidx * G;
+    double S[D][D], d[D], z[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        d[a] = cell[1 + a] - prior_mean[a];
+        z[a] = d[a];
+#pragma unroll
+        for (int e = 0; e < D; ++e) S[a][e] = cell[1 + D + a * D + e] + prior_cov[a * D + e];
+    }
+    chol_inplace<D>(S);
+    chol_solve<D>(S, z);
+    out[0] += c;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        out[1 + a] += -c * z[a];
+        atomicAdd(&g_prior_mean[a], c * z[a]);
+    }
+#pragma unroll
+    for (int e = 0; e < D; ++e) {          // column e of P = S^-1
+        double x[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) x[a] = (a == e) ? 1.0 : 0.0;
+        chol_solve<D>(S, x);
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            const double sb = 0.5 * c * (z[a] * z[e] - x[a]);
+            out[1 + D + a * D + e] += sb;
+            atomicAdd(&g_prior_cov[a * D + e], sb);
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(32)
+k_gauss_bwd_diag(int L, int w, const int* __restrict__ lengths, const double* __restrict__ cov_left,
+                 const double* __restrict__ cov_right, const double* __restrict__ chart, double* __restrict__ adj,
+                 double* __restrict__ g_cov_left, double* __restrict__ g_cov_right, double* __restrict__ g_log_struct) {
+    constexpr int G = GCell<D>::kStride;
+    constexpr int DD = D * D;
+    extern __shared__ double sm[];
+    double* mA = sm;                 // lane-interleaved work matrices
+    double* mP = mA + DD * 32;
+    double* mK = mP + DD * 32;
+    double* mQ = mK + DD * 32;
+    double* mAb = mQ + DD * 32;
+    double* mSb = mAb + DD * 32;
+    double* lw = mSb + DD * 32;      // [L]
+    double* ob = lw + L;             // [L]  omega_bar
+    double* par = ob + L;            // parent: [0] a_bar, [1..D] mu_bar_tot, [1+D..] M2_bar (symmetric)
+    double* pmu = par + G;           // parent mean [D]
+    double* cL = pmu + D;            // [DD]
+    double* cR = cL + DD;            // [DD]
+    double* gL = cR + DD;            // [DD] accumulators
+    double* gR = gL + DD;            // [DD]
+    const int lane = threadIdx.x;
+    const int nI = L - w + 1;
+    const int b = blockIdx.x / nI, i = blockIdx.x % nI;
+    if (i + w > lengths[b]) return;
+    const size_t seq_off = (size_t)b * cells_per_seq(L);
+    const double* seq = chart + seq_off * G;
+    double* aseq = adj + seq_off * G;
+    const size_t pcell = cell_off(w, L) + i;
+    const double abar = aseq[pcell * G];
+    // skip spans that no gradient reaches
+    {
+        double any = 0.0;
+        for (int t = lane; t < G; t += 32) any += fabs(aseq[pcell * G + t]);
+        for (int o = 16; o > 0; o >>= 1) any += __shfl_xor_sync(0xffffffffu, any, o);
+        if (any == 0.0) return;
+    }
+    for (int t = lane; t < DD; t += 32) {
+        cL[t] = cov_left[t];
+        cR[t] = cov_right[t];
+        gL[t] = 0.0;
+        gR[t] = 0.0;
+        const int a = t / D, c = t % D;
+        par[1 + D + t] = 0.5 * (aseq[pcell * G + 1 + D + a * D + c] + aseq[pcell * G + 1 + D + c * D + a]);
+    }
+    if (lane < D) pmu[lane] = seq[pcell * G + 1 + lane];
+    __syncwarp();
+    if (lane < D) {
+        double s = aseq[pcell * G + 1 + lane];
+        for (int c = 0; c < D; ++c) s -= 2.0 * par[1 + D + lane * D + c] * pmu[c];
+        par[1 + lane] = s;             // mu_bar_tot = mu_bar - 2 Sigma_bar mu
+    }
+    if (lane == 0) {
+        par[0] = abar;
+        atomicAdd(&g_log_struct[1], abar);
+    }
+    __syncwarp();
+
+    double mean[D], Areg[D][D], cov[D][D];
+    // pass 1: log weights and omega_bar
+    double mx = -INFINITY;
+    for (int u = 1 + lane; u < w; u += 32) {
+        const double* l = seq + (size_t)(cell_off(u, L) + i) * G;
+        const double* r = seq + (size_t)(cell_off(w - u, L) + i + u) * G;
+        const double v = split_product<D, true>(l, r, cL, cR, mean, Areg, cov);
+        lw[u] = v;
+        mx = fmax(mx, v);
+        double o = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            o += par[1 + a] * mean[a];
+#pragma unroll
+            for (int c = 0; c < D; ++c) o += par[1 + D + a * D + c] * (cov[a][c] + mean[a] * mean[c]);
+        }
+        ob[u] = o;
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double se = 0.0;
+    for (int u = 1 + lane; u < w; u += 32) se += exp(lw[u] - mx);
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const double log_norm = mx + log(se);
+    double swo = 0.0;
+    for (int u = 1 + lane; u < w; u += 32) swo += exp(lw[u] - log_norm) * ob[u];
+    for (int o = 16; o > 0; o >>= 1) swo += __shfl_xor_sync(0xffffffffu, swo, o);
+
+    // pass 2: adjoints of every split
+    for (int u = 1 + lane; u < w; u += 32) {
+        const size_t lcell = cell_off(u, L) + i, rcell = cell_off(w - u, L) + i + u;
+        const double* l = seq + lcell * G;
+        const double* r = seq + rcell * G;
+        const double om = exp(lw[u] - log_norm);
+        const double lwb = om * (ob[u] - swo + abar);
+        // recompute A, S -> P = S^-1, z, m
+        double S[D][D], d[D], z[D], m[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            d[a] = r[1 + a] - l[1 + a];
+            z[a] = d[a];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const double av = l[1 + D + a * D + c] + cL[a * D + c];
+                SMAT(mA, a, c) = av;
+                S[a][c] = av + r[1 + D + a * D + c] + cR[a * D + c];
+            }
+        }
+        chol_inplace<D>(S);
+        chol_solve<D>(S, z);
+#pragma unroll
+        for (int e = 0; e < D; ++e) {
+            double x[D];
+#pragma unroll
+            for (int a = 0; a < D; ++a) x[a] = (a == e) ? 1.0 : 0.0;
+            chol_solve<D>(S, x);
+#pragma unroll
+            for (int a = 0; a < D; ++a) SMAT(mP, a, e) = x[a];
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double s = l[1 + a];
+#pragma unroll
+            for (int c = 0; c < D; ++c) s += SMAT(mA, a, c) * z[c];
+            m[a] = s;
+        }
+        // K = A P
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) s += SMAT(mA, a, k) * SMAT(mP, k, c);
+                SMAT(mK, a, c) = s;
+            }
+        // Q = M2_bar K   (C_bar = om * M2_bar)
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) s += par[1 + D + a * D + k] * SMAT(mK, k, c);
+                SMAT(mQ, a, c) = s;
+            }
+        // m_bar = om (mu_bar_tot + 2 M2_bar m);  z_bar = A m_bar;  pz = P z_bar;  d_bar = -lwb z + pz
+        double mb[D], zb[D], pz[D], db[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double s = par[1 + a];
+#pragma unroll
+            for (int c = 0; c < D; ++c) s += 2.0 * par[1 + D + a * D + c] * m[c];
+            mb[a] = om * s;
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) s += SMAT(mA, a, c) * mb[c];
+            zb[a] = s;
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) s += SMAT(mP, a, c) * zb[c];
+            pz[a] = s;
+            db[a] = -lwb * z[a] + s;
+        }
+        // S_bar = 1/2 lwb (z z^T - P) - pz z^T + om K^T Q ;  A_bar = mb z^T + om (M2_bar - Q - Q^T) + S_bar
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double ktq = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) ktq += SMAT(mK, k, a) * SMAT(mQ, k, c);
+                const double sb = 0.5 * lwb * (z[a] * z[c] - SMAT(mP, a, c)) - pz[a] * z[c] + om * ktq;
+                SMAT(mSb, a, c) = sb;
+                SMAT(mAb, a, c) = mb[a] * z[c] + om * (par[1 + D + a * D + c] - SMAT(mQ, a, c) - SMAT(mQ, c, a)) + sb;
+            }
+        // scatter: children adjoints and parameter gradients (symmetrised)
+        double* la = aseq + lcell * G;
+        double* ra = aseq + rcell * G;
+        atomicAdd(&la[0], lwb);
+        atomicAdd(&ra[0], lwb);
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            atomicAdd(&la[1 + a], mb[a] - db[a]);
+            atomicAdd(&ra[1 + a], db[a]);
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const double sa = 0.5 * (SMAT(mAb, a, c) + SMAT(mAb, c, a));
+                const double ss = 0.5 * (SMAT(mSb, a, c) + SMAT(mSb, c, a));
+                atomicAdd(&la[1 + D + a * D + c], sa);
+                atomicAdd(&ra[1 + D + a * D + c], ss);
+                atomicAdd(&gL[a * D + c], sa);
+                atomicAdd(&gR[a * D + c], ss);
+            }
+        }
+    }
+    __syncwarp();
+    for (int t = lane; t < DD; t += 32) {
+        if (gL[t] != 0.0) atomicAdd(&g_cov_left[t], gL[t]);
+        if (gR[t] != 0.0) atomicAdd(&g_cov_right[t], gR[t]);
+    }
+}
+
+template <int D>
+__global__ void k_gauss_bwd_width1(int L, const int* __restrict__ lengths, const double* __restrict__ adj,
+                                   double* __restrict__ g_y, double* __restrict__ g_cov_term,
+                                   double* __restrict__ g_log_struct) {
+    constexpr int G = GCell<D>::kStride;
+    int b = blockIdx.x / L, i = blockIdx.x % L;
+    if (i >= lengths[b]) return;
+    const double* cell = adj + ((size_t)b * cells_per_seq(L) + i) * G;
+    for (int t = threadIdx.x; t < G; t += blockDim.x) {
+        const double v = cell[t];
+        if (t == 0) { if (v != 0.0) atomicAdd(&g_log_struct[0], v); }
+        else if (t <= D) g_y[((size_t)b * L + i) * D + (t - 1)] = v;
+        else {
+            const int a = (t - 1 - D) / D, c = (t - 1 - D) % D;
+            const double s = 0.5 * (v + cell[1 + D + c * D + a]);
+            if (s != 0.0) atomicAdd(&g_cov_term[a * D + c], s);
+        }
+    }
+}
+
+template <int D>
+static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_left, const double* cov_right,
+                            const double* prior_mean, const double* prior_cov, const double* chart, double* adj,
+                            const double* coef, double* g_y, double* g_cov_term, double* g_cov_left,
+                            double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
+                            cudaStream_t st) {
+    constexpr int G = GCell<D>::kStride;
+    constexpr int DD = D * D;
+    RBN_CUDA_CHECK(cudaMemsetAsync(adj, 0, (size_t)B * cells_per_seq(L) * G * sizeof(double), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(g_y, 0, (size_t)B * L * D * sizeof(double), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(g_cov_term, 0, DD * sizeof(double), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(g_cov_left, 0, DD * sizeof(double), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(g_cov_right, 0, DD * sizeof(double), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(g_prior_mean, 0, D * sizeof(double), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(g_prior_cov, 0, DD * sizeof(double), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(g_log_struct, 0, 2 * sizeof(double), st));
+    { ProfScope ps(KC_OTHER, st);
+      k_gauss_bwd_root<D><<<(B + 63) / 64, 64, 0, st>>>(L, B, lengths, prior_mean, prior_cov, chart, coef, adj, g_prior_mean, g_prior_cov); }
+    RBN_LAUNCH_CHECK("k_gauss_bwd_root");
+    size_t smem = ((size_t)6 * DD * 32 + 2 * L + G + D + 4 * DD) * sizeof(double);
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(k_gauss_bwd_diag<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int w = L; w >= 2; --w) {
+        { ProfScope ps(KC_OTHER, st);
+          k_gauss_bwd_diag<D><<<B * (L - w + 1), 32, smem, st>>>(L, w, lengths, cov_left, cov_right, chart, adj, g_cov_left, g_cov_right, g_log_struct); }
+        RBN_LAUNCH_CHECK("k_gauss_bwd_diag");
+    }
+    { ProfScope ps(KC_EMISSION, st); k_gauss_bwd_width1<D><<<B * L, 96, 0, st>>>(L, lengths, adj, g_y, g_cov_term, g_log_struct); }
+    RBN_LAUNCH_CHECK("k_gauss_bwd_width1");
+    return RBN_OK;
+}
+
+int gauss_backward(int D, int B, int L, const int* lengths, const double* cov_left, const double* cov_right,
+                   const double* prior_mean, const double* prior_cov, const double* chart, double* adj,
+                   const double* coef, double* g_y, double* g_cov_term, double* g_cov_left, double* g_cov_right,
+                   double* g_prior_mean, double* g_prior_cov, double* g_log_struct, cudaStream_t st) {
+#define RBN_G(DD_) case DD_: return gauss_backward_t<DD_>(B, L, lengths, cov_left, cov_right, prior_mean, prior_cov, chart, adj, coef, g_y, g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct, st)
+    switch (D) {
+        RBN_G(1); RBN_G(2); RBN_G(3); RBN_G(4); RBN_G(8);
+        default:
+            set_error("Gaussian path is instantiated for D in {1,2,3,4,8} (got %d)", D);
+            return RBN_E_UNSUPPORTED;
+    }
+#undef RBN_G
+}
+
+}  // namespace rbn

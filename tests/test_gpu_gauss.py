@@ -27,3 +27,48 @@ def test_gauss_inside_forward_vs_oracle(D, B, L, ragged):
     lz = gauss_logZ(C["y"], C["cov_term"], C["cov_left"], C["cov_right"], C["prior_mean"], C["prior_cov"],
                     C["log_struct"], torch.tensor(lengths))
     np.testing.assert_allclose(lz.cpu().numpy(), ref.numpy(), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("D,B,L,ragged", [(8, 3, 10, True), (2, 4, 7, False), (8, 2, 24, False), (3, 2, 5, True)])
+def test_gauss_gradients_vs_oracle_autograd(D, B, L, ragged):
+    """d(sum coef log Z)/d(y, covariances, prior mean, structural log-probabilities): CUDA outside pass against
+    torch.autograd through the fp64 oracle (covariance gradients compared symmetrised)."""
+    from oracle import gauss_oracle as G
+    from rbn_b200.gaussian import gauss_logZ
+    g, lengths = _case(D, B, L, seed=D * 7 + L, ragged=ragged)
+    coef = np.random.default_rng(1).uniform(0.5, 1.5, B)
+    names = ["y", "cov_term", "cov_left", "cov_right", "prior_mean", "prior_cov", "log_struct"]
+    T = {k: torch.tensor(g[k], requires_grad=True) for k in names}
+    ref = G.gauss_inside(T["y"], torch.tensor(lengths), T["cov_term"], T["cov_left"], T["cov_right"], T["prior_mean"],
+                         T["prior_cov"], T["log_struct"])
+    (ref * torch.tensor(coef)).sum().backward()
+    C = {k: torch.tensor(g[k], device="cuda", requires_grad=True) for k in names}
+    lz = gauss_logZ(C["y"], C["cov_term"], C["cov_left"], C["cov_right"], C["prior_mean"], C["prior_cov"],
+                    C["log_struct"], torch.tensor(lengths))
+    (lz * torch.tensor(coef, device="cuda")).sum().backward()
+    for k in names:
+        got, want = C[k].grad.cpu().numpy(), T[k].grad.numpy()
+        if k.startswith("cov") or k == "prior_cov":
+            want = 0.5 * (want + want.T)
+            got = 0.5 * (got + got.T)
+        if k == "y":          # padding positions carry no gradient
+            for b in range(B):
+                want[b, lengths[b]:] = 0
+        scale = max(np.abs(want).max(), 1e-12)
+        assert np.abs(got - want).max() <= 1e-7 * scale, (k, np.abs(got - want).max(), scale)
+
+
+def test_gaussian_rbn_module_end_to_end():
+    from oracle import gauss_oracle as G
+    from rbn_b200.gaussian import GaussianRBN
+    g = G.synthetic_gauss(8, 3, 9, seed=5)
+    m = GaussianRBN(8, g["cov_term"], g["cov_left"], g["cov_right"], g["prior_mean"], g["prior_cov"], (0.4, 0.6)).cuda()
+    lz = m.log_inside_batch(torch.tensor(g["y"], device="cuda"))
+    T = {k: torch.tensor(v) for k, v in g.items()}
+    ref = G.gauss_inside(T["y"], torch.tensor([9, 9, 9]), T["cov_term"], T["cov_left"], T["cov_right"], T["prior_mean"],
+                         T["prior_cov"], T["log_struct"])
+    np.testing.assert_allclose(lz.detach().cpu().numpy(), ref.numpy(), rtol=1e-9)
+    (-lz.sum()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    z = m.inside(g["y"][0])
+    assert abs(float(torch.log(z)) - float(ref[0])) < 1e-8
