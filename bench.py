@@ -215,10 +215,11 @@ def run_ours(args, wl):
     tok_d = torch.tensor(tok_np, dtype=torch.int32, device=dev)
     len_d = torch.tensor(len_np, dtype=torch.int32, device=dev)
 
+    from rbn_b200.distributed import allreduce_counts
+
     def allreduce_grads(tensors):
         if world > 1:
-            for t in tensors:
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            allreduce_counts(tensors)
 
     def device_step():
         lz = inside_logZ(Wd, Td, pd, tok_d, len_d, chunk_items=args.chunk)
