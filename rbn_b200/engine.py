@@ -190,7 +190,7 @@ class InsideEngine:
         tsize = {}
         for c in cells:
             for t in c.transitions():
-                if isinstance(t, pcfg.DiscreteTerminalTransition):
+                if hasattr(t, "term_idx"):          # duck-typed so reference (rbnet) bricks flatten too
                     V = int(t.transition_probabilities.p.shape[0])
                     tsize[int(t.term_idx)] = max(tsize.get(int(t.term_idx), 0), V)
         n_tvars = (max(tsize) + 1) if tsize else 1
@@ -210,7 +210,7 @@ class InsideEngine:
             pv = slice(int(off[v]), int(off[v + 1]))
             for k, tr in enumerate(cell.transitions()):
                 P = tr.transition_probabilities.p
-                if isinstance(tr, pcfg.DiscreteTerminalTransition):
+                if hasattr(tr, "term_idx"):
                     t = int(tr.term_idx)
                     rows = slice(int(toff[t]), int(toff[t]) + P.shape[0])
                     if P.shape[1] != off[v + 1] - off[v]:

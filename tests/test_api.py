@@ -237,3 +237,23 @@ def test_library_loads_and_exports_every_declared_symbol():
     ok = _lib.RbnDesc(N=10, V=19, B=1, L=20, n_tvars=1, path=0, chunk_items=0, flags=0)
     assert lib.rbn_workspace_bytes(ctypes.byref(ok)) > 0
     assert lib.rbn_resolve_path(ctypes.byref(ok)) == _lib.PATH_SIMT
+
+
+def test_engine_flattens_unmodified_reference_objects():
+    """the engine works on the reference's own bricks (duck-typed)."""
+    from oracle.reference_loader import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("/root/reference not present")
+    ref = load_reference()
+    rp, ru = ref["pcfg"], ref["util"]
+    g = rp.AbstractedPCFG(non_terminals="SAB", terminals="ab", start="S", rules=[
+        ("S --> A B", 1), ("S --> B A", 1), ("A --> B A", 1), ("B --> A B", 1), ("A --> a", 1), ("B --> b", 1)],
+        prob_rep=ru.Prob)
+    ours = _binary_pcfg(util.Prob)
+    Wr, Tr, pr = InsideEngine(g).flatten()
+    Wo, To, po = InsideEngine(ours).flatten()
+    np.testing.assert_array_equal(Wr.detach().numpy(), Wo.detach().numpy())
+    np.testing.assert_array_equal(Tr.detach().numpy(), To.detach().numpy())
+    np.testing.assert_array_equal(pr.detach().numpy(), po.detach().numpy())
+    tok, lengths = InsideEngine(g).pack_sequences([g.tokenise("aaab")])
+    assert tok[0, :, 0].tolist() == [0, 0, 0, 1]
