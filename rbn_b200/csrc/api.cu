@@ -95,11 +95,11 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
     auto take = [&](size_t bytes) { size_t r = off; off = align_up(off + bytes, 1024); return r; };
     o->chart_val = take(B * C * N * sizeof(float));
     o->chart_exp = take(B * C * sizeof(int));
-    o->alpha = take(B * C * N * sizeof(float));
+    if (path != RBN_PATH_TCGEN05) o->alpha = take(B * C * N * sizeof(float));
     o->zroot = take(B * sizeof(float));
     o->rootexp = take(B * sizeof(int));
     if (path == RBN_PATH_TCGEN05) {
-        size_t Lp = align_up(L + 16, 16);
+        size_t Lp = align_up(L + 32, 16);
         o->Lp = (int)Lp;
         size_t max_items = B * (L - 1);                        // widest diagonal (w = 2)
         // default: whole waves of 128-span tiles on 148 SMs, split-sum buffer Y of at most ~6 GB
@@ -110,7 +110,9 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         if (chunk > max_items) chunk = max_items;
         chunk = align_up(chunk, 128);
         o->chunk = (int)chunk;
-        o->alpha2 = take(B * C * N * sizeof(float));
+        // outside charts of the tensor-core path: start-major (left-child sums + root seed) and end-major (right-child sums)
+        o->alpha = take(B * L * Lp * N * sizeof(float));
+        o->alpha2 = take(B * (L + 1) * Lp * N * sizeof(float));
         o->lc = take(B * L * Lp * N * sizeof(__half));
         o->rc = take(B * (L + 1) * Lp * N * sizeof(__half));
         o->wt = take(N * N * N * sizeof(__half));

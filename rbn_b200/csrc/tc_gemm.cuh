@@ -217,6 +217,9 @@ PFN_encodeTiled get_encode_fn();
 // 2-D fp16 tensor [outer][inner] (inner contiguous), box = {64, box_outer}, 128-byte swizzle, OOB reads give zeros.
 int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                  uint32_t box_outer);
+// 2-D fp32 tensor [outer][inner], box = {box_inner, box_outer}, no swizzle (target of TMA reduce-add stores).
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                     uint32_t box_inner, uint32_t box_outer);
 
 template <bool A_MN, bool B_MN, int BLOCK_N, int STAGES, int SEG, class Epi>
 int launch_tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape shape, const Epi& epi, int num_sms,

@@ -60,6 +60,27 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t out
     return RBN_OK;
 }
 
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                     uint32_t box_inner, uint32_t box_outer) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return RBN_E_CUDA;
+    }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(f32) failed (%d)", (int)r);
+        return RBN_E_CUDA;
+    }
+    return RBN_OK;
+}
+
 static int sm_count() {
     static int n = 0;
     if (!n) {
@@ -412,11 +433,13 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                const __grid_constant__ CUtensorMap tmRC,    // RC rows, box {64, Npad}
                const __grid_constant__ CUtensorMap tmLC,    // LC rows, box {64, Npad}
                int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths,
-               const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp,
-               float* __restrict__ alphaL, float* __restrict__ alphaR) {
+               const __grid_constant__ CUtensorMap tmAL,    // alphaL (start-major outside chart, fp32), box {128, 32}
+               const __grid_constant__ CUtensorMap tmAR,    // alphaR (end-major), box {128, 32}
+               const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = (uint64_t*)(smem + kK5Stages * kK5StageBytes);
+    uint8_t* rbuf = smem + kK5Stages * kK5StageBytes;        // [2 groups][2] x 16 KB tiles [32 splits][128 nonterminals] fp32
+    uint64_t* full = (uint64_t*)(rbuf + 65536);
     uint64_t* empty = full + kK5Stages;
     uint64_t* afull = empty + kK5Stages;     // [4]
     uint64_t* aempty = afull + 4;            // [4]
@@ -483,23 +506,6 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                 }
             }
         }
-    } else if (warp == 3) {
-        // L2 prefetch of the chart rows the epilogue will read-modify-write, one span ahead of it
-        for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
-            const int m = m0 + t;
-            const int b = m / nI, i = m - b * nI, k = i + w;
-            if (k > lengths[b]) continue;
-            const int lines_per_row = N / 32;                    // 128-byte lines per chart row
-            const int total = 2 * (w - 1) * lines_per_row;
-            for (int idx = lane; idx < total; idx += 32) {
-                const int kind = idx / ((w - 1) * lines_per_row);
-                const int rem = idx - kind * (w - 1) * lines_per_row;
-                const int us = rem / lines_per_row + 1, ln = rem - (us - 1) * lines_per_row;
-                const int cell = kind ? (cell_off(w - us, L) + i + us) : (cell_off(us, L) + i);
-                const float* ptr = (kind ? alphaR : alphaL) + ((size_t)b * C + cell) * N + ln * 32;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-            }
-        }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc_k = ptx::make_idesc_f16(128, Npad, false, false, 0);
@@ -537,50 +543,57 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
             }
         }
     } else if (warp >= 4) {
-        // Epilogue.  Within one launch every child row receives exactly one left-child contribution (from the span
-        // that starts where it starts) and one right-child contribution (from the span that ends where it ends);
-        // the two kinds go to separate charts, so plain read-modify-write is race-free: no atomics.
-        // Two groups of four warps (4-7, 8-11) take alternate units, so two read-modify-write streams are in flight.
+        // Epilogue: D[x, split] (TMEM) * factor -> smem tile [32 splits][128 nonterminals] -> TMA reduce-add into the
+        // outside chart.  Left-child gradients go to the start-major chart (rows of one start are contiguous),
+        // right-child gradients to the end-major chart; the fp32 add happens at L2, the SM never reads the chart.
+        // Two groups of four warps (4-7, 8-11) take alternate units.
         const int q = warp & 3;
         const int grp = (warp - 4) >> 2;
         const int p = (threadIdx.x - 128) & 127;
-        uint32_t slot_phase = 0;
+        const bool issuer = (p == 0);
+        uint32_t slot_phase = 0, nred = 0;
         int fbuf = 0;
+        uint8_t* mybuf = rbuf + grp * 32768;
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI, k = i + w;
             if (k > lengths[b]) continue;
             const int* ce_seq = ce + (size_t)b * C;
             float* facb = fac + (grp * 2 + fbuf) * 128;
-            if (p < w - 1) {
-                const int us = p + 1;
-                const int sft = ce_seq[cell_off(us, L) + i] + ce_seq[cell_off(w - us, L) + i + us] - item_e[t] + gexp[t];
-                facb[p] = ldexpf(1.0f, min(max(sft, -126), 126));
+            {
+                float f = 0.f;
+                if (p < w - 1) {
+                    const int us = p + 1;
+                    const int sft = ce_seq[cell_off(us, L) + i] + ce_seq[cell_off(w - us, L) + i + us] - item_e[t] + gexp[t];
+                    f = ldexpf(1.0f, min(max(sft, -126), 126));
+                }
+                facb[p] = f;                                     // 0 for the padding splits: they add nothing
             }
             ptx::named_bar_sync(2 + grp, 128);
+            const int rowL = (int)(((size_t)b * L + i) * Lp + (i + 1));
+            const int rowR = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
             for (int u = grp; u < units; u += 2) {
                 const int kind = u / halves, h = u - kind * halves;
                 ptx::mbar_wait(&afull[u], slot_phase);
                 ptx::tc_fence_after();
-                const int x = h * 128 + q * 32 + lane;          // nonterminal index of this thread's row
+                const int xl = q * 32 + lane;                    // row of the 128-wide tile
                 const uint32_t taddr = tmem_base + u * 128 + ((uint32_t)(q * 32) << 16);
-                float* al_seq = (kind ? alphaR : alphaL) + (size_t)b * C * N + x;
                 for (int c0 = 0; c0 < Npad; c0 += 32) {
                     float v[32];
-                    ptx::tmem_ld32(taddr + c0, v);               // Npad is a multiple of 16: columns past it are never used
-                    int cell[32];
-                    float old[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int us = c0 + j + 1;               // left width of this split
-                        const bool ok = (us < w) && (x < N);
-                        cell[j] = ok ? (kind ? (cell_off(w - us, L) + i + us) : (cell_off(us, L) + i)) : -1;
-                        old[j] = ok ? al_seq[(size_t)cell[j] * N] : 0.f;
-                    }
+                    ptx::tmem_ld32(taddr + c0, v);
+                    float* tile = reinterpret_cast<float*>(mybuf + (nred & 1) * 16384);
+                    if (issuer) ptx::bulk_wait_read<1>();        // the reduce that used this tile two chunks ago has read it
+                    ptx::named_bar_sync(2 + grp, 128);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (cell[j] >= 0) al_seq[(size_t)cell[j] * N] = fmaf(v[j], facb[c0 + j], old[j]);
+                    for (int j = 0; j < 32; ++j) tile[j * 128 + xl] = v[j] * facb[c0 + j];
+                    ptx::fence_proxy_async_smem();
+                    ptx::named_bar_sync(2 + grp, 128);
+                    if (issuer) {
+                        ptx::tma_reduce_add_2d(kind ? &tmAR : &tmAL, tile, h * 128, (kind ? rowR : rowL) + c0);
+                        ptx::bulk_commit();
+                    }
+                    ++nred;
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&aempty[u]);
@@ -588,6 +601,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
             slot_phase ^= 1;
             fbuf ^= 1;
         }
+        if (issuer) ptx::bulk_wait_all();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -647,8 +661,43 @@ __global__ void k_copy_width1(int N, int L, int Lp, const int* __restrict__ leng
         r[a] = h;
     }
 }
+// root seed into the start-major outside chart (and the prior gradient)
+__global__ void k_tc_outside_seed(int N, int L, int Lp, const float* __restrict__ prior, const int* __restrict__ lengths,
+                                  const float* __restrict__ cv, const float* __restrict__ ws_zroot,
+                                  const float* __restrict__ coef, float* __restrict__ alphaL, float* __restrict__ gPrior) {
+    int b = blockIdx.x;
+    int n = lengths[b];
+    size_t cell = (size_t)b * cells_per_seq(L) + cell_off(n, L);
+    size_t row = ((size_t)b * L + 0) * Lp + n;
+    float z = ws_zroot[b];
+    float f = coef[b] / (z > 0.f ? z : 1.0f);
+    if (f == 0.f) return;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        alphaL[row * N + a] = f * prior[a];
+        float m = cv[cell * N + a];
+        if (m != 0.f) atomicAdd(&gPrior[a], f * m);
+    }
+}
+__global__ void k_tc_emission_bwd(int N, int L, int Lp, int nt, const int* __restrict__ tokens,
+                                  const int* __restrict__ lengths, const int* __restrict__ ce,
+                                  const float* __restrict__ alphaL, const float* __restrict__ alphaR,
+                                  float* __restrict__ gT) {
+    int b = blockIdx.x / L, i = blockIdx.x % L;
+    if (i >= lengths[b]) return;
+    size_t cell = (size_t)b * cells_per_seq(L) + i;
+    size_t rl = ((size_t)b * L + i) * Lp + (i + 1), rr = ((size_t)b * (L + 1) + (i + 1)) * Lp + i;
+    int e = ce[cell];
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        float g = ldexpf(alphaL[rl * N + a] + alphaR[rr * N + a], -e);
+        if (g == 0.f) continue;
+        for (int t = 0; t < nt; ++t) {
+            int y = tokens[((size_t)b * L + i) * nt + t];
+            if (y >= 0) atomicAdd(&gT[(size_t)y * N + a], g);
+        }
+    }
+}
 // upstream gradient of one chunk:  G = alpha * 2^-e_new ;  Ghat = G * 2^wexp[a] normalised per item ; Gabs = G * 2^-8
-__global__ void k_prep_g(int N, int L, int w, int m0, int cnt, const int* __restrict__ lengths, const int* __restrict__ ce,
+__global__ void k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths, const int* __restrict__ ce,
                          const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
                          const float* __restrict__ alpha2, __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
     __shared__ float red[32];
@@ -662,7 +711,9 @@ __global__ void k_prep_g(int N, int L, int w, int m0, int cnt, const int* __rest
     if (valid) {
         const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
         const int e_new = ce[cell] - item_e[t];
-        g = ldexpf(alpha[cell * N + a] + alpha2[cell * N + a], -e_new);
+        const int k = i + w;
+        const size_t rl = ((size_t)b * L + i) * Lp + k, rr = ((size_t)b * (L + 1) + k) * Lp + i;
+        g = ldexpf(alpha[rl * N + a] + alpha2[rr * N + a], -e_new);
         gs = ldexpf(g, wexp[a]);
     }
     float mx = fabsf(gs);
@@ -823,11 +874,16 @@ static int launch_k5(TcCtx& c, int w, int m0, int cnt) {
     if (rc) return rc;
     rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, (uint32_t)Npad);
     if (rc) return rc;
-    size_t smem = (size_t)kK5Stages * kK5StageBytes + 256 + 2048 + 1024;
+    CUtensorMap tmAL, tmAR;
+    rc = make_tmap_2d_f32(&tmAL, c.alpha, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 4, 128, 32);
+    if (rc) return rc;
+    rc = make_tmap_2d_f32(&tmAR, c.alpha2, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 4, 128, 32);
+    if (rc) return rc;
+    size_t smem = (size_t)kK5Stages * kK5StageBytes + 65536 + 256 + 2048 + 1024;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < c.sms ? cnt : c.sms;
-    { ProfScope ps(KC_CHILD, c.st); k_tc_childgrad<<<grid, 384, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, c.ce, c.item_e,
-                                              c.gexp, c.alpha, c.alpha2); }
+    { ProfScope ps(KC_CHILD, c.st); k_tc_childgrad<<<grid, 384, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, tmAL, tmAR, c.ce, c.item_e,
+                                              c.gexp); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;
 }
@@ -869,14 +925,14 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     fill_ctx(c, d, ws, base, lengths, st);
     int N = c.N, L = c.L, B = c.B;
     size_t C = cells_per_seq(L);
-    RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha, 0, (size_t)B * C * N * sizeof(float), st));
-    RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha2, 0, (size_t)B * C * N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha, 0, (size_t)B * L * c.Lp * N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha2, 0, (size_t)B * (L + 1) * c.Lp * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gW, 0, (size_t)N * N * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(c.y, 0, (size_t)c.chunk * N * N * sizeof(__half), st));
-    { ProfScope ps(KC_OTHER, st); k_outside_seed<<<B, 128, 0, st>>>(N, L, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior); }
-    RBN_LAUNCH_CHECK("k_outside_seed");
+    { ProfScope ps(KC_OTHER, st); k_tc_outside_seed<<<B, 128, 0, st>>>(N, L, c.Lp, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior); }
+    RBN_LAUNCH_CHECK("k_tc_outside_seed");
     int rc;
     for (int w = L; w >= 2; --w) {
         int items = B * (L - w + 1);
@@ -884,14 +940,14 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
             int cnt = items - m0 < c.chunk ? items - m0 : c.chunk;
             if ((rc = launch_k1(c, w, m0, cnt))) return rc;
             int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
-            { ProfScope ps(KC_PREP, st); k_prep_g<<<pg, N, 0, st>>>(N, L, w, m0, cnt, lengths, c.ce, c.item_e, c.wexp, c.alpha, c.alpha2, c.ghat, c.gabs, c.gexp); }
+            { ProfScope ps(KC_PREP, st); k_prep_g<<<pg, N, 0, st>>>(N, L, c.Lp, w, m0, cnt, lengths, c.ce, c.item_e, c.wexp, c.alpha, c.alpha2, c.ghat, c.gabs, c.gexp); }
             RBN_LAUNCH_CHECK("k_prep_g");
             if ((rc = launch_k3(c, cnt))) return rc;
             if ((rc = launch_k4(c, cnt, gW))) return rc;
             if ((rc = launch_k5(c, w, m0, cnt))) return rc;
         }
     }
-    { ProfScope ps(KC_EMISSION, st); k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, c.ce, c.alpha, c.alpha2, gT); }
+    { ProfScope ps(KC_EMISSION, st); k_tc_emission_bwd<<<B * L, 128, 0, st>>>(N, L, c.Lp, d->n_tvars, tokens, lengths, c.ce, c.alpha, c.alpha2, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");
     return RBN_OK;
 }

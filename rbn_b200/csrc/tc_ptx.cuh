@@ -56,6 +56,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
 }
+// smem tile (no swizzle) += into global (fp32 add performed at L2), bulk-group completion
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int x, int y) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
