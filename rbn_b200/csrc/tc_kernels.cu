@@ -609,6 +609,152 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
 }
 
 // =======================================================================================================================
+// K3: gY[m][(b,c)] = sum_a Ghat[m][a] * Wk[(b,c)][a]  -- A-resident variant
+// =======================================================================================================================
+// Output-heavy GEMM (K = N only): a CTA keeps the upstream-gradient rows of 256 spans resident in shared memory
+// (two 128-row M tiles) and streams 128-row tiles of Wk past them, so every Wk tile feeds 256 spans (halves the
+// L2 -> SM operand traffic that bounded the generic kernel) and the gradient rows are loaded once per work unit.
+//   warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM owner, warps 4-7 epilogue (TMEM -> fp16 -> smem -> TMA store)
+static constexpr int kGYStages = 4;
+
+__global__ void __launch_bounds__(256, 1)
+k_tc_gy(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box {64, 128}
+        const __grid_constant__ CUtensorMap tmW,     // Wk [N*N rows][N], box {64, 128}
+        const __grid_constant__ CUtensorMap tmOut,   // gY [cnt rows][N*N], box {64, 128}
+        int N, int supertiles, int ranges) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int kblocks = N / 64;
+    const int ntiles_total = N * N / 128;
+    const int ntiles_per_range = ntiles_total / ranges;
+    uint8_t* sAres = smem;                                        // [2 mtiles][kblocks] x 16 KB
+    uint8_t* sBring = sAres + (size_t)2 * kblocks * 16384;        // [stages] x 16 KB
+    uint8_t* ebuf = sBring + kGYStages * 16384;                   // 2 x 16 KB staging tiles
+    uint64_t* full = (uint64_t*)(ebuf + 32768);
+    uint64_t* empty = full + kGYStages;
+    uint64_t* tfull = empty + kGYStages;      // [2]
+    uint64_t* tempty = tfull + 2;             // [2]
+    uint64_t* a_full = tempty + 2;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(a_empty + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGYStages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], 128);
+        }
+        ptx::mbar_init(a_full, 1);
+        ptx::mbar_init(a_empty, 1);
+        ptx::fence_barrier_init();
+        ptx::tma_prefetch_desc(&tmG);
+        ptx::tma_prefetch_desc(&tmW);
+        ptx::tma_prefetch_desc(&tmOut);
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int units = supertiles * ranges;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                const int st = unit / ranges, r = unit - st * ranges;
+                ptx::mbar_wait(a_empty, aphase ^ 1);
+                ptx::mbar_expect_tx(a_full, (uint32_t)2 * kblocks * 16384);
+                for (int mt = 0; mt < 2; ++mt)
+                    for (int kb = 0; kb < kblocks; ++kb)
+                        ptx::tma_load_2d(sAres + (size_t)(mt * kblocks + kb) * 16384, &tmG, a_full, kb * 64, st * 256 + mt * 128);
+                aphase ^= 1;
+                for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt)
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        ptx::mbar_wait(&empty[stage], phase ^ 1);
+                        ptx::mbar_expect_tx(&full[stage], 16384);
+                        ptx::tma_load_2d(sBring + stage * 16384, &tmW, &full[stage], kb * 64, nt * 128);
+                        if (++stage == kGYStages) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_f16(128, 128, false, false, 0);
+            int stage = 0, buf = 0;
+            uint32_t phase = 0, aphase = 0, bphase = 0;
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                const int st = unit / ranges, r = unit - st * ranges;
+                (void)st;
+                ptx::mbar_wait(a_full, aphase);
+                aphase ^= 1;
+                ptx::tc_fence_after();
+                const uint32_t aA = ptx::smem_u32(sAres);
+                for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt) {
+                    ptx::mbar_wait(&tempty[buf], bphase ^ 1);
+                    ptx::tc_fence_after();
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        ptx::mbar_wait(&full[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t sB = ptx::smem_u32(sBring + stage * 16384);
+                        for (int mt = 0; mt < 2; ++mt) {
+                            const uint32_t sA = aA + (uint32_t)(mt * kblocks + kb) * 16384;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::mma_f16_ss(tmem_base + buf * 256 + mt * 128, ptx::make_smem_desc(sA + k * 32, 16, 1024),
+                                                ptx::make_smem_desc(sB + k * 32, 16, 1024), idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        ptx::mma_commit(&empty[stage]);
+                        if (++stage == kGYStages) { stage = 0; phase ^= 1; }
+                    }
+                    ptx::mma_commit(&tfull[buf]);
+                    if (++buf == 2) { buf = 0; bphase ^= 1; }
+                }
+                ptx::mma_commit(a_empty);          // the resident A tiles may be replaced once these MMAs retire
+            }
+        }
+    } else if (warp >= 4) {
+        // NOTE (measured): this kernel is shared-memory-bandwidth bound (MMA operand reads + TMA fills + staging
+        // ~250 B/cycle against 128 B/cycle); a second epilogue group made it slower, see DESIGN.md section 4.
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const bool issuer = (threadIdx.x == 128);
+        int buf = 0;
+        uint32_t bphase = 0, nstore = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            const int st = unit / ranges, r = unit - st * ranges;
+            for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt) {
+                ptx::mbar_wait(&tfull[buf], bphase);
+                ptx::tc_fence_after();
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint32_t taddr = tmem_base + buf * 256 + mt * 128 + ((uint32_t)(q * 32) << 16);
+                    for (int c0 = 0; c0 < 128; c0 += 64) {
+                        float v[64];
+                        ptx::tmem_ld32(taddr + c0, v);
+                        ptx::tmem_ld32(taddr + c0 + 32, v + 32);
+                        ptx::tmem_ld_wait();
+                        ptx::stage_store_tile(ebuf, &tmOut, nt * 128 + c0, st * 256 + mt * 128, row, v, nstore, 3, issuer, true);
+                        ++nstore;
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tempty[buf]);
+                if (++buf == 2) { buf = 0; bphase ^= 1; }
+            }
+        }
+        if (issuer) ptx::bulk_wait_all();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// =======================================================================================================================
 // element-wise helpers of the tensor-core path
 // =======================================================================================================================
 // per-parent exponent of max_{b,c} W[b][c][a]
@@ -829,16 +975,24 @@ static int launch_k2(TcCtx& c, int w, int m0, int cnt) {
 
 static int launch_k3(TcCtx& c, int cnt) {
     size_t NN = (size_t)c.N * c.N;
-    CUtensorMap tmA, tmB;
-    int rc = make_tmap_2d(&tmA, c.ghat, (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 128);
+    CUtensorMap tmG, tmW, tmOut;
+    int rc = make_tmap_2d(&tmG, c.ghat, (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmB, c.wk, (uint64_t)c.N, NN, (uint64_t)c.N * 2, 256);
+    rc = make_tmap_2d(&tmW, c.wk, (uint64_t)c.N, NN, (uint64_t)c.N * 2, 128);
     if (rc) return rc;
-    EpiGY epi;
-    rc = make_tmap_2d(&epi.tm, c.gy, NN, (uint64_t)cnt, NN * 2, 128);
+    rc = make_tmap_2d(&tmOut, c.gy, NN, (uint64_t)cnt, NN * 2, 128);
     if (rc) return rc;
-    GemmShape shape{(cnt + 127) / 128, (int)(NN / 256), c.N / 64};
-    return launch_tc_gemm<false, false, 256, 4, 0, EpiGY>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<gY>", KC_GY);
+    int supertiles = (cnt + 255) / 256;
+    int ntiles = (int)(NN / 128);
+    int ranges = 1;
+    while (ranges < 16 && supertiles * ranges < 2 * c.sms && ntiles % (ranges * 2) == 0 && ntiles / (ranges * 2) >= 8) ranges *= 2;
+    size_t smem = (size_t)2 * (c.N / 64) * 16384 + kGYStages * 16384 + 32768 + 256 + 1024;
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int units = supertiles * ranges;
+    int grid = units < c.sms ? units : c.sms;
+    { ProfScope ps(KC_GY, c.st); k_tc_gy<<<grid, 256, smem, c.st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges); }
+    RBN_LAUNCH_CHECK("k_tc_gy");
+    return RBN_OK;
 }
 
 template <int BN>

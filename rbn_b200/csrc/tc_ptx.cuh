@@ -69,10 +69,11 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // Epilogue helper: 128 threads (thread <-> tile row) stage a [128 x 64] fp16 tile (64 fp32 values per thread) in a
 // 16 KB 128-byte-swizzled buffer and one of them TMA-stores it: every global write is a full 128-byte line.
 // `nstore` counts the stores issued so far by this CTA (selects the ping-pong buffer).
+template <int NBUF = 2>
 __device__ __forceinline__ void stage_store_tile(uint8_t* bufs, const CUtensorMap* tm, int x, int y, int row,
                                                  const float* v, uint32_t nstore, uint32_t bar_id, bool issuer, bool active) {
-    uint8_t* buf = bufs + (nstore & 1) * 16384;
-    if (issuer) bulk_wait_read<1>();                 // the store that used this buffer two tiles ago has been read
+    uint8_t* buf = bufs + (NBUF == 2 ? (nstore & 1) * 16384 : 0);
+    if (issuer) bulk_wait_read<NBUF - 1>();          // the store that last used this buffer has been read
     named_bar_sync(bar_id, 128);
     uint4 pk[8];
     __half2* h = reinterpret_cast<__half2*>(pk);
