@@ -208,6 +208,201 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// =======================================================================================================================
+// 2-CTA variant (cta_group::2): a pair of CTAs on one TPC computes a 256 x BLOCK_N tile.  Each CTA stages its own 128
+// rows of A and HALF of B (BLOCK_N/2 rows), so per-SM shared-memory traffic (TMA fills + MMA operand reads) drops
+// from ~190 B/cycle -- above the 128 B/cycle an SM can move, which capped the 1-CTA kernel near 70 % -- to ~125.
+// The even CTA (leader) issues the MMAs; its `full` barriers collect the bytes of both CTAs' TMA loads; commits are
+// multicast to both CTAs; the odd CTA's epilogue threads arrive remotely on the leader's `tempty` / `segfree`.
+// =======================================================================================================================
+template <int BLOCK_N, int STAGES, int EPI_SMEM>
+struct Gemm2Smem {
+    static constexpr int A_BYTES = kBM * kBK * 2;
+    static constexpr int B_BYTES = (BLOCK_N / 2) * kBK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = EPI_OFF + EPI_SMEM;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <bool A_MN, bool B_MN, int BLOCK_N, int STAGES, int SEG, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape,
+           const __grid_constant__ Epi epi) {
+    using S = Gemm2Smem<BLOCK_N, STAGES, Epi::kSmem>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 1;
+    uint64_t* segfull = tempty + 1;
+    uint64_t* segfree = segfull + 1;
+    uint32_t* tmem_slot = (uint32_t*)(segfree + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = (rank == 0);
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * BLOCK_N);
+    constexpr int SEGD = SEG > 0 ? SEG : 1;
+    constexpr int HALF_N = BLOCK_N / 2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        ptx::mbar_init(tfull, 1);
+        ptx::mbar_init(tempty, 256);
+        ptx::mbar_init(segfull, 1);
+        ptx::mbar_init(segfree, 256);
+        ptx::fence_barrier_init();
+        ptx::tma_prefetch_desc(&tmA);
+        ptx::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 2) ptx::tmem_alloc2(tmem_slot, TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                         // peer barriers are initialised before any remote arrive / multicast
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int total_tiles = shape.m_tiles * shape.n_tiles;      // m_tiles counts 256-row tiles here
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < total_tiles; tile += npairs) {
+                const int nt = tile / shape.m_tiles, mt = tile - nt * shape.m_tiles;
+                const int row0 = mt * 256 + (int)rank * kBM;                 // this CTA's rows of A
+                const int col0 = nt * BLOCK_N + (int)rank * HALF_N;          // this CTA's half of B
+                for (int kb = 0; kb < shape.k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * S::STAGE_BYTES;
+                    uint8_t* sB = sA + S::A_BYTES;
+                    if (leader) ptx::mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
+                    if (!A_MN) {
+                        ptx::tma_load_2d_pair(sA, &tmA, &full[stage], kb * kBK, row0);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < kBM / 64; ++a)
+                            ptx::tma_load_2d_pair(sA + a * 8192, &tmA, &full[stage], row0 + a * 64, kb * kBK);
+                    }
+                    if (!B_MN) {
+                        ptx::tma_load_2d_pair(sB, &tmB, &full[stage], kb * kBK, col0);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < HALF_N / 64; ++a)
+                            ptx::tma_load_2d_pair(sB + a * 8192, &tmB, &full[stage], col0 + a * 64, kb * kBK);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(256, BLOCK_N, A_MN, B_MN, 0);
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0, flush_waits = 0;
+            for (int tile = pair; tile < total_tiles; tile += npairs) {
+                ptx::mbar_wait(tempty, acc_phase ^ 1);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < shape.k_blocks; ++kb) {
+                    uint32_t d_tmem = tmem_base;
+                    bool seg_start = (kb == 0);
+                    if (SEG > 0) {
+                        const int seg = kb / SEGD;
+                        seg_start = (kb - seg * SEGD) == 0;
+                        d_tmem = tmem_base + (seg == 0 ? 0 : BLOCK_N);
+                        if (seg_start && seg >= 2) {
+                            ptx::mbar_wait(segfree, flush_waits & 1);
+                            ++flush_waits;
+                            ptx::tc_fence_after();
+                        }
+                    }
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sA = ptx::smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint32_t sB = sA + S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t ad = A_MN ? ptx::make_smem_desc(sA + k * 2048, 8192, 1024)
+                                                 : ptx::make_smem_desc(sA + k * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? ptx::make_smem_desc(sB + k * 2048, 8192, 1024)
+                                                 : ptx::make_smem_desc(sB + k * 32, 16, 1024);
+                        ptx::mma_f16_ss_pair(d_tmem, ad, bd, idesc, (uint32_t)(!(seg_start && k == 0)));
+                    }
+                    ptx::mma_commit_pair(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (SEG > 0) {
+                        const int seg = kb / SEGD;
+                        const bool seg_end = ((kb + 1) % SEGD == 0) && (kb + 1 < shape.k_blocks);
+                        if (seg_end && seg >= 1) ptx::mma_commit_pair(segfull);
+                    }
+                }
+                ptx::mma_commit_pair(tfull);
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        uint32_t acc_phase = 0, flushes = 0, nstore = 0;
+        uint8_t* epi_smem = smem + S::EPI_OFF;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        for (int tile = pair; tile < total_tiles; tile += npairs) {
+            const int nt = tile / shape.m_tiles, mt = tile - nt * shape.m_tiles;
+            const uint32_t t0 = tmem_base + lane_off;
+            uint32_t t1 = 0;
+            if (SEG > 0) {
+                const int nseg = (shape.k_blocks + SEGD - 1) / SEGD;
+                const uint32_t tA = tmem_base + BLOCK_N + lane_off;
+                for (int sg = 1; sg + 1 < nseg; ++sg) {
+                    ptx::mbar_wait(segfull, flushes & 1);
+                    ++flushes;
+                    ptx::tc_fence_after();
+                    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                        float v[32];
+                        ptx::tmem_ld32_sum(t0, tA, c0, v);
+                        ptx::tmem_st32(t0 + c0, v);
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive_leader(segfree);
+                }
+                if (nseg >= 2) t1 = tA;
+            }
+            ptx::mbar_wait(tfull, acc_phase);
+            ptx::tc_fence_after();
+            epi(mt * 2 + (int)rank, nt, q * 32 + lane, t0, t1, epi_smem, nstore);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive_leader(tempty);
+            acc_phase ^= 1;
+        }
+        if (Epi::kSmem > 0 && threadIdx.x == 128) ptx::bulk_wait_all();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                         // nobody leaves while the peer may still read its smem / barriers
+    if (warp == 2) ptx::tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
+template <bool A_MN, bool B_MN, int BLOCK_N, int STAGES, int SEG, class Epi>
+int launch_tc_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape shape, const Epi& epi, int num_sms,
+                    cudaStream_t st, const char* name, int kclass) {
+    using S = Gemm2Smem<BLOCK_N, STAGES, Epi::kSmem>;
+    auto kern = k_tc_gemm2<A_MN, B_MN, BLOCK_N, STAGES, SEG, Epi>;
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    int tiles = shape.m_tiles * shape.n_tiles;
+    int pairs = num_sms / 2;
+    if (tiles < pairs) pairs = tiles;
+    if (pairs < 1) return RBN_OK;
+    { ProfScope ps(kclass, st); kern<<<2 * pairs, 256, S::TOTAL, st>>>(tmA, tmB, shape, epi); }
+    RBN_LAUNCH_CHECK(name);
+    return RBN_OK;
+}
+
 // ---- host: TMA descriptor encoding (driver entry point fetched at run time; libcuda is never linked) --------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

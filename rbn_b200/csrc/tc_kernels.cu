@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include <limits.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace rbn {
@@ -79,6 +80,16 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t
         return RBN_E_CUDA;
     }
     return RBN_OK;
+}
+
+// CTA-pair (cta_group::2) GEMMs for the rule contraction and the count GEMM; RBN_TC_1CTA=1 selects the 1-CTA kernels
+static bool use_pairs() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RBN_TC_1CTA");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 static int sm_count() {
@@ -961,6 +972,13 @@ static int launch_k2_bn(TcCtx& c, int w, int m0, int cnt) {
     rc = make_tmap_2d(&tmB, c.wt, NN, (uint64_t)c.N, NN * 2, BN);
     if (rc) return rc;
     EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.item_e, c.cv, c.ce, c.lc, c.rc};
+    if (use_pairs()) {
+        CUtensorMap tmB2;
+        rc = make_tmap_2d(&tmB2, c.wt, NN, (uint64_t)c.N, NN * 2, BN / 2);
+        if (rc) return rc;
+        GemmShape shape2{(cnt + 255) / 256, 1, (int)(NN / 64)};
+        return launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, c.sms, c.st, "k_tc_gemm2<rule>", KC_RULE);
+    }
     GemmShape shape{(cnt + 127) / 128, 1, (int)(NN / 64)};
     return launch_tc_gemm<false, false, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiRule>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<rule>", KC_RULE);
 }
@@ -1004,6 +1022,10 @@ static int launch_k4_bn(TcCtx& c, int cnt, float* gW) {
     rc = make_tmap_2d(&tmB, c.gabs, (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 64);   // MN-major B: [K=items][N=a]
     if (rc) return rc;
     EpiCounts epi{gW, c.N};
+    if (use_pairs() && BN % 128 == 0) {
+        GemmShape shape2{(int)(NN / 256), 1, (cnt + 63) / 64};
+        return launch_tc_gemm2<true, true, (BN % 128 == 0 ? BN : 128), 6, kSegBlocks, EpiCounts>(tmA, tmB, shape2, epi, c.sms, c.st, "k_tc_gemm2<counts>", KC_COUNTS);
+    }
     GemmShape shape{(int)(NN / 128), 1, (cnt + 63) / 64};
     return launch_tc_gemm<true, true, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiCounts>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<counts>", KC_COUNTS);
 }
@@ -1123,6 +1145,24 @@ int debug_gemm(int M, int N, int K, const __half* A, const __half* Bm, float* D,
     EpiStoreF32 epi{D, M, N, 256};
     GemmShape shape{(M + 127) / 128, 1, K / 64};
     int sms = sm_count();
+    if (seg & 2) {       // 2-CTA variant (tests): K-major/K-major and MN-major/MN-major only
+        CUtensorMap tmB2;
+        if (!b_mn) rc = make_tmap_2d(&tmB2, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 128);
+        else rc = make_tmap_2d(&tmB2, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)N * 2, 64);
+        if (rc) return rc;
+        GemmShape shape2{(M + 255) / 256, 1, K / 64};
+        if (!a_mn && !b_mn) {
+            if (seg & 1) return launch_tc_gemm2<false, false, 256, 6, kSegBlocks, EpiStoreF32>(tmA, tmB2, shape2, epi, sms, st, "debug_gemm2", KC_OTHER);
+            return launch_tc_gemm2<false, false, 256, 6, 0, EpiStoreF32>(tmA, tmB2, shape2, epi, sms, st, "debug_gemm2", KC_OTHER);
+        }
+        if (a_mn && b_mn) {
+            if (seg & 1) return launch_tc_gemm2<true, true, 256, 6, kSegBlocks, EpiStoreF32>(tmA, tmB2, shape2, epi, sms, st, "debug_gemm2", KC_OTHER);
+            return launch_tc_gemm2<true, true, 256, 6, 0, EpiStoreF32>(tmA, tmB2, shape2, epi, sms, st, "debug_gemm2", KC_OTHER);
+        }
+        set_error("debug gemm: the 2-CTA variant is instantiated for equal operand layouts only");
+        return RBN_E_BADARG;
+    }
+    seg &= 1;
 #define RBN_DBG(AM, BM_, SG) return launch_tc_gemm<AM, BM_, 256, 4, SG, EpiStoreF32>(tmA, tmB, shape, epi, sms, st, "debug_gemm", KC_OTHER)
     if (seg) {
         if (!a_mn && !b_mn) RBN_DBG(false, false, kSegBlocks);

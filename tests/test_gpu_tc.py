@@ -40,6 +40,30 @@ def test_tcgen05_gemm_template_vs_torch(a_mn, b_mn, M, K, seg):
     assert err < 4e-5 and abs(bias) < 3e-5, (a_mn, b_mn, M, K, err, bias)
 
 
+@pytest.mark.parametrize("mn", [0, 1])
+@pytest.mark.parametrize("M,K,seg", [(256, 64, 2), (300 + 4, 192, 2), (1000, 1024, 2), (520, 4096 * 3 + 128, 3), (256, 65536, 3)])
+def test_tcgen05_two_cta_gemm_vs_torch(mn, M, K, seg):
+    """cta_group::2 variant of the GEMM template (CTA pairs, 256-row tiles, B split across the pair)."""
+    from rbn_b200 import _lib
+    lib = _lib.load()
+    N = 256
+    g = torch.Generator(device="cuda").manual_seed(M + K + mn)
+    A = torch.rand((M, K), device="cuda", generator=g).half()
+    Bm = torch.rand((N, K), device="cuda", generator=g).half()
+    ref = (A.double() @ Bm.double().t()).float()
+    Ain = A.t().contiguous() if mn else A.contiguous()
+    Bin = Bm.t().contiguous() if mn else Bm.contiguous()
+    D = torch.full((M, N), float("nan"), device="cuda")
+    rc = lib.rbn_debug_gemm(M, N, K, ctypes.c_void_p(Ain.data_ptr()), ctypes.c_void_p(Bin.data_ptr()),
+                            ctypes.c_void_p(D.data_ptr()), mn, mn, seg,
+                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "rbn_debug_gemm")
+    torch.cuda.synchronize()
+    err = float((D - ref).abs().max() / ref.abs().max())
+    bias = float(((D - ref) / ref).mean())
+    assert err < 4e-5 and abs(bias) < 3e-5, (mn, M, K, err, bias)
+
+
 def _run(N, V, L, B, ragged, seed, path, chunk=0):
     from oracle import inside_oracle as O
     from rbn_b200 import inside_logZ
