@@ -126,6 +126,7 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->ghat = take(chunk * N * sizeof(__half));
         o->gabs = take(chunk * N * sizeof(__half));
         o->gexp = take(chunk * sizeof(int));
+        o->acc = take(chunk * N * sizeof(float));
     }
     o->total = off;
     return true;

@@ -62,6 +62,7 @@ struct WsLayout {
     size_t ghat;        // half [chunk][N]       item-normalised upstream gradient
     size_t gabs;        // half [chunk][N]       absolutely scaled upstream gradient (for the count GEMM)
     size_t gexp;        // int32 [chunk]
+    size_t acc;         // float [chunk][N]  K-split partial sums of the rule GEMM's tail tiles
     size_t total;
     int Lp;
     int chunk;

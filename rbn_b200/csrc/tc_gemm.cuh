@@ -17,7 +17,34 @@ static constexpr int kBK = 64;       // halves per k-block = one 128-byte swizzl
 
 struct GemmShape {
     int m_tiles, n_tiles, k_blocks;
+    // 2-CTA kernel only: tiles [0, full_tiles) are computed whole; every later tile is split along K into tail_splits
+    // work units whose partial sums the epilogue adds atomically (wave-quantisation fix).  tail_splits <= 1: no split.
+    int full_tiles, tail_splits;
 };
+
+struct GemmUnit {
+    int tile, kb0, kb1;
+    bool partial;
+};
+__device__ __forceinline__ int gemm_units(const GemmShape& s) {
+    const int total = s.m_tiles * s.n_tiles;
+    if (s.tail_splits <= 1) return total;
+    return s.full_tiles + (total - s.full_tiles) * s.tail_splits;
+}
+__device__ __forceinline__ GemmUnit gemm_unit(const GemmShape& s, int u) {
+    GemmUnit r;
+    if (s.tail_splits <= 1 || u < s.full_tiles) {
+        r.tile = u; r.kb0 = 0; r.kb1 = s.k_blocks; r.partial = false;
+    } else {
+        const int v = u - s.full_tiles;
+        const int per = (s.k_blocks + s.tail_splits - 1) / s.tail_splits;
+        r.tile = s.full_tiles + v / s.tail_splits;
+        r.kb0 = (v % s.tail_splits) * per;
+        r.kb1 = min(s.k_blocks, r.kb0 + per);
+        r.partial = true;
+    }
+    return r;
+}
 
 template <int BLOCK_N, int STAGES, int EPI_SMEM>
 struct GemmSmem {
@@ -192,7 +219,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
-            epi(mt, nt, q * 32 + lane, t0, t1, epi_smem, nstore);
+            epi(mt, nt, q * 32 + lane, t0, t1, epi_smem, nstore, false);
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[acc]);
             if (SEG == 0) {
@@ -268,17 +295,18 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const uint32_t tmem_base = *tmem_slot;
 
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int total_tiles = shape.m_tiles * shape.n_tiles;      // m_tiles counts 256-row tiles here
+    const int total_units = gemm_units(shape);                  // m_tiles counts 256-row tiles here
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = pair; tile < total_tiles; tile += npairs) {
-                const int nt = tile / shape.m_tiles, mt = tile - nt * shape.m_tiles;
+            for (int unit = pair; unit < total_units; unit += npairs) {
+                const GemmUnit gu = gemm_unit(shape, unit);
+                const int nt = gu.tile / shape.m_tiles, mt = gu.tile - nt * shape.m_tiles;
                 const int row0 = mt * 256 + (int)rank * kBM;                 // this CTA's rows of A
                 const int col0 = nt * BLOCK_N + (int)rank * HALF_N;          // this CTA's half of B
-                for (int kb = 0; kb < shape.k_blocks; ++kb) {
+                for (int kb = gu.kb0; kb < gu.kb1; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * S::STAGE_BYTES;
                     uint8_t* sB = sA + S::A_BYTES;
@@ -306,10 +334,14 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             constexpr uint32_t idesc = ptx::make_idesc_f16(256, BLOCK_N, A_MN, B_MN, 0);
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0, flush_waits = 0;
-            for (int tile = pair; tile < total_tiles; tile += npairs) {
+            for (int unit = pair; unit < total_units; unit += npairs) {
+                const GemmUnit gu = gemm_unit(shape, unit);
+                if (gu.kb0 >= gu.kb1) continue;                              // empty K range (cannot happen for sane splits)
                 ptx::mbar_wait(tempty, acc_phase ^ 1);
                 ptx::tc_fence_after();
-                for (int kb = 0; kb < shape.k_blocks; ++kb) {
+                for (int kbg = gu.kb0; kbg < gu.kb1; ++kbg) {
+                    const int kb = kbg - gu.kb0;
+                    const int nkb = gu.kb1 - gu.kb0;
                     uint32_t d_tmem = tmem_base;
                     bool seg_start = (kb == 0);
                     if (SEG > 0) {
@@ -338,7 +370,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     if (SEG > 0) {
                         const int seg = kb / SEGD;
-                        const bool seg_end = ((kb + 1) % SEGD == 0) && (kb + 1 < shape.k_blocks);
+                        const bool seg_end = ((kb + 1) % SEGD == 0) && (kb + 1 < nkb);
                         if (seg_end && seg >= 1) ptx::mma_commit_pair(segfull);
                     }
                 }
@@ -351,12 +383,14 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         uint32_t acc_phase = 0, flushes = 0, nstore = 0;
         uint8_t* epi_smem = smem + S::EPI_OFF;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        for (int tile = pair; tile < total_tiles; tile += npairs) {
-            const int nt = tile / shape.m_tiles, mt = tile - nt * shape.m_tiles;
+        for (int unit = pair; unit < total_units; unit += npairs) {
+            const GemmUnit gu = gemm_unit(shape, unit);
+            if (gu.kb0 >= gu.kb1) continue;
+            const int nt = gu.tile / shape.m_tiles, mt = gu.tile - nt * shape.m_tiles;
             const uint32_t t0 = tmem_base + lane_off;
             uint32_t t1 = 0;
             if (SEG > 0) {
-                const int nseg = (shape.k_blocks + SEGD - 1) / SEGD;
+                const int nseg = (gu.kb1 - gu.kb0 + SEGD - 1) / SEGD;
                 const uint32_t tA = tmem_base + BLOCK_N + lane_off;
                 for (int sg = 1; sg + 1 < nseg; ++sg) {
                     ptx::mbar_wait(segfull, flushes & 1);
@@ -375,7 +409,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             }
             ptx::mbar_wait(tfull, acc_phase);
             ptx::tc_fence_after();
-            epi(mt * 2 + (int)rank, nt, q * 32 + lane, t0, t1, epi_smem, nstore);
+            epi(mt * 2 + (int)rank, nt, q * 32 + lane, t0, t1, epi_smem, nstore, gu.partial);
             ptx::tc_fence_before();
             ptx::mbar_arrive_leader(tempty);
             acc_phase ^= 1;
@@ -395,6 +429,7 @@ int launch_tc_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape sh
     auto kern = k_tc_gemm2<A_MN, B_MN, BLOCK_N, STAGES, SEG, Epi>;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     int tiles = shape.m_tiles * shape.n_tiles;
+    if (shape.tail_splits > 1) tiles = shape.full_tiles + (tiles - shape.full_tiles) * shape.tail_splits;
     int pairs = num_sms / 2;
     if (tiles < pairs) pairs = tiles;
     if (pairs < 1) return RBN_OK;

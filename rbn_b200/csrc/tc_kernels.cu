@@ -110,8 +110,8 @@ struct EpiStoreF32 {   // diagnostics: D -> float [M][N]
     static constexpr int kSmem = 0;
     float* D;
     int M, N, block_n;
-    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore) const {
-        (void)es; (void)nstore;
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore, bool partial) const {
+        (void)es; (void)nstore; (void)partial;
         int r = mt * kBM + row;
         for (int c0 = 0; c0 < block_n; c0 += 32) {
             float v[32];
@@ -136,10 +136,25 @@ struct EpiRule {
     int* ce;
     __half* lc;
     __half* rc;
-    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore) const {
+    float* acc;          // [chunk][N] fp32 partial sums of K-split tail tiles (finished by k_rule_finalize)
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore, bool partial) const {
         (void)es; (void)nstore;
         (void)nt;
         const int t = mt * kBM + row;
+        if (partial) {
+            float* dst = acc + (size_t)t * N;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                float v[32];
+                ptx::tmem_ld32_sum(t0, t1, c0, v);
+                if (t < cnt) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(v[j]), "f"(v[j + 1]),
+                                     "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                }
+            }
+            return;
+        }
         const int nI = L - w + 1;
         const int m = m0 + t;
         const int b = m / nI, i = m - b * nI, k = i + w;
@@ -185,7 +200,8 @@ struct EpiRule {
 struct EpiGY {
     static constexpr int kSmem = 32768;
     CUtensorMap tm;      // gY as [cnt rows][N*N cols], box {64, 128}
-    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore) const {
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore, bool partial) const {
+        (void)partial;
         for (int c0 = 0; c0 < 256; c0 += 64) {
             float v[64];
             ptx::tmem_ld32_sum(t0, t1, c0, v);
@@ -203,21 +219,29 @@ struct EpiCounts {
     static constexpr int kSmem = 0;
     float* gW;
     int N;
-    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore) const {
-        (void)es; (void)nstore;
+    __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore, bool partial) const {
+        (void)es; (void)nstore; (void)partial;
         (void)nt;
         float* dst = gW + ((size_t)mt * kBM + row) * N;
         for (int c0 = 0; c0 < N; c0 += 32) {
             float v[32];
             ptx::tmem_ld32_sum(t0, t1, c0, v);
+            const float sc = (float)(1 << kGabsShift);
+            if (partial) {        // several K-split units add into the same tile
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 o = *reinterpret_cast<float4*>(dst + c0 + j);
-                o.x += ldexpf(v[j], kGabsShift);
-                o.y += ldexpf(v[j + 1], kGabsShift);
-                o.z += ldexpf(v[j + 2], kGabsShift);
-                o.w += ldexpf(v[j + 3], kGabsShift);
-                *reinterpret_cast<float4*>(dst + c0 + j) = o;
+                for (int j = 0; j < 32; j += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(v[j] * sc),
+                                 "f"(v[j + 1] * sc), "f"(v[j + 2] * sc), "f"(v[j + 3] * sc) : "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = *reinterpret_cast<float4*>(dst + c0 + j);
+                    o.x += v[j] * sc;
+                    o.y += v[j + 1] * sc;
+                    o.z += v[j + 2] * sc;
+                    o.w += v[j + 3] * sc;
+                    *reinterpret_cast<float4*>(dst + c0 + j) = o;
+                }
             }
         }
     }
@@ -818,6 +842,37 @@ __global__ void k_copy_width1(int N, int L, int Lp, const int* __restrict__ leng
         r[a] = h;
     }
 }
+// max-shift epilogue of the K-split tail tiles of the rule GEMM: acc[t][a] (fp32 sums) -> chart, exponents, fp16 copies
+__global__ void k_rule_finalize(int N, int L, int Lp, int w, int m0, int t_begin, int cnt, const int* __restrict__ lengths,
+                                const float* __restrict__ wscale, const int* __restrict__ item_e,
+                                const float* __restrict__ acc, float* __restrict__ cv, int* __restrict__ ce,
+                                __half* __restrict__ lc, __half* __restrict__ rc) {
+    __shared__ float red[32];
+    const int t = t_begin + blockIdx.x;
+    if (t >= cnt) return;
+    const int nI = L - w + 1;
+    const int m = m0 + t;
+    const int b = m / nI, i = m - b * nI, k = i + w;
+    if (k > lengths[b]) return;
+    const int a = threadIdx.x;                       // blockDim.x == N
+    const float x = acc[(size_t)t * N + a] * wscale[a];
+    float mx = x;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((a & 31) == 0) red[a >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int q = 1; q < (blockDim.x >> 5); ++q) mx = fmaxf(mx, red[q]);
+    int e_new = 0;
+    if (mx > 0.f) frexpf(mx, &e_new);
+    const float v = ldexpf(x, -e_new);
+    const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
+    cv[cell * N + a] = v;
+    const __half h = __float2half_rn(v);
+    lc[((size_t)((size_t)b * L + i) * Lp + k) * N + a] = h;
+    rc[((size_t)((size_t)b * (L + 1) + k) * Lp + i) * N + a] = h;
+    if (a == 0) ce[cell] = item_e[t] + e_new;
+}
+
 // root seed into the start-major outside chart (and the prior gradient)
 __global__ void k_tc_outside_seed(int N, int L, int Lp, const float* __restrict__ prior, const int* __restrict__ lengths,
                                   const float* __restrict__ cv, const float* __restrict__ ws_zroot,
@@ -903,6 +958,7 @@ struct TcCtx {
     __half *lc, *rc, *wt, *wk, *y, *gy, *ghat, *gabs;
     int *wexp, *wbits, *item_e, *gexp;
     float* wscale;
+    float* acc;      // [chunk][N] K-split partial sums of the rule GEMM
     const int* lengths;
     cudaStream_t st;
 };
@@ -914,7 +970,7 @@ static void fill_ctx(TcCtx& c, const RbnDesc* d, const WsLayout& ws, char* base,
     c.lc = (__half*)(base + ws.lc); c.rc = (__half*)(base + ws.rc); c.wt = (__half*)(base + ws.wt);
     c.wk = (__half*)(base + ws.wk); c.y = (__half*)(base + ws.y); c.gy = (__half*)(base + ws.gy);
     c.ghat = (__half*)(base + ws.ghat); c.gabs = (__half*)(base + ws.gabs);
-    c.wexp = (int*)(base + ws.wexp); c.wbits = (int*)(base + ws.wbits); c.wscale = (float*)(base + ws.wscale); c.item_e = (int*)(base + ws.item_e); c.gexp = (int*)(base + ws.gexp);
+    c.wexp = (int*)(base + ws.wexp); c.wbits = (int*)(base + ws.wbits); c.wscale = (float*)(base + ws.wscale); c.acc = (float*)(base + ws.acc); c.item_e = (int*)(base + ws.item_e); c.gexp = (int*)(base + ws.gexp);
     c.lengths = lengths; c.st = st;
 }
 
@@ -971,12 +1027,30 @@ static int launch_k2_bn(TcCtx& c, int w, int m0, int cnt) {
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, c.wt, NN, (uint64_t)c.N, NN * 2, BN);
     if (rc) return rc;
-    EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.item_e, c.cv, c.ce, c.lc, c.rc};
+    EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.item_e, c.cv, c.ce, c.lc, c.rc, c.acc};
     if (use_pairs()) {
         CUtensorMap tmB2;
         rc = make_tmap_2d(&tmB2, c.wt, NN, (uint64_t)c.N, NN * 2, BN / 2);
         if (rc) return rc;
-        GemmShape shape2{(cnt + 255) / 256, 1, (int)(NN / 64)};
+        GemmShape shape2{(cnt + 255) / 256, 1, (int)(NN / 64), 0, 1};
+        // wave quantisation: the last, partial wave of tiles is split along K so that all CTA pairs stay busy
+        const int pairs = c.sms / 2, T = shape2.m_tiles;
+        const int full = (T / pairs) * pairs, r = T - full;
+        int splits = (r > 0) ? pairs / r : 1;
+        if (splits > 16) splits = 16;
+        while (splits > 1 && shape2.k_blocks / splits < 16) --splits;
+        if (splits > 1) {
+            shape2.full_tiles = full;
+            shape2.tail_splits = splits;
+            const int t_begin = full * 256;
+            RBN_CUDA_CHECK(cudaMemsetAsync(c.acc + (size_t)t_begin * c.N, 0, (size_t)(cnt - t_begin) * c.N * sizeof(float), c.st));
+            rc = launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, c.sms, c.st, "k_tc_gemm2<rule>", KC_RULE);
+            if (rc) return rc;
+            { ProfScope ps(KC_RULE, c.st);
+              k_rule_finalize<<<cnt - t_begin, c.N, 0, c.st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.item_e, c.acc, c.cv, c.ce, c.lc, c.rc); }
+            RBN_LAUNCH_CHECK("k_rule_finalize");
+            return RBN_OK;
+        }
         return launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, c.sms, c.st, "k_tc_gemm2<rule>", KC_RULE);
     }
     GemmShape shape{(cnt + 127) / 128, 1, (int)(NN / 64)};
@@ -1023,7 +1097,19 @@ static int launch_k4_bn(TcCtx& c, int cnt, float* gW) {
     if (rc) return rc;
     EpiCounts epi{gW, c.N};
     if (use_pairs() && BN % 128 == 0) {
-        GemmShape shape2{(int)(NN / 256), 1, (cnt + 63) / 64};
+        GemmShape shape2{(int)(NN / 256), 1, (cnt + 63) / 64, 0, 1};
+        {   // K-split so that the work units fill whole waves of CTA pairs (256 tiles on 74 pairs = 3.46 waves otherwise)
+            const int pairs = c.sms / 2, tiles = (int)(NN / 256);
+            int best = 1;
+            double best_eff = 0;
+            for (int sp = 1; sp <= 4; ++sp) {
+                if (shape2.k_blocks / sp < 16) break;
+                const int units = tiles * sp;
+                const double eff = (double)units / (((units + pairs - 1) / pairs) * (double)pairs);
+                if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
+            }
+            shape2.tail_splits = best;
+        }
         return launch_tc_gemm2<true, true, (BN % 128 == 0 ? BN : 128), 6, kSegBlocks, EpiCounts>(tmA, tmB, shape2, epi, c.sms, c.st, "k_tc_gemm2<counts>", KC_COUNTS);
     }
     GemmShape shape{(int)(NN / 128), 1, (cnt + 63) / 64};
