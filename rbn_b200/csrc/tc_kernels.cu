@@ -789,6 +789,147 @@ k_tc_gy(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box 
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+// K3, CTA-pair variant (cta_group::2): the pair keeps the gradient rows of 256 spans resident (128 per CTA) and every
+// CTA stages only HALF of each 256-row Wk tile, which halves both the TMA fill and the MMA operand reads per SM --
+// the 1-CTA kernel above is shared-memory-bandwidth bound (~250 B/cycle needed, 128 available).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box {64, 128}
+         const __grid_constant__ CUtensorMap tmW,     // Wk [N*N rows][N], box {64, 128}
+         const __grid_constant__ CUtensorMap tmOut,   // gY [cnt rows][N*N], box {64, 128}
+         int N, int supertiles, int ranges) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int kblocks = N / 64;
+    const int ntiles_total = N * N / 256;
+    const int ntiles_per_range = ntiles_total / ranges;
+    uint8_t* sAres = smem;                                        // [kblocks] x 16 KB (this CTA's 128 rows)
+    uint8_t* sBring = sAres + (size_t)kblocks * 16384;            // [stages] x 16 KB (this CTA's half of a Wk tile)
+    uint8_t* ebuf = sBring + kGYStages * 16384;                   // [2 groups][2] x 16 KB staging tiles
+    uint64_t* full = (uint64_t*)(ebuf + 65536);
+    uint64_t* empty = full + kGYStages;
+    uint64_t* tfull = empty + kGYStages;      // [2]
+    uint64_t* tempty = tfull + 2;             // [2]
+    uint64_t* a_full = tempty + 2;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(a_empty + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = (rank == 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGYStages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], 512);
+        }
+        ptx::mbar_init(a_full, 1);
+        ptx::mbar_init(a_empty, 1);
+        ptx::fence_barrier_init();
+        ptx::tma_prefetch_desc(&tmG);
+        ptx::tma_prefetch_desc(&tmW);
+        ptx::tma_prefetch_desc(&tmOut);
+    }
+    if (warp == 2) ptx::tmem_alloc2(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int units = supertiles * ranges;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int unit = pair; unit < units; unit += npairs) {
+                const int st = unit / ranges, r = unit - st * ranges;
+                ptx::mbar_wait(a_empty, aphase ^ 1);
+                if (leader) ptx::mbar_expect_tx(a_full, (uint32_t)2 * kblocks * 16384);
+                for (int kb = 0; kb < kblocks; ++kb)
+                    ptx::tma_load_2d_pair(sAres + (size_t)kb * 16384, &tmG, a_full, kb * 64, st * 256 + (int)rank * 128);
+                aphase ^= 1;
+                for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt)
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        ptx::mbar_wait(&empty[stage], phase ^ 1);
+                        if (leader) ptx::mbar_expect_tx(&full[stage], 2 * 16384);
+                        ptx::tma_load_2d_pair(sBring + stage * 16384, &tmW, &full[stage], kb * 64, nt * 256 + (int)rank * 128);
+                        if (++stage == kGYStages) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            const uint32_t idesc = ptx::make_idesc_f16(256, 256, false, false, 0);
+            int stage = 0, buf = 0;
+            uint32_t phase = 0, aphase = 0, bphase = 0;
+            for (int unit = pair; unit < units; unit += npairs) {
+                const int st = unit / ranges, r = unit - st * ranges;
+                (void)st;
+                ptx::mbar_wait(a_full, aphase);
+                aphase ^= 1;
+                ptx::tc_fence_after();
+                const uint32_t aA = ptx::smem_u32(sAres);
+                for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt) {
+                    ptx::mbar_wait(&tempty[buf], bphase ^ 1);
+                    ptx::tc_fence_after();
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        ptx::mbar_wait(&full[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t sB = ptx::smem_u32(sBring + stage * 16384);
+                        const uint32_t sA = aA + (uint32_t)kb * 16384;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::mma_f16_ss_pair(tmem_base + buf * 256, ptx::make_smem_desc(sA + k * 32, 16, 1024),
+                                                 ptx::make_smem_desc(sB + k * 32, 16, 1024), idesc, (uint32_t)((kb | k) != 0));
+                        ptx::mma_commit_pair(&empty[stage]);
+                        if (++stage == kGYStages) { stage = 0; phase ^= 1; }
+                    }
+                    ptx::mma_commit_pair(&tfull[buf]);
+                    if (++buf == 2) { buf = 0; bphase ^= 1; }
+                }
+                ptx::mma_commit_pair(a_empty);
+            }
+        }
+    } else if (warp >= 4) {
+        // two epilogue groups per CTA: warps 4-7 drain columns 0-127, warps 8-11 columns 128-255 of every accumulator
+        const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const bool issuer = ((threadIdx.x - 128) & 127) == 0;
+        uint8_t* mybuf = ebuf + grp * 32768;
+        int buf = 0;
+        uint32_t bphase = 0, nstore = 0;
+        for (int unit = pair; unit < units; unit += npairs) {
+            const int st = unit / ranges, r = unit - st * ranges;
+            for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt) {
+                ptx::mbar_wait(&tfull[buf], bphase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + buf * 256 + grp * 128 + ((uint32_t)(q * 32) << 16);
+                for (int c0 = 0; c0 < 128; c0 += 64) {
+                    float v[64];
+                    ptx::tmem_ld32(taddr + c0, v);
+                    ptx::tmem_ld32(taddr + c0 + 32, v + 32);
+                    ptx::tmem_ld_wait();
+                    ptx::stage_store_tile(mybuf, &tmOut, nt * 256 + grp * 128 + c0, st * 256 + (int)rank * 128, row, v, nstore, 3 + grp, issuer, true);
+                    ++nstore;
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive_leader(&tempty[buf]);
+                if (++buf == 2) { buf = 0; bphase ^= 1; }
+            }
+        }
+        if (issuer) ptx::bulk_wait_all();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc2(tmem_base, 512);
+}
+
 // =======================================================================================================================
 // element-wise helpers of the tensor-core path
 // =======================================================================================================================
@@ -1075,6 +1216,18 @@ static int launch_k3(TcCtx& c, int cnt) {
     rc = make_tmap_2d(&tmOut, c.gy, NN, (uint64_t)cnt, NN * 2, 128);
     if (rc) return rc;
     int supertiles = (cnt + 255) / 256;
+    if (use_pairs()) {
+        int ntiles2 = (int)(NN / 256), pairs = c.sms / 2;
+        int ranges2 = 1;
+        while (ranges2 < 16 && supertiles * ranges2 < 2 * pairs && ntiles2 % (ranges2 * 2) == 0 && ntiles2 / (ranges2 * 2) >= 8) ranges2 *= 2;
+        size_t smem2 = (size_t)(c.N / 64) * 16384 + kGYStages * 16384 + 65536 + 256 + 1024;
+        RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gy2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        int units2 = supertiles * ranges2;
+        int np = units2 < pairs ? units2 : pairs;
+        { ProfScope ps(KC_GY, c.st); k_tc_gy2<<<2 * np, 384, smem2, c.st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges2); }
+        RBN_LAUNCH_CHECK("k_tc_gy2");
+        return RBN_OK;
+    }
     int ntiles = (int)(NN / 128);
     int ranges = 1;
     while (ranges < 16 && supertiles * ranges < 2 * c.sms && ntiles % (ranges * 2) == 0 && ntiles / (ranges * 2) >= 8) ranges *= 2;
