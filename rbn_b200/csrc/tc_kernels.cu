@@ -470,6 +470,8 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths,
                const __grid_constant__ CUtensorMap tmAL,    // alphaL (start-major outside chart, fp32), box {128, 32}
                const __grid_constant__ CUtensorMap tmAR,    // alphaR (end-major), box {128, 32}
+               const __grid_constant__ CUtensorMap tmALt,   // same charts, box {128, tail_rows}: last chunk of a span's splits
+               const __grid_constant__ CUtensorMap tmARt,
                const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -613,7 +615,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                 ptx::tc_fence_after();
                 const int xl = q * 32 + lane;                    // row of the 128-wide tile
                 const uint32_t taddr = tmem_base + u * 128 + ((uint32_t)(q * 32) << 16);
-                for (int c0 = 0; c0 < Npad; c0 += 32) {
+                for (int c0 = 0; c0 < w - 1; c0 += 32) {
                     float v[32];
                     ptx::tmem_ld32(taddr + c0, v);
                     float* tile = reinterpret_cast<float*>(mybuf + (nred & 1) * 16384);
@@ -625,7 +627,9 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                     ptx::fence_proxy_async_smem();
                     ptx::named_bar_sync(2 + grp, 128);
                     if (issuer) {
-                        ptx::tma_reduce_add_2d(kind ? &tmAR : &tmAL, tile, h * 128, (kind ? rowR : rowL) + c0);
+                        const bool last = (c0 + 32 >= w - 1);       // the tail box covers only the rows that hold splits
+                        const CUtensorMap* tm = kind ? (last ? &tmARt : &tmAR) : (last ? &tmALt : &tmAL);
+                        ptx::tma_reduce_add_2d(tm, tile, h * 128, (kind ? rowR : rowL) + c0);
                         ptx::bulk_commit();
                     }
                     ++nred;
@@ -1289,15 +1293,20 @@ static int launch_k5(TcCtx& c, int w, int m0, int cnt) {
     if (rc) return rc;
     rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, (uint32_t)Npad);
     if (rc) return rc;
-    CUtensorMap tmAL, tmAR;
+    CUtensorMap tmAL, tmAR, tmALt, tmARt;
+    const uint32_t tail_rows = (uint32_t)(((w - 1) % 32) ? ((w - 1) % 32) : 32);
     rc = make_tmap_2d_f32(&tmAL, c.alpha, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 4, 128, 32);
     if (rc) return rc;
     rc = make_tmap_2d_f32(&tmAR, c.alpha2, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 4, 128, 32);
     if (rc) return rc;
+    rc = make_tmap_2d_f32(&tmALt, c.alpha, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 4, 128, tail_rows);
+    if (rc) return rc;
+    rc = make_tmap_2d_f32(&tmARt, c.alpha2, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 4, 128, tail_rows);
+    if (rc) return rc;
     size_t smem = (size_t)kK5Stages * kK5StageBytes + 65536 + 256 + 2048 + 1024;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < c.sms ? cnt : c.sms;
-    { ProfScope ps(KC_CHILD, c.st); k_tc_childgrad<<<grid, 384, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, tmAL, tmAR, c.ce, c.item_e,
+    { ProfScope ps(KC_CHILD, c.st); k_tc_childgrad<<<grid, 384, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, tmAL, tmAR, tmALt, tmARt, c.ce, c.item_e,
                                               c.gexp); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;
