@@ -100,3 +100,42 @@ def test_tc_path_vs_cuda_core_path_long():
     W, T, pr, tok, lengths, coef = inp
     assert abs((gW_t * W).sum() - (coef * (lengths - 1)).sum()) <= 1e-3 * (coef * lengths).sum()
     assert abs((gT_t * T).sum() - (coef * lengths).sum()) <= 1e-3 * (coef * lengths).sum()
+
+
+def test_full_size_shape_properties_n256_l128():
+    """BASELINE configs[2] shape (N = 256, L = 128) through size-independent properties: expected-count identities
+    (binary L-1, terminal L, prior 1 per sequence), permutation invariance over the batch, and agreement of the
+    shared prefix lengths with independently run shorter batches."""
+    from oracle import inside_oracle as O
+    from rbn_b200 import inside_logZ, _lib
+    N, V, L = 256, 32, 128
+    W, T, pr = O.synthetic_grammar(N, V, seed=0)
+    tok, _ = O.synthetic_tokens(6, L, V, seed=1)
+    lengths = np.array([128, 128, 100, 77, 64, 5])
+    for b in range(6):
+        tok[b, lengths[b]:] = -1
+    Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+    lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), path=_lib.PATH_TCGEN05)
+    assert torch.isfinite(lz).all()
+    lz.sum().backward()
+    gW, gT, gP = Wt.grad.cpu().numpy(), Tt.grad.cpu().numpy(), pt.grad.cpu().numpy()
+    tot = float(lengths.sum())
+    assert abs((gW * W).sum() - (lengths - 1).sum()) <= 1e-3 * tot
+    assert abs((gT * T).sum() - tot) <= 1e-3 * tot
+    assert abs((gP * pr).sum() - 6) <= 1e-3 * 6
+    # permutation of the batch + a different chunking must not change any sequence's result
+    perm = np.array([3, 0, 5, 2, 1, 4])
+    lz2 = inside_logZ(torch.tensor(W, device="cuda"), torch.tensor(T, device="cuda"), torch.tensor(pr, device="cuda"),
+                      torch.tensor(tok[perm]), torch.tensor(lengths[perm]), path=_lib.PATH_TCGEN05, chunk_items=256)
+    np.testing.assert_allclose(lz2.cpu().numpy(), lz.detach().cpu().numpy()[perm], rtol=2e-6)
+
+
+def test_n256_vs_oracle_medium_length():
+    from oracle import inside_oracle as O
+    from rbn_b200 import _lib
+    inp, lz, gW, gT, gP = _run(256, 32, 40, 2, True, seed=21, path=_lib.PATH_TCGEN05)
+    W, T, pr, tok, lengths, coef = inp
+    lz_ref, gW_ref, gT_ref, gP_ref = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths, grad_logZ=coef)
+    assert np.abs(lz - lz_ref.numpy()).max() <= LOGZ_RTOL * np.abs(lz_ref.numpy()).max()
+    errs = (_rel(gW, gW_ref.numpy()), _rel(gT, gT_ref.numpy()), _rel(gP, gP_ref.numpy()))
+    assert max(errs) <= GRAD_RTOL, errs
