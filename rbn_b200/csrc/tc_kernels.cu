@@ -913,16 +913,17 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
                 ptx::mbar_wait(&tfull[buf], bphase);
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem_base + buf * 256 + grp * 128 + ((uint32_t)(q * 32) << 16);
+                float v[128];
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) ptx::tmem_ld32(taddr + c0, v + c0);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive_leader(&tempty[buf]);           // the accumulator is in registers: release it early
+#pragma unroll
                 for (int c0 = 0; c0 < 128; c0 += 64) {
-                    float v[64];
-                    ptx::tmem_ld32(taddr + c0, v);
-                    ptx::tmem_ld32(taddr + c0 + 32, v + 32);
-                    ptx::tmem_ld_wait();
-                    ptx::stage_store_tile(mybuf, &tmOut, nt * 256 + grp * 128 + c0, st * 256 + (int)rank * 128, row, v, nstore, 3 + grp, issuer, true);
+                    ptx::stage_store_tile(mybuf, &tmOut, nt * 256 + grp * 128 + c0, st * 256 + (int)rank * 128, row, v + c0, nstore, 3 + grp, issuer, true);
                     ++nstore;
                 }
-                ptx::tc_fence_before();
-                ptx::mbar_arrive_leader(&tempty[buf]);
                 if (++buf == 2) { buf = 0; bphase ^= 1; }
             }
         }

@@ -72,9 +72,13 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 template <int NBUF = 2>
 __device__ __forceinline__ void stage_store_tile(uint8_t* bufs, const CUtensorMap* tm, int x, int y, int row,
                                                  const float* v, uint32_t nstore, uint32_t bar_id, bool issuer, bool active) {
+    // One barrier per tile: buffer (nstore & 1) was declared free by the barrier of the previous call (before which
+    // the issuer had waited for the store that last read it), so it can be written straight away.
     uint8_t* buf = bufs + (NBUF == 2 ? (nstore & 1) * 16384 : 0);
-    if (issuer) bulk_wait_read<NBUF - 1>();          // the store that last used this buffer has been read
-    named_bar_sync(bar_id, 128);
+    if (NBUF == 1) {
+        if (issuer) bulk_wait_read<0>();
+        named_bar_sync(bar_id, 128);
+    }
     uint4 pk[8];
     __half2* h = reinterpret_cast<__half2*>(pk);
 #pragma unroll
@@ -83,6 +87,7 @@ __device__ __forceinline__ void stage_store_tile(uint8_t* bufs, const CUtensorMa
     for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(buf + row * 128 + ((c ^ (row & 7)) << 4)) = pk[c];
     fence_proxy_async_smem();
+    if (NBUF == 2 && issuer) bulk_wait_read<0>();    // the previous store (other buffer) has been read: free after the barrier
     named_bar_sync(bar_id, 128);
     if (issuer && active) {
         tma_store_2d(tm, buf, x, y);
