@@ -33,6 +33,10 @@ WORKLOADS = {
                name="PCFG N=256 L=128 batch 512/GPU inside+outside (BASELINE configs[2])"),
     "c2": dict(N=64, V=32, L=64, B=1024, outside=False,
                name="discrete RBN N=64 L=64 batch 1024/GPU inside only (BASELINE configs[1])"),
+    # configs[4]: global batch 8192 over 8 GPUs = 1024 sequences per GPU, run as micro-batches of 512 (chart + outside
+    # chart of 512 sequences are 88 GB at N = 512); counts accumulate over the micro-batches, one all-reduce per step
+    "c5": dict(N=512, V=32, L=128, B=1024, micro=512, outside=True,
+               name="PCFG N=512 L=128 batch 1024/GPU (8192 over 8 GPUs) inside+outside, EM E-step (BASELINE configs[4])"),
     "tiny": dict(N=64, V=32, L=16, B=8, outside=True, name="tiny self-test"),
 }
 
@@ -221,14 +225,21 @@ def run_ours(args, wl):
         if world > 1:
             allreduce_counts(tensors)
 
+    micro = min(B, wl.get("micro", B))
+
     def device_step():
-        lz = inside_logZ(Wd, Td, pd, tok_d, len_d, chunk_items=args.chunk)
         if wl["outside"]:
             for t in (Wd, Td, pd):
                 t.grad = None
-            lz.sum().backward()
+        outs = []
+        for b0 in range(0, B, micro):       # micro-batches share the workspace; their counts accumulate in .grad
+            lz = inside_logZ(Wd, Td, pd, tok_d[b0:b0 + micro], len_d[b0:b0 + micro], chunk_items=args.chunk)
+            if wl["outside"]:
+                lz.sum().backward()
+            outs.append(lz.detach())
+        if wl["outside"]:
             allreduce_grads([Wd.grad, Td.grad, pd.grad])
-        return lz
+        return outs[0] if len(outs) == 1 else torch.cat(outs)
 
     def barrier():
         if world > 1:
@@ -272,14 +283,19 @@ def run_ours(args, wl):
     def e2e_step():
         tk = tok_pin.to(dev, non_blocking=True)
         ln = len_pin.to(dev, non_blocking=True)
-        lz = model.log_inside_batch(tokens=tk, lengths=ln)
-        loss = -lz.sum()
         if wl["outside"]:
             for p in params:
                 p.grad = None
-            loss.backward()
+        total = None
+        for b0 in range(0, B, micro):
+            lz = model.log_inside_batch(tokens=tk[b0:b0 + micro], lengths=ln[b0:b0 + micro])
+            loss = -lz.sum()
+            if wl["outside"]:
+                loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        if wl["outside"]:
             allreduce_grads([p.grad for p in params])
-        return float(loss)          # device -> host read of the step's result
+        return float(total)         # device -> host read of the step's result
 
     if args.skip_e2e:
         ms_e2e = float('nan')

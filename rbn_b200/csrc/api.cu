@@ -72,13 +72,13 @@ static bool desc_ok(const RbnDesc* d) {
     return true;
 }
 
-static bool tc_shape_ok(const RbnDesc* d) { return d->N % 64 == 0 && d->N >= 64 && d->N <= 256 && d->L >= 2; }
+static bool tc_shape_ok(const RbnDesc* d) { return ((d->N % 64 == 0 && d->N >= 64 && d->N <= 256) || d->N == 512) && d->L >= 2; }
 
 int resolve_path(const RbnDesc* d) {
     if (d->path == RBN_PATH_SIMT) return RBN_PATH_SIMT;
     if (d->path == RBN_PATH_TCGEN05) {
         if (!tc_shape_ok(d)) {
-            set_error("tensor-core path needs N in {64,128,192,256} and L >= 2 (got N=%d L=%d)", d->N, d->L);
+            set_error("tensor-core path needs N in {64,128,192,256,512} and L >= 2 (got N=%d L=%d)", d->N, d->L);
             return RBN_E_UNSUPPORTED;
         }
         return RBN_PATH_TCGEN05;
@@ -102,7 +102,8 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         size_t Lp = align_up(L + 32, 16);
         o->Lp = (int)Lp;
         size_t max_items = B * (L - 1);                        // widest diagonal (w = 2)
-        // default: whole waves of 128-span tiles on 148 SMs, split-sum buffer Y of at most ~6 GB
+        // default: whole waves of 128-span tiles on 148 SMs, split-sum buffer Y of at most ~6 GB per slot
+        const TcTune& tune = tc_tune();
         size_t wave = 148 * 128;
         size_t chunk = (size_t)(6.0e9 / (2.0 * N * N)) / wave * wave;
         if (chunk < wave) chunk = wave;
@@ -110,6 +111,8 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         if (chunk > max_items) chunk = max_items;
         chunk = align_up(chunk, 128);
         o->chunk = (int)chunk;
+        const size_t ns = (size_t)(tune.overlap ? tune.nslot : 1);
+        o->nslot = (int)ns;
         // outside charts of the tensor-core path: start-major (left-child sums + root seed) and end-major (right-child sums)
         o->alpha = take(B * L * Lp * N * sizeof(float));
         o->alpha2 = take(B * (L + 1) * Lp * N * sizeof(float));
@@ -120,13 +123,13 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->wexp = take(N * sizeof(int));
         o->wscale = take(N * sizeof(float));
         o->wbits = take(N * sizeof(int));
-        o->y = take(chunk * N * N * sizeof(__half));
-        o->gy = take(chunk * N * N * sizeof(__half));
-        o->item_e = take(chunk * sizeof(int));
-        o->ghat = take(chunk * N * sizeof(__half));
-        o->gabs = take(chunk * N * sizeof(__half));
-        o->gexp = take(chunk * sizeof(int));
-        o->acc = take(chunk * N * sizeof(float));
+        o->y = take(ns * chunk * N * N * sizeof(__half));
+        o->gy = take(ns * chunk * N * N * sizeof(__half));
+        o->item_e = take(ns * chunk * sizeof(int));
+        o->ghat = take(ns * chunk * N * sizeof(__half));
+        o->gabs = take(ns * chunk * N * sizeof(__half));
+        o->gexp = take(ns * chunk * sizeof(int));
+        o->acc = take(ns * chunk * N * sizeof(float));
     }
     o->total = off;
     return true;

@@ -56,17 +56,35 @@ struct WsLayout {
     size_t wexp;        // int32 [N]   W = W16 * 2^wexp[a]
     size_t wscale;      // float [N]   2^wexp[a]
     size_t wbits;       // int32 [N]   scratch: float bits of max_{b,c} W[b][c][a]
-    size_t y;           // half [chunk][N*N]
-    size_t gy;          // half [chunk][N*N]
-    size_t item_e;      // int32 [chunk]         E_m = max_j (e_ij + e_jk)
-    size_t ghat;        // half [chunk][N]       item-normalised upstream gradient
-    size_t gabs;        // half [chunk][N]       absolutely scaled upstream gradient (for the count GEMM)
-    size_t gexp;        // int32 [chunk]
-    size_t acc;         // float [chunk][N]  K-split partial sums of the rule GEMM's tail tiles
+    // per-chunk buffers: `nslot` copies each (slot s at offset + s * chunk * row bytes), so that chunks in flight on
+    // the two launch streams of the overlapped schedule never share a buffer
+    size_t y;           // half [nslot][chunk][N*N]
+    size_t gy;          // half [nslot][chunk][N*N]
+    size_t item_e;      // int32 [nslot][chunk]         E_m = max_j (e_ij + e_jk)
+    size_t ghat;        // half [nslot][chunk][N]       item-normalised upstream gradient
+    size_t gabs;        // half [nslot][chunk][N]       absolutely scaled upstream gradient (for the count GEMM)
+    size_t gexp;        // int32 [nslot][chunk]
+    size_t acc;         // float [nslot][chunk][N]  K-split partial sums of the rule GEMM's tail tiles
     size_t total;
     int Lp;
     int chunk;
+    int nslot;
 };
+
+// ---- schedule of the tensor-core path (read once from the environment) -----------------------
+// overlap = 1: two launch streams with disjoint SM partitions.  Write-bound kernels (split-sum, gY GEMM) run beside
+// read-/tensor-bound ones (rule GEMM, count GEMM, child gradients) of ANOTHER group of sequences, so that both
+// directions of the HBM interface and the tensor pipe are busy at the same time.
+struct TcTune {
+    int overlap;        // RBN_TC_OVERLAP   (default 0: measured slower on B200)
+    int groups;         // RBN_TC_GROUPS    sequence groups that pipeline against each other (default 2)
+    int fwd_sms0;       // RBN_TC_FWD_SMS0  SMs of the split-sum partition in the inside pass (even)
+    int bwd_sms0;       // RBN_TC_BWD_SMS0  SMs of the {split-sum, prep, gY} partition in the outside pass (even)
+    int nslot;          // RBN_TC_SLOTS     per-chunk buffer copies
+    int k3_stream;      // RBN_TC_K3_STREAM 0: gY GEMM beside the split-sum, 1: beside the child-gradient kernel
+};
+const TcTune& tc_tune();
+int device_sm_count();
 
 // ---- per-kernel-class launch accounting (always) and CUDA-event timing (when enabled) ------------------------------
 enum KernelClass { KC_EMISSION = 0, KC_SPLITSUM, KC_RULE, KC_GY, KC_COUNTS, KC_CHILD, KC_PREP, KC_SIMT_INSIDE,

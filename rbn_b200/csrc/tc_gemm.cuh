@@ -20,6 +20,9 @@ struct GemmShape {
     // 2-CTA kernel only: tiles [0, full_tiles) are computed whole; every later tile is split along K into tail_splits
     // work units whose partial sums the epilogue adds atomically (wave-quantisation fix).  tail_splits <= 1: no split.
     int full_tiles, tail_splits;
+    // 2-CTA kernel only: every unit reports partial = true (N = 512: the max-shift epilogue needs both halves of a row,
+    // so all tiles add into the fp32 buffer that k_rule_finalize turns into chart cells)
+    int all_partial;
 };
 
 struct GemmUnit {
@@ -34,7 +37,7 @@ __device__ __forceinline__ int gemm_units(const GemmShape& s) {
 __device__ __forceinline__ GemmUnit gemm_unit(const GemmShape& s, int u) {
     GemmUnit r;
     if (s.tail_splits <= 1 || u < s.full_tiles) {
-        r.tile = u; r.kb0 = 0; r.kb1 = s.k_blocks; r.partial = false;
+        r.tile = u; r.kb0 = 0; r.kb1 = s.k_blocks; r.partial = s.all_partial != 0;
     } else {
         const int v = u - s.full_tiles;
         const int per = (s.k_blocks + s.tail_splits - 1) / s.tail_splits;
@@ -303,8 +306,8 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             uint32_t phase = 0;
             for (int unit = pair; unit < total_units; unit += npairs) {
                 const GemmUnit gu = gemm_unit(shape, unit);
-                const int nt = gu.tile / shape.m_tiles, mt = gu.tile - nt * shape.m_tiles;
-                const int row0 = mt * 256 + (int)rank * kBM;                 // this CTA's rows of A
+                const int mt = gu.tile / shape.n_tiles, nt = gu.tile - mt * shape.n_tiles;   // n fastest: the pairs that
+                const int row0 = mt * 256 + (int)rank * kBM;                 // share an A tile run side by side (L2 hit)
                 const int col0 = nt * BLOCK_N + (int)rank * HALF_N;          // this CTA's half of B
                 for (int kb = gu.kb0; kb < gu.kb1; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -386,7 +389,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         for (int unit = pair; unit < total_units; unit += npairs) {
             const GemmUnit gu = gemm_unit(shape, unit);
             if (gu.kb0 >= gu.kb1) continue;
-            const int nt = gu.tile / shape.m_tiles, mt = gu.tile - nt * shape.m_tiles;
+            const int mt = gu.tile / shape.n_tiles, nt = gu.tile - mt * shape.n_tiles;
             const uint32_t t0 = tmem_base + lane_off;
             uint32_t t1 = 0;
             if (SEG > 0) {

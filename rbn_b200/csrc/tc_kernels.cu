@@ -16,6 +16,7 @@
 #include <limits.h>
 #include <stdlib.h>
 #include <mutex>
+#include <vector>
 
 namespace rbn {
 
@@ -137,13 +138,13 @@ struct EpiRule {
     __half* lc;
     __half* rc;
     float* acc;          // [chunk][N] fp32 partial sums of K-split tail tiles (finished by k_rule_finalize)
+    int bn;              // parents per tile (N, or 256 when N = 512: every tile is then 'partial' and nt selects the half)
     __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore, bool partial) const {
         (void)es; (void)nstore;
-        (void)nt;
         const int t = mt * kBM + row;
         if (partial) {
-            float* dst = acc + (size_t)t * N;
-            for (int c0 = 0; c0 < N; c0 += 32) {
+            float* dst = acc + (size_t)t * N + nt * bn;
+            for (int c0 = 0; c0 < bn; c0 += 32) {
                 float v[32];
                 ptx::tmem_ld32_sum(t0, t1, c0, v);
                 if (t < cnt) {
@@ -219,11 +220,11 @@ struct EpiCounts {
     static constexpr int kSmem = 0;
     float* gW;
     int N;
+    int bn;              // parents per tile (N, or 256 when N = 512)
     __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore, bool partial) const {
         (void)es; (void)nstore; (void)partial;
-        (void)nt;
-        float* dst = gW + ((size_t)mt * kBM + row) * N;
-        for (int c0 = 0; c0 < N; c0 += 32) {
+        float* dst = gW + ((size_t)mt * kBM + row) * N + nt * bn;
+        for (int c0 = 0; c0 < bn; c0 += 32) {
             float v[32];
             ptx::tmem_ld32_sum(t0, t1, c0, v);
             const float sc = (float)(1 << kGabsShift);
@@ -266,9 +267,13 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int Kpad = ((w - 1) + 15) & ~15;
     const int parts = (Kpad + 63) / 64;
-    const int halves = (N + 127) / 128;
-    const int a_atoms = halves * 2;            // A operand covers halves * 128 rows (zero beyond N)
-    const int b_atoms = N / 64;
+    // N > 256: the N x N split-sum is cut into (N/256)^2 sub-blocks of 256 x 256, each handled like a span of its own
+    const int NS = N > 256 ? 256 : N;          // nonterminals per sub-block side
+    const int nblk = N / NS;
+    const int nsub = nblk * nblk;
+    const int halves = (NS + 127) / 128;
+    const int a_atoms = halves * 2;            // A operand covers halves * 128 rows (zero beyond NS)
+    const int b_atoms = NS / 64;
     const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * 8192;
     uint8_t* ybuf = smem + (size_t)stages * stage_bytes;       // 2 x 16 KB staging tiles for the Y stores
     uint8_t* tail = ybuf + 32768;
@@ -282,7 +287,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     float* cj = (float*)(red + 4);                // [128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t TMEM_COLS = tmem_cols_pow2(halves * N);
+    const uint32_t TMEM_COLS = tmem_cols_pow2(halves * NS);
     const int nI = L - w + 1;
     const size_t C = cells_per_seq(L);
 
@@ -323,18 +328,21 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                 if (k > lengths[b]) continue;
                 const int lc_row = (int)(((size_t)b * L + i) * Lp + (i + 1));
                 const int rc_row = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
-                for (int part = 0; part < parts; ++part) {
-                    ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sL = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sR = sL + (size_t)a_atoms * 8192;
-                    // the box of this slab holds exactly Ks = min(64, Kpad - 64 part) chart rows (its atom stays 8 KB apart)
-                    const int Ks = min(64, Kpad - part * 64);
-                    ptx::mbar_expect_tx(&tma_full[stage], (uint32_t)b_atoms * 2 * (uint32_t)Ks * 128);
-                    for (int a = 0; a < b_atoms; ++a) {
-                        ptx::tma_load_2d(sL + a * 8192, part ? &tmLC1 : &tmLC, &tma_full[stage], a * 64, lc_row + part * 64);
-                        ptx::tma_load_2d(sR + a * 8192, part ? &tmRC1 : &tmRC, &tma_full[stage], a * 64, rc_row + part * 64);
+                for (int sub = 0; sub < nsub; ++sub) {
+                    const int bcol = (sub / nblk) * NS, ccol = (sub % nblk) * NS;
+                    for (int part = 0; part < parts; ++part) {
+                        ptx::mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sL = smem + (size_t)stage * stage_bytes;
+                        uint8_t* sR = sL + (size_t)a_atoms * 8192;
+                        // the box of this slab holds exactly Ks = min(64, Kpad - 64 part) chart rows (its atom stays 8 KB apart)
+                        const int Ks = min(64, Kpad - part * 64);
+                        ptx::mbar_expect_tx(&tma_full[stage], (uint32_t)b_atoms * 2 * (uint32_t)Ks * 128);
+                        for (int a = 0; a < b_atoms; ++a) {
+                            ptx::tma_load_2d(sL + a * 8192, part ? &tmLC1 : &tmLC, &tma_full[stage], bcol + a * 64, lc_row + part * 64);
+                            ptx::tma_load_2d(sR + a * 8192, part ? &tmRC1 : &tmRC, &tma_full[stage], ccol + a * 64, rc_row + part * 64);
+                        }
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -343,7 +351,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         const int p = threadIdx.x - 128;                // 0..127
         int stage = 0;
         uint32_t phase = 0;
-        const int chunks_per_row = N / 8;               // 16-byte chunks per chart row
+        const int chunks_per_row = NS / 8;              // 16-byte chunks per (sub-block) chart row
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI, k = i + w;
@@ -363,7 +371,8 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
             cj[p] = (p < w - 1) ? ldexpf(1.0f, max(sft - E, -60)) : 0.f;
             if (p == 0) item_e[t] = E;
             ptx::named_bar_sync(1, 128);
-            for (int part = 0; part < parts; ++part) {
+            for (int sp = 0; sp < nsub * parts; ++sp) {
+                const int part = sp % parts;
                 const int Ks = min(64, Kpad - part * 64);
                 ptx::mbar_wait(&tma_full[stage], phase);
                 uint8_t* sL = smem + (size_t)stage * stage_bytes;
@@ -391,13 +400,14 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     } else if (warp == 9) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_f16(128, N, true, true, 0);
+            const uint32_t idesc = ptx::make_idesc_f16(128, NS, true, true, 0);
             int stage = 0;
             uint32_t phase = 0, it_phase = 0;
             for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
                 const int m = m0 + t;
                 const int b = m / nI, i = m - b * nI;
                 if (i + w > lengths[b]) continue;
+                for (int sub = 0; sub < nsub; ++sub) {
                 for (int part = 0; part < parts; ++part) {
                     const int Ks = min(64, Kpad - part * 64);
                     ptx::mbar_wait(&fix_full[stage], phase);
@@ -412,7 +422,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                         for (int k16 = 0; k16 < Ks / 16; ++k16) {
                             const uint64_t ad = ptx::make_smem_desc(aL + (uint32_t)(h * 2) * 8192 + k16 * 2048, 8192, 1024);
                             const uint64_t bd = ptx::make_smem_desc(aR + k16 * 2048, 8192, 1024);
-                            ptx::mma_f16_ss(tmem_base + h * N, ad, bd, idesc, (uint32_t)!(part == 0 && k16 == 0));
+                            ptx::mma_f16_ss(tmem_base + h * NS, ad, bd, idesc, (uint32_t)!(part == 0 && k16 == 0));
                         }
                         if (part == parts - 1) ptx::mma_commit(&acc_full[h]);
                     }
@@ -420,6 +430,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 it_phase ^= 1;
+                }
             }
         }
     } else if (warp < 4) {
@@ -431,23 +442,26 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI;
             if (i + w > lengths[b]) continue;
-            for (int h = 0; h < halves; ++h) {
-                ptx::mbar_wait(&acc_full[h], it_phase);
-                ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + h * N + ((uint32_t)(warp * 32) << 16);
-                const bool tail_half = (h * 128 + 128 > N);          // only 64 valid rows (N = 64 or 192)
-                for (int c0 = 0; c0 < N; c0 += 64) {
-                    float v[64];
-                    ptx::tmem_ld32(taddr + c0, v);
-                    ptx::tmem_ld32(taddr + c0 + 32, v + 32);
-                    ptx::tmem_ld_wait();
-                    ptx::stage_store_tile(ybuf, tail_half ? &tmYtail : &tmY, c0, t * N + h * 128, row, v, nstore, 3, issuer, true);
-                    ++nstore;
+            for (int sub = 0; sub < nsub; ++sub) {
+                const int brow = (sub / nblk) * NS, ccol = (sub % nblk) * NS;
+                for (int h = 0; h < halves; ++h) {
+                    ptx::mbar_wait(&acc_full[h], it_phase);
+                    ptx::tc_fence_after();
+                    const uint32_t taddr = tmem_base + h * NS + ((uint32_t)(warp * 32) << 16);
+                    const bool tail_half = (h * 128 + 128 > NS);         // only 64 valid rows (N = 64 or 192)
+                    for (int c0 = 0; c0 < NS; c0 += 64) {
+                        float v[64];
+                        ptx::tmem_ld32(taddr + c0, v);
+                        ptx::tmem_ld32(taddr + c0 + 32, v + 32);
+                        ptx::tmem_ld_wait();
+                        ptx::stage_store_tile(ybuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true);
+                        ++nstore;
+                    }
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&acc_empty[h]);
                 }
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(&acc_empty[h]);
+                it_phase ^= 1;
             }
-            it_phase ^= 1;
         }
         if (issuer) ptx::bulk_wait_all();
     }
@@ -549,16 +563,17 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
             const uint32_t idesc_m = ptx::make_idesc_f16(128, Npad, true, false, 0);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t slot_phase = 0;      // all four slots complete once per processed item (unused slots are skipped)
+            uint32_t nunit = 0;           // running unit counter: accumulator slot = nunit % 4, its phase = (nunit / 4) & 1
             for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
                 const int m = m0 + t;
                 const int b = m / nI, i = m - b * nI;
                 if (i + w > lengths[b]) continue;
-                for (int u = 0; u < units; ++u) {
+                for (int u = 0; u < units; ++u, ++nunit) {
                     const int kind = u / halves;
-                    ptx::mbar_wait(&aempty[u], slot_phase ^ 1);
+                    const uint32_t slot = nunit & 3, slot_phase = (nunit >> 2) & 1;
+                    ptx::mbar_wait(&aempty[slot], slot_phase ^ 1);
                     ptx::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + u * 128;
+                    const uint32_t d_tmem = tmem_base + slot * 128;
                     for (int kb = 0; kb < kblocks; ++kb) {
                         ptx::mbar_wait(&full[stage], phase);
                         ptx::tc_fence_after();
@@ -574,9 +589,8 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                         ptx::mma_commit(&empty[stage]);
                         if (++stage == kK5Stages) { stage = 0; phase ^= 1; }
                     }
-                    ptx::mma_commit(&afull[u]);
+                    ptx::mma_commit(&afull[slot]);
                 }
-                slot_phase ^= 1;
             }
         }
     } else if (warp >= 4) {
@@ -588,7 +602,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
         const int grp = (warp - 4) >> 2;
         const int p = (threadIdx.x - 128) & 127;
         const bool issuer = (p == 0);
-        uint32_t slot_phase = 0, nred = 0;
+        uint32_t nunit0 = 0, nred = 0;      // nunit0: running unit counter at the start of the current span
         int fbuf = 0;
         uint8_t* mybuf = rbuf + grp * 32768;
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
@@ -611,10 +625,11 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
             const int rowR = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
             for (int u = grp; u < units; u += 2) {
                 const int kind = u / halves, h = u - kind * halves;
-                ptx::mbar_wait(&afull[u], slot_phase);
+                const uint32_t slot = (nunit0 + u) & 3, slot_phase = ((nunit0 + u) >> 2) & 1;
+                ptx::mbar_wait(&afull[slot], slot_phase);
                 ptx::tc_fence_after();
                 const int xl = q * 32 + lane;                    // row of the 128-wide tile
-                const uint32_t taddr = tmem_base + u * 128 + ((uint32_t)(q * 32) << 16);
+                const uint32_t taddr = tmem_base + slot * 128 + ((uint32_t)(q * 32) << 16);
                 for (int c0 = 0; c0 < w - 1; c0 += 32) {
                     float v[32];
                     ptx::tmem_ld32(taddr + c0, v);
@@ -635,9 +650,9 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                     ++nred;
                 }
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(&aempty[u]);
+                ptx::mbar_arrive(&aempty[slot]);
             }
-            slot_phase ^= 1;
+            nunit0 += units;
             fbuf ^= 1;
         }
         if (issuer) ptx::bulk_wait_all();
@@ -796,6 +811,7 @@ k_tc_gy(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box 
 // K3, CTA-pair variant (cta_group::2): the pair keeps the gradient rows of 256 spans resident (128 per CTA) and every
 // CTA stages only HALF of each 256-row Wk tile, which halves both the TMA fill and the MMA operand reads per SM --
 // the 1-CTA kernel above is shared-memory-bandwidth bound (~250 B/cycle needed, 128 available).
+template <int NBUF>      // staging tiles per epilogue group (2; 1 when N = 512 leaves no room)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box {64, 128}
          const __grid_constant__ CUtensorMap tmW,     // Wk [N*N rows][N], box {64, 128}
@@ -808,8 +824,8 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
     const int ntiles_per_range = ntiles_total / ranges;
     uint8_t* sAres = smem;                                        // [kblocks] x 16 KB (this CTA's 128 rows)
     uint8_t* sBring = sAres + (size_t)kblocks * 16384;            // [stages] x 16 KB (this CTA's half of a Wk tile)
-    uint8_t* ebuf = sBring + kGYStages * 16384;                   // [2 groups][2] x 16 KB staging tiles
-    uint64_t* full = (uint64_t*)(ebuf + 65536);
+    uint8_t* ebuf = sBring + kGYStages * 16384;                   // [2 groups][NBUF] x 16 KB staging tiles
+    uint64_t* full = (uint64_t*)(ebuf + 2 * NBUF * 16384);
     uint64_t* empty = full + kGYStages;
     uint64_t* tfull = empty + kGYStages;      // [2]
     uint64_t* tempty = tfull + 2;             // [2]
@@ -904,7 +920,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
         const int grp = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const bool issuer = ((threadIdx.x - 128) & 127) == 0;
-        uint8_t* mybuf = ebuf + grp * 32768;
+        uint8_t* mybuf = ebuf + grp * (NBUF * 16384);
         int buf = 0;
         uint32_t bphase = 0, nstore = 0;
         for (int unit = pair; unit < units; unit += npairs) {
@@ -921,7 +937,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
                 ptx::mbar_arrive_leader(&tempty[buf]);           // the accumulator is in registers: release it early
 #pragma unroll
                 for (int c0 = 0; c0 < 128; c0 += 64) {
-                    ptx::stage_store_tile(mybuf, &tmOut, nt * 256 + grp * 128 + c0, st * 256 + (int)rank * 128, row, v + c0, nstore, 3 + grp, issuer, true);
+                    ptx::stage_store_tile<NBUF>(mybuf, &tmOut, nt * 256 + grp * 128 + c0, st * 256 + (int)rank * 128, row, v + c0, nstore, 3 + grp, issuer, true);
                     ++nstore;
                 }
                 if (++buf == 2) { buf = 0; bphase ^= 1; }
@@ -1092,50 +1108,205 @@ __global__ void k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, const int
 // =======================================================================================================================
 // drivers
 // =======================================================================================================================
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+int device_sm_count() { return sm_count(); }
+const TcTune& tc_tune() {
+    static TcTune t;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        t.overlap = env_int("RBN_TC_OVERLAP", 0) != 0;
+        t.groups = env_int("RBN_TC_GROUPS", 2);
+        t.fwd_sms0 = env_int("RBN_TC_FWD_SMS0", 40) & ~1;
+        t.bwd_sms0 = env_int("RBN_TC_BWD_SMS0", 74) & ~1;
+        t.nslot = env_int("RBN_TC_SLOTS", 3);
+        t.k3_stream = env_int("RBN_TC_K3_STREAM", 0) != 0;
+        if (t.groups < 1) t.groups = 1;
+        if (t.nslot < 2) t.nslot = 2;
+        if (t.nslot > 8) t.nslot = 8;
+    });
+    return t;
+}
+
 struct TcCtx {
     const RbnDesc* d;
     const WsLayout* ws;
     char* base;
-    int N, L, B, Lp, chunk, sms;
+    int N, L, B, Lp, chunk;
     float* cv;
     int* ce;
     float* alpha;    // left-child contributions (+ root seed)
     float* alpha2;   // right-child contributions
-    __half *lc, *rc, *wt, *wk, *y, *gy, *ghat, *gabs;
-    int *wexp, *wbits, *item_e, *gexp;
+    __half *lc, *rc, *wt, *wk;
+    int *wexp, *wbits;
     float* wscale;
-    float* acc;      // [chunk][N] K-split partial sums of the rule GEMM
     const int* lengths;
-    cudaStream_t st;
+    // per-chunk buffers, `nslot` copies
+    __half* y(int s) const { return (__half*)(base + ws->y) + (size_t)s * chunk * N * N; }
+    __half* gy(int s) const { return (__half*)(base + ws->gy) + (size_t)s * chunk * N * N; }
+    __half* ghat(int s) const { return (__half*)(base + ws->ghat) + (size_t)s * chunk * N; }
+    __half* gabs(int s) const { return (__half*)(base + ws->gabs) + (size_t)s * chunk * N; }
+    float* acc(int s) const { return (float*)(base + ws->acc) + (size_t)s * chunk * N; }
+    int* item_e(int s) const { return (int*)(base + ws->item_e) + (size_t)s * chunk; }
+    int* gexp(int s) const { return (int*)(base + ws->gexp) + (size_t)s * chunk; }
 };
 
-static void fill_ctx(TcCtx& c, const RbnDesc* d, const WsLayout& ws, char* base, const int* lengths, cudaStream_t st) {
+static void fill_ctx(TcCtx& c, const RbnDesc* d, const WsLayout& ws, char* base, const int* lengths) {
     c.d = d; c.ws = &ws; c.base = base; c.N = d->N; c.L = d->L; c.B = d->B; c.Lp = ws.Lp; c.chunk = ws.chunk;
-    c.sms = sm_count();
     c.cv = (float*)(base + ws.chart_val); c.ce = (int*)(base + ws.chart_exp); c.alpha = (float*)(base + ws.alpha); c.alpha2 = (float*)(base + ws.alpha2);
     c.lc = (__half*)(base + ws.lc); c.rc = (__half*)(base + ws.rc); c.wt = (__half*)(base + ws.wt);
-    c.wk = (__half*)(base + ws.wk); c.y = (__half*)(base + ws.y); c.gy = (__half*)(base + ws.gy);
-    c.ghat = (__half*)(base + ws.ghat); c.gabs = (__half*)(base + ws.gabs);
-    c.wexp = (int*)(base + ws.wexp); c.wbits = (int*)(base + ws.wbits); c.wscale = (float*)(base + ws.wscale); c.acc = (float*)(base + ws.acc); c.item_e = (int*)(base + ws.item_e); c.gexp = (int*)(base + ws.gexp);
-    c.lengths = lengths; c.st = st;
+    c.wk = (__half*)(base + ws.wk);
+    c.wexp = (int*)(base + ws.wexp); c.wbits = (int*)(base + ws.wbits); c.wscale = (float*)(base + ws.wscale);
+    c.lengths = lengths;
 }
 
-static int prep_weights(TcCtx& c, const float* W) {
+// ---- two launch streams with disjoint SM partitions ------------------------------------------------------------------------
+// Stream 0 is the caller's; stream 1 and the events come from a process-wide pool (created on first use, never
+// destroyed; a pass returns them as soon as its last launch is queued -- later records / launches on a recycled
+// event or stream simply order after the earlier ones).
+struct AuxPool {
+    std::mutex mu;
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> events;
+};
+static AuxPool& aux_pool(int dev) {
+    static AuxPool pools[16];
+    return pools[dev & 15];
+}
+
+struct Sched {
+    cudaStream_t st[2];
+    int sms[2];
+    bool two;                 // two streams in use
+    bool pair_launch;         // launch the one-CTA-per-SM kernels as clusters of 2 so that they fill whole TPCs
+    int dev;
+    int err;
+    std::vector<cudaEvent_t> taken;
+
+    Sched() : two(false), pair_launch(false), dev(0), err(RBN_OK) { st[0] = st[1] = nullptr; sms[0] = sms[1] = 0; }
+
+    int begin(cudaStream_t user, bool overlap, int sms0) {
+        const int total = sm_count();
+        st[0] = st[1] = user;
+        sms[0] = sms[1] = total;
+        two = false;
+        if (!overlap) return RBN_OK;
+        if (sms0 < 2) sms0 = 2;
+        if (sms0 > total - 2) sms0 = (total - 2) & ~1;
+        RBN_CUDA_CHECK(cudaGetDevice(&dev));
+        AuxPool& p = aux_pool(dev);
+        {
+            std::lock_guard<std::mutex> lk(p.mu);
+            if (!p.streams.empty()) { st[1] = p.streams.back(); p.streams.pop_back(); two = true; }
+        }
+        if (!two) {
+            RBN_CUDA_CHECK(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
+            two = true;
+        }
+        pair_launch = true;
+        sms[0] = sms0;
+        sms[1] = (total - sms0) & ~1;
+        cudaEvent_t e = record(0);            // fork: stream 1 starts after everything queued on the caller's stream
+        wait(1, e);
+        return err;
+    }
+    cudaEvent_t record(int s) {
+        if (!two) return nullptr;
+        cudaEvent_t e = nullptr;
+        {
+            AuxPool& p = aux_pool(dev);
+            std::lock_guard<std::mutex> lk(p.mu);
+            if (!p.events.empty()) { e = p.events.back(); p.events.pop_back(); }
+        }
+        if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("cudaEventCreate failed");
+            err = RBN_E_CUDA;
+            return nullptr;
+        }
+        taken.push_back(e);
+        if (cudaEventRecord(e, st[s]) != cudaSuccess) { set_error("cudaEventRecord failed"); err = RBN_E_CUDA; }
+        return e;
+    }
+    void wait(int s, cudaEvent_t e) {
+        if (!two || !e) return;
+        if (cudaStreamWaitEvent(st[s], e, 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); err = RBN_E_CUDA; }
+    }
+    // join: the caller's stream continues after everything queued on stream 1; hand the stream and events back
+    int end() {
+        if (!two) return err;
+        cudaEvent_t e = record(1);
+        wait(0, e);
+        AuxPool& p = aux_pool(dev);
+        std::lock_guard<std::mutex> lk(p.mu);
+        p.streams.push_back(st[1]);
+        for (cudaEvent_t ev : taken) p.events.push_back(ev);
+        taken.clear();
+        two = false;
+        return err;
+    }
+};
+
+// work unit of a pass: one chunk of spans of one diagonal and one group of sequences
+struct Unit { int w, g, m0, cnt, slot; };
+
+// Diagonal w of sequence group g covers items [b0 * nI, b1 * nI); it is cut into chunks of at most `chunk` items
+// (whole waves of `wave` items when possible).
+static void diag_units(std::vector<Unit>& out, int w, int L, int B, int groups, int chunk, int wave, int nslot, int& counter) {
+    const int nI = L - w + 1;
+    int per = chunk;
+    if (wave > 0 && per > wave) per = per / wave * wave;
+    for (int g = 0; g < groups; ++g) {
+        const int b0 = (int)((long long)B * g / groups), b1 = (int)((long long)B * (g + 1) / groups);
+        const int i0 = b0 * nI, i1 = b1 * nI;
+        for (int m0 = i0; m0 < i1; m0 += per) {
+            Unit u;
+            u.w = w; u.g = g; u.m0 = m0; u.cnt = (i1 - m0 < per) ? i1 - m0 : per; u.slot = counter % nslot;
+            ++counter;
+            out.push_back(u);
+        }
+    }
+}
+
+template <class... KArgs, class... Args>
+static cudaError_t launch_maybe_paired(void (*kern)(KArgs...), bool paired, int grid, int threads, size_t smem, cudaStream_t st,
+                                       Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    if (paired) grid = (grid + 1) & ~1;
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    if (paired) {
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+static int prep_weights(TcCtx& c, const float* W, cudaStream_t st) {
     int N = c.N;
     int* bits = c.wbits;
-    RBN_CUDA_CHECK(cudaMemsetAsync(bits, 0, (size_t)N * sizeof(int), c.st));
-    { ProfScope ps(KC_OTHER, c.st); k_w_colmax<<<256, 256, 0, c.st>>>(N, W, bits); }
+    RBN_CUDA_CHECK(cudaMemsetAsync(bits, 0, (size_t)N * sizeof(int), st));
+    { ProfScope ps(KC_OTHER, st); k_w_colmax<<<256, 256, 0, st>>>(N, W, bits); }
     RBN_LAUNCH_CHECK("k_w_colmax");
-    { ProfScope ps(KC_OTHER, c.st); k_w_exp<<<(N + 127) / 128, 128, 0, c.st>>>(N, bits, c.wexp, c.wscale); }
+    { ProfScope ps(KC_OTHER, st); k_w_exp<<<(N + 127) / 128, 128, 0, st>>>(N, bits, c.wexp, c.wscale); }
     RBN_LAUNCH_CHECK("k_w_exp");
     dim3 grid((unsigned)((size_t)N * N / 32), (unsigned)(N / 32));
-    { ProfScope ps(KC_OTHER, c.st); k_w_copies<<<grid, dim3(32, 8), 0, c.st>>>(N, W, c.wexp, c.wk, c.wt); }
+    { ProfScope ps(KC_OTHER, st); k_w_copies<<<grid, dim3(32, 8), 0, st>>>(N, W, c.wexp, c.wk, c.wt); }
     RBN_LAUNCH_CHECK("k_w_copies");
     return RBN_OK;
 }
 
-static int launch_k1(TcCtx& c, int w, int m0, int cnt) {
+static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired) {
     int N = c.N, L = c.L, B = c.B;
+    const int w = u.w, m0 = u.m0, cnt = u.cnt;
     const int Kpad = ((w - 1) + 15) & ~15;
     const uint32_t rows0 = (uint32_t)(Kpad < 64 ? Kpad : 64), rows1 = (uint32_t)(Kpad > 64 ? Kpad - 64 : 16);
     CUtensorMap tmLC, tmRC, tmLC1, tmRC1;
@@ -1148,147 +1319,190 @@ static int launch_k1(TcCtx& c, int w, int m0, int cnt) {
     rc = make_tmap_2d(&tmRC1, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, rows1);
     if (rc) return rc;
     CUtensorMap tmY, tmYtail;
-    rc = make_tmap_2d(&tmY, c.y, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
+    rc = make_tmap_2d(&tmY, c.y(u.slot), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmYtail, c.y, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
+    rc = make_tmap_2d(&tmYtail, c.y(u.slot), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
     if (rc) return rc;
-    int halves = (N + 127) / 128;
-    size_t stage_bytes = (size_t)(halves * 2 + N / 64) * 8192;
+    const int NS = N > 256 ? 256 : N;
+    int halves = (NS + 127) / 128;
+    size_t stage_bytes = (size_t)(halves * 2 + NS / 64) * 8192;
     int stages = (int)((232448 - 2048 - 32768) / stage_bytes);
     if (stages > 6) stages = 6;
     size_t smem = stages * stage_bytes + 32768 /*Y staging*/ + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_splitsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = cnt < c.sms ? cnt : c.sms;
-    { ProfScope ps(KC_SPLITSUM, c.st);
-      k_tc_splitsum<<<grid, kK1Threads, smem, c.st>>>(tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L, c.Lp, w, m0, cnt, stages, c.lengths, c.ce, c.y, c.item_e); }
+    int grid = cnt < sms ? cnt : sms;
+    { ProfScope ps(KC_SPLITSUM, st);
+      RBN_CUDA_CHECK(launch_maybe_paired(k_tc_splitsum, paired, grid, kK1Threads, smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
+                                         c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y(u.slot), c.item_e(u.slot))); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
 }
 
+// K-split factor of the partial last wave of a 2-CTA GEMM: r tiles left for `pairs` CTA pairs.  Splitting each into s
+// K-ranges gives ceil(r s / pairs) rounds of 1/s of a tile each; pick the s with the shortest tail (ties: fewer
+// partial sums to add).
+static int tail_splits_for(int r, int pairs, int k_blocks) {
+    if (r <= 0) return 1;
+    int best = 1;
+    double best_t = 1.0;
+    for (int s2 = 2; s2 <= 16 && k_blocks / s2 >= 16; ++s2) {
+        const int rounds = (r * s2 + pairs - 1) / pairs;
+        const double t = (double)rounds / s2 + 0.01 * s2;
+        if (t < best_t - 1e-9) { best_t = t; best = s2; }
+    }
+    return best;
+}
+
 template <int BN>
-static int launch_k2_bn(TcCtx& c, int w, int m0, int cnt) {
+static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
+    const int w = u.w, m0 = u.m0, cnt = u.cnt;
     size_t NN = (size_t)c.N * c.N;
     CUtensorMap tmA, tmB;
-    int rc = make_tmap_2d(&tmA, c.y, NN, (uint64_t)cnt, NN * 2, 128);
+    int rc = make_tmap_2d(&tmA, c.y(u.slot), NN, (uint64_t)cnt, NN * 2, 128);
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, c.wt, NN, (uint64_t)c.N, NN * 2, BN);
     if (rc) return rc;
-    EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.item_e, c.cv, c.ce, c.lc, c.rc, c.acc};
+    EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.cv, c.ce, c.lc, c.rc, c.acc(u.slot), BN};
+    const int n_tiles = c.N / BN;                  // 1, or 2 when N = 512
+    if (n_tiles > 1 && !use_pairs()) {
+        set_error("N = %d needs the CTA-pair kernels (unset RBN_TC_1CTA)", c.N);
+        return RBN_E_UNSUPPORTED;
+    }
     if (use_pairs()) {
         CUtensorMap tmB2;
         rc = make_tmap_2d(&tmB2, c.wt, NN, (uint64_t)c.N, NN * 2, BN / 2);
         if (rc) return rc;
-        GemmShape shape2{(cnt + 255) / 256, 1, (int)(NN / 64), 0, 1};
+        GemmShape shape2{(cnt + 255) / 256, n_tiles, (int)(NN / 64), 0, 1, 0};
         // wave quantisation: the last, partial wave of tiles is split along K so that all CTA pairs stay busy
-        const int pairs = c.sms / 2, T = shape2.m_tiles;
+        const int pairs = sms / 2, T = shape2.m_tiles * n_tiles;
         const int full = (T / pairs) * pairs, r = T - full;
-        int splits = (r > 0) ? pairs / r : 1;
-        if (splits > 16) splits = 16;
-        while (splits > 1 && shape2.k_blocks / splits < 16) --splits;
+        const int splits = tail_splits_for(r, pairs, shape2.k_blocks);
+        if (n_tiles > 1) {
+            // both halves of a row are needed for its max shift: every tile adds into acc, k_rule_finalize does the rest
+            shape2.all_partial = 1;
+            if (splits > 1) { shape2.full_tiles = full; shape2.tail_splits = splits; }
+            RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot), 0, (size_t)cnt * c.N * sizeof(float), st));
+            rc = launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
+            if (rc) return rc;
+            { ProfScope ps(KC_RULE, st);
+              k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+            RBN_LAUNCH_CHECK("k_rule_finalize");
+            return RBN_OK;
+        }
         if (splits > 1) {
             shape2.full_tiles = full;
             shape2.tail_splits = splits;
             const int t_begin = full * 256;
-            RBN_CUDA_CHECK(cudaMemsetAsync(c.acc + (size_t)t_begin * c.N, 0, (size_t)(cnt - t_begin) * c.N * sizeof(float), c.st));
-            rc = launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, c.sms, c.st, "k_tc_gemm2<rule>", KC_RULE);
+            RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot) + (size_t)t_begin * c.N, 0, (size_t)(cnt - t_begin) * c.N * sizeof(float), st));
+            rc = launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
-            { ProfScope ps(KC_RULE, c.st);
-              k_rule_finalize<<<cnt - t_begin, c.N, 0, c.st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.item_e, c.acc, c.cv, c.ce, c.lc, c.rc); }
+            { ProfScope ps(KC_RULE, st);
+              k_rule_finalize<<<cnt - t_begin, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
-        return launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, c.sms, c.st, "k_tc_gemm2<rule>", KC_RULE);
+        return launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
     }
-    GemmShape shape{(cnt + 127) / 128, 1, (int)(NN / 64)};
-    return launch_tc_gemm<false, false, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiRule>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<rule>", KC_RULE);
+    GemmShape shape{(cnt + 127) / 128, 1, (int)(NN / 64), 0, 1, 0};
+    return launch_tc_gemm<false, false, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiRule>(tmA, tmB, shape, epi, sms, st, "k_tc_gemm<rule>", KC_RULE);
 }
-static int launch_k2(TcCtx& c, int w, int m0, int cnt) {
+static int launch_k2(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
     switch (c.N) {
-        case 64: return launch_k2_bn<64>(c, w, m0, cnt);
-        case 128: return launch_k2_bn<128>(c, w, m0, cnt);
-        case 192: return launch_k2_bn<192>(c, w, m0, cnt);
-        default: return launch_k2_bn<256>(c, w, m0, cnt);
+        case 64: return launch_k2_bn<64>(c, u, st, sms);
+        case 128: return launch_k2_bn<128>(c, u, st, sms);
+        case 192: return launch_k2_bn<192>(c, u, st, sms);
+        default: return launch_k2_bn<256>(c, u, st, sms);
     }
 }
 
-static int launch_k3(TcCtx& c, int cnt) {
+static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
+    const int cnt = u.cnt;
     size_t NN = (size_t)c.N * c.N;
     CUtensorMap tmG, tmW, tmOut;
-    int rc = make_tmap_2d(&tmG, c.ghat, (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 128);
+    int rc = make_tmap_2d(&tmG, c.ghat(u.slot), (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 128);
     if (rc) return rc;
     rc = make_tmap_2d(&tmW, c.wk, (uint64_t)c.N, NN, (uint64_t)c.N * 2, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmOut, c.gy, NN, (uint64_t)cnt, NN * 2, 128);
+    rc = make_tmap_2d(&tmOut, c.gy(u.slot), NN, (uint64_t)cnt, NN * 2, 128);
     if (rc) return rc;
     int supertiles = (cnt + 255) / 256;
     if (use_pairs()) {
-        int ntiles2 = (int)(NN / 256), pairs = c.sms / 2;
+        int ntiles2 = (int)(NN / 256), pairs = sms / 2;
         int ranges2 = 1;
         while (ranges2 < 16 && supertiles * ranges2 < 2 * pairs && ntiles2 % (ranges2 * 2) == 0 && ntiles2 / (ranges2 * 2) >= 8) ranges2 *= 2;
-        size_t smem2 = (size_t)(c.N / 64) * 16384 + kGYStages * 16384 + 65536 + 256 + 1024;
-        RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gy2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        const int nbuf = c.N > 256 ? 1 : 2;
+        size_t smem2 = (size_t)(c.N / 64) * 16384 + kGYStages * 16384 + (size_t)2 * nbuf * 16384 + 256 + 1024;
+        auto kern = nbuf == 2 ? k_tc_gy2<2> : k_tc_gy2<1>;
+        RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         int units2 = supertiles * ranges2;
         int np = units2 < pairs ? units2 : pairs;
-        { ProfScope ps(KC_GY, c.st); k_tc_gy2<<<2 * np, 384, smem2, c.st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges2); }
+        { ProfScope ps(KC_GY, st); kern<<<2 * np, 384, smem2, st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges2); }
         RBN_LAUNCH_CHECK("k_tc_gy2");
         return RBN_OK;
     }
     int ntiles = (int)(NN / 128);
     int ranges = 1;
-    while (ranges < 16 && supertiles * ranges < 2 * c.sms && ntiles % (ranges * 2) == 0 && ntiles / (ranges * 2) >= 8) ranges *= 2;
+    while (ranges < 16 && supertiles * ranges < 2 * sms && ntiles % (ranges * 2) == 0 && ntiles / (ranges * 2) >= 8) ranges *= 2;
     size_t smem = (size_t)2 * (c.N / 64) * 16384 + kGYStages * 16384 + 32768 + 256 + 1024;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int units = supertiles * ranges;
-    int grid = units < c.sms ? units : c.sms;
-    { ProfScope ps(KC_GY, c.st); k_tc_gy<<<grid, 256, smem, c.st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges); }
+    int grid = units < sms ? units : sms;
+    { ProfScope ps(KC_GY, st); k_tc_gy<<<grid, 256, smem, st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges); }
     RBN_LAUNCH_CHECK("k_tc_gy");
     return RBN_OK;
 }
 
 template <int BN>
-static int launch_k4_bn(TcCtx& c, int cnt, float* gW) {
+static int launch_k4_bn(TcCtx& c, const Unit& u, float* gW, cudaStream_t st, int sms) {
+    const int cnt = u.cnt;
     size_t NN = (size_t)c.N * c.N;
     CUtensorMap tmA, tmB;
-    int rc = make_tmap_2d(&tmA, c.y, NN, (uint64_t)cnt, NN * 2, 64);            // MN-major A: [K=items][M=(b,c)]
+    int rc = make_tmap_2d(&tmA, c.y(u.slot), NN, (uint64_t)cnt, NN * 2, 64);            // MN-major A: [K=items][M=(b,c)]
     if (rc) return rc;
-    rc = make_tmap_2d(&tmB, c.gabs, (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 64);   // MN-major B: [K=items][N=a]
+    rc = make_tmap_2d(&tmB, c.gabs(u.slot), (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 64);   // MN-major B: [K=items][N=a]
     if (rc) return rc;
-    EpiCounts epi{gW, c.N};
+    EpiCounts epi{gW, c.N, BN};
+    const int n_tiles = c.N / BN;
+    if (n_tiles > 1 && !use_pairs()) {
+        set_error("N = %d needs the CTA-pair kernels (unset RBN_TC_1CTA)", c.N);
+        return RBN_E_UNSUPPORTED;
+    }
     if (use_pairs() && BN % 128 == 0) {
-        GemmShape shape2{(int)(NN / 256), 1, (cnt + 63) / 64, 0, 1};
+        GemmShape shape2{(int)(NN / 256), n_tiles, (cnt + 63) / 64, 0, 1, 0};
         {   // K-split so that the work units fill whole waves of CTA pairs (256 tiles on 74 pairs = 3.46 waves otherwise)
-            const int pairs = c.sms / 2, tiles = (int)(NN / 256);
+            const int pairs = sms / 2, tiles = (int)(NN / 256) * n_tiles;
             int best = 1;
             double best_eff = 0;
             for (int sp = 1; sp <= 4; ++sp) {
-                if (shape2.k_blocks / sp < 16) break;
+                if (sp > 1 && shape2.k_blocks / sp < 16) break;
                 const int units = tiles * sp;
                 const double eff = (double)units / (((units + pairs - 1) / pairs) * (double)pairs);
                 if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
             }
             shape2.tail_splits = best;
         }
-        return launch_tc_gemm2<true, true, (BN % 128 == 0 ? BN : 128), 6, kSegBlocks, EpiCounts>(tmA, tmB, shape2, epi, c.sms, c.st, "k_tc_gemm2<counts>", KC_COUNTS);
+        return launch_tc_gemm2<true, true, (BN % 128 == 0 ? BN : 128), 6, kSegBlocks, EpiCounts>(tmA, tmB, shape2, epi, sms, st, "k_tc_gemm2<counts>", KC_COUNTS);
     }
-    GemmShape shape{(int)(NN / 128), 1, (cnt + 63) / 64};
-    return launch_tc_gemm<true, true, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiCounts>(tmA, tmB, shape, epi, c.sms, c.st, "k_tc_gemm<counts>", KC_COUNTS);
+    GemmShape shape{(int)(NN / 128), 1, (cnt + 63) / 64, 0, 1, 0};
+    return launch_tc_gemm<true, true, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiCounts>(tmA, tmB, shape, epi, sms, st, "k_tc_gemm<counts>", KC_COUNTS);
 }
-static int launch_k4(TcCtx& c, int cnt, float* gW) {
+static int launch_k4(TcCtx& c, const Unit& u, float* gW, cudaStream_t st, int sms) {
     switch (c.N) {
-        case 64: return launch_k4_bn<64>(c, cnt, gW);
-        case 128: return launch_k4_bn<128>(c, cnt, gW);
-        case 192: return launch_k4_bn<192>(c, cnt, gW);
-        default: return launch_k4_bn<256>(c, cnt, gW);
+        case 64: return launch_k4_bn<64>(c, u, gW, st, sms);
+        case 128: return launch_k4_bn<128>(c, u, gW, st, sms);
+        case 192: return launch_k4_bn<192>(c, u, gW, st, sms);
+        default: return launch_k4_bn<256>(c, u, gW, st, sms);
     }
 }
 
-static int launch_k5(TcCtx& c, int w, int m0, int cnt) {
+static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired) {
     int N = c.N, L = c.L, B = c.B;
+    const int w = u.w, m0 = u.m0, cnt = u.cnt;
     int Npad = ((w - 1) + 15) & ~15;
     CUtensorMap tmGYk, tmGYm, tmRC, tmLC;
-    int rc = make_tmap_2d(&tmGYk, c.gy, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
+    int rc = make_tmap_2d(&tmGYk, c.gy(u.slot), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmGYm, c.gy, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
+    rc = make_tmap_2d(&tmGYm, c.gy(u.slot), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
     if (rc) return rc;
     rc = make_tmap_2d(&tmRC, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, (uint32_t)Npad);
     if (rc) return rc;
@@ -1306,21 +1520,27 @@ static int launch_k5(TcCtx& c, int w, int m0, int cnt) {
     if (rc) return rc;
     size_t smem = (size_t)kK5Stages * kK5StageBytes + 65536 + 256 + 2048 + 1024;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = cnt < c.sms ? cnt : c.sms;
-    { ProfScope ps(KC_CHILD, c.st); k_tc_childgrad<<<grid, 384, smem, c.st>>>(tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt, c.lengths, tmAL, tmAR, tmALt, tmARt, c.ce, c.item_e,
-                                              c.gexp); }
+    int grid = cnt < sms ? cnt : sms;
+    { ProfScope ps(KC_CHILD, st);
+      RBN_CUDA_CHECK(launch_maybe_paired(k_tc_childgrad, paired, grid, 384, smem, st, tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt,
+                                         c.lengths, tmAL, tmAR, tmALt, tmARt, (const int*)c.ce, (const int*)c.item_e(u.slot),
+                                         (const int*)c.gexp(u.slot))); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;
 }
 
+// Inside pass.  Stream 0 runs the split-sums (HBM-write bound), stream 1 the rule GEMMs (tensor / HBM-read bound).
+// A split-sum of diagonal w needs every narrower cell of ITS sequences, i.e. the rule GEMMs of the same sequence
+// group on diagonal w - 1; the other group's kernels fill the gap.
 int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
                const int* tokens, const int* lengths, float* logZ, float* zroot, float* rootexp, cudaStream_t st) {
     TcCtx c;
-    fill_ctx(c, d, ws, base, lengths, st);
+    fill_ctx(c, d, ws, base, lengths);
     int N = c.N, L = c.L, B = c.B;
-    int rc = prep_weights(c, W);
+    const TcTune& tune = tc_tune();
+    int rc = prep_weights(c, W, st);
     if (rc) return rc;
-    RBN_CUDA_CHECK(cudaMemsetAsync(c.y, 0, (size_t)c.chunk * N * N * sizeof(__half), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.y(0), 0, (size_t)ws.nslot * c.chunk * N * N * sizeof(__half), st));
     // TMA slabs over-read rows of cells that are never written (start >= end, beyond a sequence's length): keep them 0
     RBN_CUDA_CHECK(cudaMemsetAsync(c.lc, 0, (size_t)B * L * c.Lp * N * sizeof(__half), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(c.rc, 0, (size_t)B * (L + 1) * c.Lp * N * sizeof(__half), st));
@@ -1328,50 +1548,106 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
     RBN_LAUNCH_CHECK("k_emission");
     { ProfScope ps(KC_EMISSION, st); k_copy_width1<<<B * L, 128, 0, st>>>(N, L, c.Lp, lengths, c.cv, c.lc, c.rc); }
     RBN_LAUNCH_CHECK("k_copy_width1");
-    for (int w = 2; w <= L; ++w) {
-        int items = B * (L - w + 1);
-        for (int m0 = 0; m0 < items; m0 += c.chunk) {
-            int cnt = items - m0 < c.chunk ? items - m0 : c.chunk;
-            if ((rc = launch_k1(c, w, m0, cnt))) return rc;
-            if ((rc = launch_k2(c, w, m0, cnt))) return rc;
+
+    const bool overlap = tune.overlap && ws.nslot >= 2 && B >= 2 * tune.groups;
+    const int groups = overlap ? tune.groups : 1;
+    Sched S;
+    if ((rc = S.begin(st, overlap, tune.fwd_sms0))) return rc;
+    const int wave = (S.sms[1] / 2) * 256;                     // rule-GEMM rows per wave of CTA pairs
+    std::vector<Unit> units;
+    std::vector<cudaEvent_t> evK2;
+    std::vector<int> last_prev(groups, -1), last_cur(groups, -1);
+    int counter = 0;
+    for (int w = 2; w <= L && !rc; ++w) {
+        const size_t first = units.size();
+        diag_units(units, w, L, B, groups, c.chunk, wave, ws.nslot, counter);
+        evK2.resize(units.size(), nullptr);
+        for (size_t ui = first; ui < units.size() && !rc; ++ui) {
+            const Unit& u = units[ui];
+            if (last_prev[u.g] >= 0) S.wait(0, evK2[last_prev[u.g]]);            // narrower cells of this group are written
+            if ((int)ui - ws.nslot >= 0) S.wait(0, evK2[ui - ws.nslot]);         // the slot's previous reader is done
+            if ((rc = launch_k1(c, u, S.st[0], S.sms[0], S.pair_launch))) break;
+            S.wait(1, S.record(0));
+            if ((rc = launch_k2(c, u, S.st[1], S.sms[1]))) break;
+            evK2[ui] = S.record(1);
+            last_cur[u.g] = (int)ui;
         }
+        last_prev = last_cur;
     }
+    int rc2 = S.end();
+    if (rc) return rc;
+    if (rc2) return rc2;
     { ProfScope ps(KC_OTHER, st); k_root<<<B, 128, 0, st>>>(N, L, prior, lengths, c.cv, c.ce, logZ, zroot, rootexp, (float*)(base + ws.zroot),
                               (int*)(base + ws.rootexp)); }
     RBN_LAUNCH_CHECK("k_root");
     return RBN_OK;
 }
 
+// Outside pass.  Stream 0: split-sum recompute, upstream-gradient prep, gY GEMM (HBM-write bound); stream 1: count GEMM
+// and child gradients (HBM-read / reduce bound).  The prep of diagonal w needs the child gradients of every wider
+// diagonal of ITS sequence group.
 int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
                 const int* tokens, const int* lengths, const float* coef, float* gW, float* gT, float* gPrior,
                 cudaStream_t st) {
     (void)W; (void)T;
     TcCtx c;
-    fill_ctx(c, d, ws, base, lengths, st);
+    fill_ctx(c, d, ws, base, lengths);
     int N = c.N, L = c.L, B = c.B;
-    size_t C = cells_per_seq(L);
+    const TcTune& tune = tc_tune();
     RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha, 0, (size_t)B * L * c.Lp * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha2, 0, (size_t)B * (L + 1) * c.Lp * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gW, 0, (size_t)N * N * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
-    RBN_CUDA_CHECK(cudaMemsetAsync(c.y, 0, (size_t)c.chunk * N * N * sizeof(__half), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.y(0), 0, (size_t)ws.nslot * c.chunk * N * N * sizeof(__half), st));
     { ProfScope ps(KC_OTHER, st); k_tc_outside_seed<<<B, 128, 0, st>>>(N, L, c.Lp, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior); }
     RBN_LAUNCH_CHECK("k_tc_outside_seed");
+
+    const bool overlap = tune.overlap && ws.nslot >= 2 && B >= 2 * tune.groups;
+    const int groups = overlap ? tune.groups : 1;
+    Sched S;
     int rc;
-    for (int w = L; w >= 2; --w) {
-        int items = B * (L - w + 1);
-        for (int m0 = 0; m0 < items; m0 += c.chunk) {
-            int cnt = items - m0 < c.chunk ? items - m0 : c.chunk;
-            if ((rc = launch_k1(c, w, m0, cnt))) return rc;
+    if ((rc = S.begin(st, overlap, tune.bwd_sms0))) return rc;
+    const int s3 = (overlap && tune.k3_stream) ? 1 : 0;        // stream of the gY GEMM
+    const int wave = (S.sms[s3] / 2) * 256;
+    std::vector<Unit> units;
+    std::vector<cudaEvent_t> evK5;
+    std::vector<int> last_prev(groups, -1), last_cur(groups, -1);
+    int counter = 0;
+    for (int w = L; w >= 2 && !rc; --w) {
+        const size_t first = units.size();
+        diag_units(units, w, L, B, groups, c.chunk, wave, ws.nslot, counter);
+        evK5.resize(units.size(), nullptr);
+        for (size_t ui = first; ui < units.size() && !rc; ++ui) {
+            const Unit& u = units[ui];
+            const int cnt = u.cnt;
+            if ((int)ui - ws.nslot >= 0) S.wait(0, evK5[ui - ws.nslot]);         // every reader of the slot's buffers is done
+            if ((rc = launch_k1(c, u, S.st[0], S.sms[0], S.pair_launch))) break;
+            if (last_prev[u.g] >= 0) S.wait(0, evK5[last_prev[u.g]]);            // alpha of this diagonal is complete
             int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
-            { ProfScope ps(KC_PREP, st); k_prep_g<<<pg, N, 0, st>>>(N, L, c.Lp, w, m0, cnt, lengths, c.ce, c.item_e, c.wexp, c.alpha, c.alpha2, c.ghat, c.gabs, c.gexp); }
+            { ProfScope ps(KC_PREP, S.st[0]);
+              k_prep_g<<<pg, N, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, lengths, c.ce, c.item_e(u.slot), c.wexp, c.alpha, c.alpha2,
+                                             c.ghat(u.slot), c.gabs(u.slot), c.gexp(u.slot)); }
             RBN_LAUNCH_CHECK("k_prep_g");
-            if ((rc = launch_k3(c, cnt))) return rc;
-            if ((rc = launch_k4(c, cnt, gW))) return rc;
-            if ((rc = launch_k5(c, w, m0, cnt))) return rc;
+            S.wait(1, S.record(0));
+            if (s3 == 0) {
+                if ((rc = launch_k3(c, u, S.st[0], S.sms[0]))) break;
+                cudaEvent_t e3 = S.record(0);
+                if ((rc = launch_k4(c, u, gW, S.st[1], S.sms[1]))) break;
+                S.wait(1, e3);
+            } else {
+                if ((rc = launch_k3(c, u, S.st[1], S.sms[1]))) break;
+                if ((rc = launch_k4(c, u, gW, S.st[1], S.sms[1]))) break;
+            }
+            if ((rc = launch_k5(c, u, S.st[1], S.sms[1], S.pair_launch))) break;
+            evK5[ui] = S.record(1);
+            last_cur[u.g] = (int)ui;
         }
+        last_prev = last_cur;
     }
+    int rc2 = S.end();
+    if (rc) return rc;
+    if (rc2) return rc2;
     { ProfScope ps(KC_EMISSION, st); k_tc_emission_bwd<<<B * L, 128, 0, st>>>(N, L, c.Lp, d->n_tvars, tokens, lengths, c.ce, c.alpha, c.alpha2, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");
     return RBN_OK;
@@ -1392,14 +1668,14 @@ int debug_gemm(int M, int N, int K, const __half* A, const __half* Bm, float* D,
     else rc = make_tmap_2d(&tmB, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)N * 2, 64);
     if (rc) return rc;
     EpiStoreF32 epi{D, M, N, 256};
-    GemmShape shape{(M + 127) / 128, 1, K / 64};
+    GemmShape shape{(M + 127) / 128, 1, K / 64, 0, 1, 0};
     int sms = sm_count();
     if (seg & 2) {       // 2-CTA variant (tests): K-major/K-major and MN-major/MN-major only
         CUtensorMap tmB2;
         if (!b_mn) rc = make_tmap_2d(&tmB2, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 128);
         else rc = make_tmap_2d(&tmB2, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)N * 2, 64);
         if (rc) return rc;
-        GemmShape shape2{(M + 255) / 256, 1, K / 64};
+        GemmShape shape2{(M + 255) / 256, 1, K / 64, 0, 1, 0};
         if (!a_mn && !b_mn) {
             if (seg & 1) return launch_tc_gemm2<false, false, 256, 6, kSegBlocks, EpiStoreF32>(tmA, tmB2, shape2, epi, sms, st, "debug_gemm2", KC_OTHER);
             return launch_tc_gemm2<false, false, 256, 6, 0, EpiStoreF32>(tmA, tmB2, shape2, epi, sms, st, "debug_gemm2", KC_OTHER);

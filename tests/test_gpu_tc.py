@@ -77,7 +77,8 @@ def _run(N, V, L, B, ragged, seed, path, chunk=0):
 
 
 @pytest.mark.parametrize("N,V,L,B,ragged,chunk", [(64, 16, 8, 3, False, 0), (64, 16, 12, 5, True, 128), (128, 8, 9, 3, True, 0),
-                                                  (192, 8, 6, 2, False, 0), (256, 32, 7, 2, True, 0), (256, 32, 20, 2, False, 0)])
+                                                  (192, 8, 6, 2, False, 0), (256, 32, 7, 2, True, 0), (256, 32, 20, 2, False, 0),
+                                                  (512, 8, 6, 2, True, 0), (512, 16, 19, 3, True, 0)])
 def test_tc_path_vs_fp64_oracle(N, V, L, B, ragged, chunk):
     from oracle import inside_oracle as O
     from rbn_b200 import _lib
@@ -139,3 +140,55 @@ def test_n256_vs_oracle_medium_length():
     assert np.abs(lz - lz_ref.numpy()).max() <= LOGZ_RTOL * np.abs(lz_ref.numpy()).max()
     errs = (_rel(gW, gW_ref.numpy()), _rel(gT, gT_ref.numpy()), _rel(gP, gP_ref.numpy()))
     assert max(errs) <= GRAD_RTOL, errs
+
+
+def test_n512_count_identities_and_chunk_invariance():
+    """N = 512 (BASELINE configs[4] grammar size; sub-blocked split-sum, n-tiled rule / count GEMMs): expected-count
+    identities at L = 72 (two split slabs) and independence of the chunking."""
+    from oracle import inside_oracle as O
+    from rbn_b200 import inside_logZ, _lib
+    N, V, L = 512, 32, 72
+    W, T, pr = O.synthetic_grammar(N, V, seed=3)
+    tok, _ = O.synthetic_tokens(3, L, V, seed=4)
+    lengths = np.array([72, 40, 9])
+    for b in range(3):
+        tok[b, lengths[b]:] = -1
+    Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+    lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), path=_lib.PATH_TCGEN05)
+    assert torch.isfinite(lz).all()
+    lz.sum().backward()
+    gW, gT, gP = Wt.grad.cpu().numpy(), Tt.grad.cpu().numpy(), pt.grad.cpu().numpy()
+    tot = float(lengths.sum())
+    assert abs((gW.astype(np.float64) * W).sum() - (lengths - 1).sum()) <= 1e-3 * tot
+    assert abs((gT.astype(np.float64) * T).sum() - tot) <= 1e-3 * tot
+    assert abs((gP.astype(np.float64) * pr).sum() - 3) <= 1e-3 * 3
+    lz2 = inside_logZ(torch.tensor(W, device="cuda"), torch.tensor(T, device="cuda"), torch.tensor(pr, device="cuda"),
+                      torch.tensor(tok), torch.tensor(lengths), path=_lib.PATH_TCGEN05, chunk_items=128)
+    np.testing.assert_allclose(lz2.cpu().numpy(), lz.detach().cpu().numpy(), rtol=2e-6)
+
+
+def test_two_stream_schedule_matches_oracle():
+    """RBN_TC_OVERLAP=1 (two launch streams, SM partitions, sequence groups, slot ring) in a fresh process."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import numpy as np, torch
+from oracle import inside_oracle as O
+from rbn_b200 import inside_logZ, _lib
+N, V, L, B = 128, 8, 14, 9
+W, T, pr = O.synthetic_grammar(N, V, seed=5)
+tok, lengths = O.synthetic_tokens(B, L, V, seed=6, ragged=True)
+Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), path=_lib.PATH_TCGEN05, chunk_items=128)
+lz.sum().backward()
+ref, gW, gT, gP = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths)
+assert np.abs(lz.detach().cpu().numpy() - ref.numpy()).max() <= 1e-4 * np.abs(ref.numpy()).max()
+for a, b in ((Wt.grad, gW), (Tt.grad, gT), (pt.grad, gP)):
+    assert float((a.cpu() - b).abs().max() / b.abs().max()) <= 1e-3
+print("two-stream OK")
+"""
+    env = dict(os.environ, RBN_TC_OVERLAP="1", RBN_TC_GROUPS="2", RBN_TC_SLOTS="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "two-stream OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
