@@ -37,6 +37,12 @@ WORKLOADS = {
     # chart of 512 sequences are 88 GB at N = 512); counts accumulate over the micro-batches, one all-reduce per step
     "c5": dict(N=512, V=32, L=128, B=1024, micro=512, outside=True,
                name="PCFG N=512 L=128 batch 1024/GPU (8192 over 8 GPUs) inside+outside, EM E-step (BASELINE configs[4])"),
+    # configs[0]: the reference's own CPU-runnable case (plot_PCFG.py-style): latency-bound, one sequence
+    "c1": dict(N=10, V=19, L=20, B=1, outside=True,
+               name="discrete PCFG N=10 V=19, single length-20 sequence, inside+outside (BASELINE configs[0]; latency-bound)"),
+    # configs[3]: continuous RBN, multivariate-normal transitions (separate code path: run_gauss)
+    "c4": dict(D=8, L=64, B=256, outside=True, gauss=True,
+               name="Gaussian RBN D=8 L=64 batch 256/GPU, inside marginal likelihood + gradient (BASELINE configs[3])"),
     "tiny": dict(N=64, V=32, L=16, B=8, outside=True, name="tiny self-test"),
 }
 
@@ -343,6 +349,111 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def run_gauss(args, wl):
+    """BASELINE configs[3]: fp64 Gaussian chart pass (csrc/gauss_kernels.cu).  HBM roofline per SURVEY.md 8(d): per cell
+    4 (1 + D + D^2) bytes at the reference's fp32 = 292 B (this build stores fp64: 584 B); a pass re-reads two child
+    cells per split, 2 (L^3 - L)/6 cells per sequence; inside + outside = forward reads + backward reads and adjoint
+    read-modify-writes of the same cells (3x)."""
+    import numpy as np
+    import torch
+    from oracle import gauss_oracle as GO      # synthetic workload generator + the cpu_baseline leg only
+    from rbn_b200 import _lib
+    from rbn_b200.gaussian import GaussianRBN
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    D, L, B = wl["D"], wl["L"], args.batch or wl["B"]
+    syn = GO.synthetic_gauss(D, B, L, seed=10 + rank)
+    y_np = syn["y"]
+    model = GaussianRBN(D, cov_term=syn["cov_term"], cov_left=syn["cov_left"], cov_right=syn["cov_right"],
+                        prior_mean=syn["prior_mean"], prior_cov=syn["prior_cov"], struct_weights=(0.4, 0.6)).to(dev)
+    params = list(model.parameters())
+    y_d = torch.tensor(y_np, dtype=torch.float64, device=dev)
+    y_pin = torch.tensor(y_np, dtype=torch.float64).pin_memory()
+
+    def step(y):
+        for p in params:
+            p.grad = None
+        lz = model.log_inside_batch(y)
+        (-lz.sum()).backward()
+        if world > 1:
+            from rbn_b200.distributed import allreduce_counts
+            allreduce_counts([p.grad for p in params])
+        return lz
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, out
+
+    for _ in range(args.warmup):
+        step(y_d)
+    _lib.profile_read(reset=True)
+    _lib.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step, lz = timed(lambda: step(y_d), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = _lib.profile_read(reset=True)
+    _lib.profile_enable(False)
+    ms_e2e, _ = timed(lambda: float(step(y_pin.to(dev, non_blocking=True)).sum()), args.steps)
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    cell_bytes = 8 * (1 + D + D * D)
+    splits = (L ** 3 - L) // 6
+    alg_bytes = 3.0 * B * 2 * splits * cell_bytes             # child-cell reads fwd + bwd + adjoint updates
+    diag_ms, diag_launches = prof["other"]
+    ach = alg_bytes * args.steps / (diag_ms * 1e-3) / 1e9 if diag_ms > 0 else None
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        t0 = time.perf_counter()
+        n_cpu = 0
+        tt = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != "y")) for k, v in syn.items()}
+        while time.perf_counter() - t0 < 15.0:
+            lzc = GO.gauss_inside(torch.tensor(y_np[n_cpu % B:n_cpu % B + 1]), [L], tt["cov_term"], tt["cov_left"], tt["cov_right"],
+                                  tt["prior_mean"], tt["prior_cov"], tt["log_struct"])
+            lzc.sum().backward()
+            n_cpu += 1
+        dt = time.perf_counter() - t0
+        cpu = dict(value=n_cpu / dt, unit="seq/s", cores=torch.get_num_threads(), kind="port",
+                   sample=f"{n_cpu} sequences of the same workload, fp64 torch restatement on rbnet.multivariate_normal's algebra, {dt:.1f}s")
+    line = dict(metric="inside+gradient sequences/sec", value=world * B / (ms_step * 1e-3), unit="seq/s", n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=wl["name"], D=D, L=L, batch_per_gpu=B, global_batch=world * B, parallelism=f"dp{world}",
+                            l2="chart (80 MB) fits L2: latency-bound launch train, no flush"),
+                e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="seq/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(y_pin.numel() * 8),
+                         d2h_bytes_per_step=8),
+                gpu_launches=int(sum(v[1] for v in prof.values())),
+                roofline=dict(bound="hbm", kernel="k_gauss_diag / k_gauss_bwd_diag (per-diagonal cell pass)", achieved=ach,
+                              peak=peaks["hbm"], unit="GB/s", frac=(ach / peaks["hbm"]) if ach else None, traffic=None,
+                              peak_source=f"{peaks['source']} hbm_gbs", launches=int(diag_launches),
+                              avg_launch_ms=(diag_ms / diag_launches) if diag_launches else None,
+                              algorithmic_bytes_per_step=alg_bytes,
+                              kernels_ms_per_step={k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]}),
+                clocks=clocks, logZ_mean=float(lz.detach().double().mean()))
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -358,6 +469,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif wl.get("gauss"):
+        run_gauss(args, wl)
     else:
         run_ours(args, wl)
 

@@ -233,7 +233,7 @@ static int gauss_forward_t(int B, int L, const double* y, const int* lengths, co
     RBN_LAUNCH_CHECK("k_gauss_width1");
     size_t smem = ((size_t)L + D + 3 * D * D) * sizeof(double);
     for (int w = 2; w <= L; ++w) {
-        { ProfScope ps(KC_OTHER, st);
+        { ProfScope ps(KC_SIMT_INSIDE, st);
           k_gauss_diag<D><<<B * (L - w + 1), 64, smem, st>>>(L, w, lengths, cov_left, cov_right, log_struct, chart); }
         RBN_LAUNCH_CHECK("k_gauss_diag");
     }
@@ -564,7 +564,7 @@ static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_
     size_t smem = ((size_t)6 * DD * 32 + 2 * L + G + D + 4 * DD) * sizeof(double);
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_gauss_bwd_diag<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int w = L; w >= 2; --w) {
-        { ProfScope ps(KC_OTHER, st);
+        { ProfScope ps(KC_SIMT_OUTSIDE, st);
           k_gauss_bwd_diag<D><<<B * (L - w + 1), 32, smem, st>>>(L, w, lengths, cov_left, cov_right, chart, adj, g_cov_left, g_cov_right, g_log_struct); }
         RBN_LAUNCH_CHECK("k_gauss_bwd_diag");
     }
