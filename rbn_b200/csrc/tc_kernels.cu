@@ -257,7 +257,8 @@ struct EpiCounts {
 //   warps 0-3 epilogue (TMEM -> fp16 -> Y)   warps 4-7 fix-up   warp 8 TMA producer   warp 9 MMA issuer / TMEM owner
 static constexpr int kK1Threads = 320;
 
-__global__ void __launch_bounds__(kK1Threads, 1)
+template <int MINB>       // co-resident CTAs per SM the register budget is cut for (2 for small N)
+__global__ void __launch_bounds__(kK1Threads, MINB)
 k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ CUtensorMap tmRC,
               const __grid_constant__ CUtensorMap tmLC1, const __grid_constant__ CUtensorMap tmRC1,   // second K-slab (rows = Kpad - 64)
               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYtail,
@@ -287,7 +288,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     float* cj = (float*)(red + 4);                // [128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t TMEM_COLS = tmem_cols_pow2(halves * NS);
+    const uint32_t TMEM_COLS = tmem_cols_pow2(2 * NS);      // two accumulators: the halves of a span, or (N <= 64... one half) consecutive spans
     const int nI = L - w + 1;
     const size_t C = cells_per_seq(L);
 
@@ -352,16 +353,27 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         const int chunks_per_row = NS / 8;              // 16-byte chunks per (sub-block) chart row
+        // e_left + e_right of this thread's split of span t (INT_MIN: no such split / span beyond its sequence)
+        // (kept as two registers and added at the point of use, so that the loads stay in flight across the iteration)
+        auto fetch_sft = [&](int t, int& ea, int& eb) {
+            ea = INT_MIN; eb = 0;
+            if (t >= cnt || p >= w - 1) return;
+            const int m = m0 + t;
+            const int b = m / nI, i = m - b * nI;
+            if (i + w > lengths[b]) return;
+            const int* ce_seq = ce + (size_t)b * C;
+            const int u = p + 1;
+            ea = ce_seq[cell_off(u, L) + i];
+            eb = ce_seq[cell_off(w - u, L) + i + u];
+        };
+        int ea_next, eb_next;
+        fetch_sft(blockIdx.x, ea_next, eb_next);
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+            const int sft = (ea_next == INT_MIN) ? INT_MIN : ea_next + eb_next;
+            fetch_sft(t + gridDim.x, ea_next, eb_next);   // in flight while this span is processed (global-load latency)
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI, k = i + w;
             if (k > lengths[b]) continue;
-            const int* ce_seq = ce + (size_t)b * C;
-            int sft = INT_MIN;
-            if (p < w - 1) {
-                const int u = p + 1;
-                sft = ce_seq[cell_off(u, L) + i] + ce_seq[cell_off(w - u, L) + i + u];
-            }
             int mxs = sft;
             for (int o = 16; o > 0; o >>= 1) mxs = max(mxs, __shfl_xor_sync(0xffffffffu, mxs, o));
             ptx::named_bar_sync(1, 128);                // every fix-up thread is done with the previous span's cj / red
@@ -402,7 +414,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         if (lane == 0) {
             const uint32_t idesc = ptx::make_idesc_f16(128, NS, true, true, 0);
             int stage = 0;
-            uint32_t phase = 0, it_phase = 0;
+            uint32_t phase = 0, nacc = 0;       // nacc: accumulators used so far; slot = n & 1, its phase = (n >> 1) & 1
             for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
                 const int m = m0 + t;
                 const int b = m / nI, i = m - b * nI;
@@ -415,27 +427,28 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                     const uint32_t aL = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint32_t aR = aL + (uint32_t)a_atoms * 8192;
                     for (int h = 0; h < halves; ++h) {
+                        const uint32_t slot = (nacc + h) & 1, slot_phase = ((nacc + h) >> 1) & 1;
                         if (part == 0) {
-                            ptx::mbar_wait(&acc_empty[h], it_phase ^ 1);
+                            ptx::mbar_wait(&acc_empty[slot], slot_phase ^ 1);
                             ptx::tc_fence_after();
                         }
                         for (int k16 = 0; k16 < Ks / 16; ++k16) {
                             const uint64_t ad = ptx::make_smem_desc(aL + (uint32_t)(h * 2) * 8192 + k16 * 2048, 8192, 1024);
                             const uint64_t bd = ptx::make_smem_desc(aR + k16 * 2048, 8192, 1024);
-                            ptx::mma_f16_ss(tmem_base + h * NS, ad, bd, idesc, (uint32_t)!(part == 0 && k16 == 0));
+                            ptx::mma_f16_ss(tmem_base + slot * NS, ad, bd, idesc, (uint32_t)!(part == 0 && k16 == 0));
                         }
-                        if (part == parts - 1) ptx::mma_commit(&acc_full[h]);
+                        if (part == parts - 1) ptx::mma_commit(&acc_full[slot]);
                     }
                     ptx::mma_commit(&empty[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                it_phase ^= 1;
+                nacc += halves;
                 }
             }
         }
     } else if (warp < 4) {
         // ---------------- epilogue: TMEM -> fp16 -> smem tile -> TMA store into Y[t][b][c] ----------------
-        uint32_t it_phase = 0, nstore = 0;
+        uint32_t nacc = 0, nstore = 0;
         const int row = warp * 32 + lane;
         const bool issuer = (threadIdx.x == 0);
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
@@ -445,9 +458,10 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
             for (int sub = 0; sub < nsub; ++sub) {
                 const int brow = (sub / nblk) * NS, ccol = (sub % nblk) * NS;
                 for (int h = 0; h < halves; ++h) {
-                    ptx::mbar_wait(&acc_full[h], it_phase);
+                    const uint32_t slot = (nacc + h) & 1, slot_phase = ((nacc + h) >> 1) & 1;
+                    ptx::mbar_wait(&acc_full[slot], slot_phase);
                     ptx::tc_fence_after();
-                    const uint32_t taddr = tmem_base + h * NS + ((uint32_t)(warp * 32) << 16);
+                    const uint32_t taddr = tmem_base + slot * NS + ((uint32_t)(warp * 32) << 16);
                     const bool tail_half = (h * 128 + 128 > NS);         // only 64 valid rows (N = 64 or 192)
                     for (int c0 = 0; c0 < NS; c0 += 64) {
                         float v[64];
@@ -458,9 +472,9 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                         ++nstore;
                     }
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive(&acc_empty[h]);
+                    ptx::mbar_arrive(&acc_empty[slot]);
                 }
-                it_phase ^= 1;
+                nacc += halves;
             }
         }
         if (issuer) ptx::bulk_wait_all();
@@ -605,21 +619,31 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
         uint32_t nunit0 = 0, nred = 0;      // nunit0: running unit counter at the start of the current span
         int fbuf = 0;
         uint8_t* mybuf = rbuf + grp * 32768;
+        // exponent pieces of the split factor c_j * 2^eG of this thread's split of span t, fetched one span ahead and
+        // combined at the point of use so that the loads stay in flight (INT_MIN: padding split, factor 0)
+        auto fetch_fac = [&](int t, int& e0, int& e1, int& e2, int& e3) {
+            e0 = INT_MIN; e1 = e2 = e3 = 0;
+            if (t >= cnt || p >= w - 1) return;
+            const int m = m0 + t;
+            const int b = m / nI, i = m - b * nI;
+            if (i + w > lengths[b]) return;
+            const int* ce_seq = ce + (size_t)b * C;
+            const int us = p + 1;
+            e0 = ce_seq[cell_off(us, L) + i];
+            e1 = ce_seq[cell_off(w - us, L) + i + us];
+            e2 = item_e[t];
+            e3 = gexp[t];
+        };
+        int e0n, e1n, e2n, e3n;
+        fetch_fac(blockIdx.x, e0n, e1n, e2n, e3n);
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+            const float f_cur = (e0n == INT_MIN) ? 0.f : ldexpf(1.0f, min(max(e0n + e1n - e2n + e3n, -126), 126));
+            fetch_fac(t + gridDim.x, e0n, e1n, e2n, e3n);
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI, k = i + w;
             if (k > lengths[b]) continue;
-            const int* ce_seq = ce + (size_t)b * C;
             float* facb = fac + (grp * 2 + fbuf) * 128;
-            {
-                float f = 0.f;
-                if (p < w - 1) {
-                    const int us = p + 1;
-                    const int sft = ce_seq[cell_off(us, L) + i] + ce_seq[cell_off(w - us, L) + i + us] - item_e[t] + gexp[t];
-                    f = ldexpf(1.0f, min(max(sft, -126), 126));
-                }
-                facb[p] = f;                                     // 0 for the padding splits: they add nothing
-            }
+            facb[p] = f_cur;
             ptx::named_bar_sync(2 + grp, 128);
             const int rowL = (int)(((size_t)b * L + i) * Lp + (i + 1));
             const int rowR = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
@@ -940,6 +964,162 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
                     ptx::stage_store_tile<NBUF>(mybuf, &tmOut, nt * 256 + grp * 128 + c0, st * 256 + (int)rank * 128, row, v + c0, nstore, 3 + grp, issuer, true);
                     ++nstore;
                 }
+                if (++buf == 2) { buf = 0; bphase ^= 1; }
+            }
+        }
+        if (issuer) ptx::bulk_wait_all();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc2(tmem_base, 512);
+}
+
+// K3, CTA-pair variant with the gradient rows in TENSOR MEMORY (tcgen05.mma with a TMEM A operand).  The kernels above
+// are shared-memory-bandwidth bound at N = 512 (MMA operand reads of A and B + TMA fills + store staging = 128 B/clk per
+// SM); here A costs nothing, the Wk ring needs 8 KB per k-block and CTA, and the accumulators are 128 columns wide:
+//   TMEM columns [0, N/2)            this CTA's 128 gradient rows, two fp16 per column (written by tcgen05.st)
+//   TMEM columns [N/2 + 128 buf ...) two accumulators of 128 (b,c) columns
+//   warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM owner, warps 4-7 load A and drain columns 0-63,
+//   warps 8-11 drain columns 64-127 of every accumulator
+static constexpr int kGY3Stages = 12;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+k_tc_gy3(const __grid_constant__ CUtensorMap tmW,     // Wk [N*N rows][N], box {64, 64}
+         const __grid_constant__ CUtensorMap tmOut,   // gY [cnt rows][N*N], box {64, 128}
+         const __half* __restrict__ ghat,             // [>= cnt rows][N]
+         int cnt, int N, int supertiles, int ranges) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int kblocks = N / 64;
+    const int ntiles_total = N * N / 128;
+    const int ntiles_per_range = ntiles_total / ranges;
+    uint8_t* sBring = smem;                                       // [stages] x 8 KB (this CTA's 64 rows of a Wk tile)
+    uint8_t* ebuf = sBring + kGY3Stages * 8192;                   // [2 groups][2] x 16 KB staging tiles
+    uint64_t* full = (uint64_t*)(ebuf + 65536);
+    uint64_t* empty = full + kGY3Stages;
+    uint64_t* tfull = empty + kGY3Stages;     // [2]
+    uint64_t* tempty = tfull + 2;             // [2]
+    uint64_t* a_full = tempty + 2;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(a_empty + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = (rank == 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGY3Stages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], 512);
+        }
+        ptx::mbar_init(a_full, 256);
+        ptx::mbar_init(a_empty, 1);
+        ptx::fence_barrier_init();
+        ptx::tma_prefetch_desc(&tmW);
+        ptx::tma_prefetch_desc(&tmOut);
+    }
+    if (warp == 2) ptx::tmem_alloc2(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_base = tmem_base + (uint32_t)(N / 2);
+    const int units = supertiles * ranges;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = pair; unit < units; unit += npairs) {
+                const int r = unit % ranges;
+                for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt)
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        ptx::mbar_wait(&empty[stage], phase ^ 1);
+                        if (leader) ptx::mbar_expect_tx(&full[stage], 2 * 8192);
+                        ptx::tma_load_2d_pair(sBring + stage * 8192, &tmW, &full[stage], kb * 64, nt * 128 + (int)rank * 64);
+                        if (++stage == kGY3Stages) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            const uint32_t idesc = ptx::make_idesc_f16(256, 128, false, false, 0);
+            int stage = 0, buf = 0;
+            uint32_t phase = 0, aphase = 0, bphase = 0;
+            for (int unit = pair; unit < units; unit += npairs) {
+                const int r = unit % ranges;
+                ptx::mbar_wait(a_full, aphase);
+                aphase ^= 1;
+                ptx::tc_fence_after();
+                for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt) {
+                    ptx::mbar_wait(&tempty[buf], bphase ^ 1);
+                    ptx::tc_fence_after();
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        ptx::mbar_wait(&full[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t sB = ptx::smem_u32(sBring + stage * 8192);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::mma_f16_ts_pair(acc_base + buf * 128, tmem_base + (uint32_t)(kb * 32 + k * 8),
+                                                 ptx::make_smem_desc(sB + k * 32, 16, 1024), idesc, (uint32_t)((kb | k) != 0));
+                        ptx::mma_commit_pair(&empty[stage]);
+                        if (++stage == kGY3Stages) { stage = 0; phase ^= 1; }
+                    }
+                    ptx::mma_commit_pair(&tfull[buf]);
+                    if (++buf == 2) { buf = 0; bphase ^= 1; }
+                }
+                ptx::mma_commit_pair(a_empty);         // the gradient rows may be replaced once these MMAs retire
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const bool issuer = ((threadIdx.x - 128) & 127) == 0;
+        uint8_t* mybuf = ebuf + grp * 32768;
+        int buf = 0;
+        uint32_t bphase = 0, nstore = 0, aphase = 0;
+        for (int unit = pair; unit < units; unit += npairs) {
+            const int st = unit / ranges, r = unit - st * ranges;
+            if (grp == 0) {
+                // this CTA's 128 gradient rows -> TMEM (one row per thread, 32 columns = 64 halves per store)
+                ptx::mbar_wait(a_empty, aphase ^ 1);
+                aphase ^= 1;
+                ptx::tc_fence_after();
+                const int grow = st * 256 + (int)rank * 128 + row;
+                const uint4* src = reinterpret_cast<const uint4*>(ghat + (size_t)grow * N);
+                for (int c0 = 0; c0 < N / 2; c0 += 32) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint4 x = make_uint4(0, 0, 0, 0);
+                        if (grow < cnt) x = __ldg(src + (c0 >> 2) + j);
+                        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+                    }
+                    ptx::tmem_st32u(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive_leader(a_full);
+            }
+            for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt) {
+                ptx::mbar_wait(&tfull[buf], bphase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = acc_base + buf * 128 + grp * 64 + ((uint32_t)(q * 32) << 16);
+                float v[64];
+                ptx::tmem_ld32(taddr, v);
+                ptx::tmem_ld32(taddr + 32, v + 32);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive_leader(&tempty[buf]);           // the accumulator is in registers: release it early
+                ptx::stage_store_tile(mybuf, &tmOut, nt * 128 + grp * 64, st * 256 + (int)rank * 128, row, v, nstore, 3 + grp, issuer, true);
+                ++nstore;
                 if (++buf == 2) { buf = 0; bphase ^= 1; }
             }
         }
@@ -1326,13 +1506,19 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     const int NS = N > 256 ? 256 : N;
     int halves = (NS + 127) / 128;
     size_t stage_bytes = (size_t)(halves * 2 + NS / 64) * 8192;
-    int stages = (int)((232448 - 2048 - 32768) / stage_bytes);
+    // small N: a span is a few KB of operands and 8-32 KB of output, the per-span hand-offs dominate -> co-resident CTAs
+    static const int k1_ctas_env = env_int("RBN_TC_K1_CTAS", 0);
+    int ctas = k1_ctas_env > 0 ? (k1_ctas_env > 2 ? 2 : k1_ctas_env) : (N <= 128 ? 2 : 1);
+    if (paired) ctas = 1;
+    int stages = (int)((232448 / ctas - 1024 * ctas - 2048 - 32768) / stage_bytes);
     if (stages > 6) stages = 6;
+    if (stages < 1) { stages = 1; ctas = 1; }
     size_t smem = stages * stage_bytes + 32768 /*Y staging*/ + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
-    RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_splitsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = cnt < sms ? cnt : sms;
+    auto kern = ctas > 1 ? k_tc_splitsum<2> : k_tc_splitsum<1>;
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = cnt < sms * ctas ? cnt : sms * ctas;
     { ProfScope ps(KC_SPLITSUM, st);
-      RBN_CUDA_CHECK(launch_maybe_paired(k_tc_splitsum, paired, grid, kK1Threads, smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
+      RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, kK1Threads, smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
                                          c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y(u.slot), c.item_e(u.slot))); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
@@ -1426,6 +1612,22 @@ static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
     rc = make_tmap_2d(&tmOut, c.gy(u.slot), NN, (uint64_t)cnt, NN * 2, 128);
     if (rc) return rc;
     int supertiles = (cnt + 255) / 256;
+    static const int gy_variant = env_int("RBN_TC_GY", 2);        // 3: gradient rows in TMEM, 2: in shared memory
+    if (use_pairs() && gy_variant == 3) {
+        CUtensorMap tmW64;
+        rc = make_tmap_2d(&tmW64, c.wk, (uint64_t)c.N, NN, (uint64_t)c.N * 2, 64);
+        if (rc) return rc;
+        int ntiles3 = (int)(NN / 128), pairs = sms / 2;
+        int ranges3 = 1;
+        while (ranges3 < 16 && supertiles * ranges3 < 2 * pairs && ntiles3 % (ranges3 * 2) == 0 && ntiles3 / (ranges3 * 2) >= 16) ranges3 *= 2;
+        size_t smem3 = (size_t)kGY3Stages * 8192 + 65536 + 512 + 1024;
+        RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gy3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        int units3 = supertiles * ranges3;
+        int np = units3 < pairs ? units3 : pairs;
+        { ProfScope ps(KC_GY, st); k_tc_gy3<<<2 * np, 384, smem3, st>>>(tmW64, tmOut, c.ghat(u.slot), cnt, c.N, supertiles, ranges3); }
+        RBN_LAUNCH_CHECK("k_tc_gy3");
+        return RBN_OK;
+    }
     if (use_pairs()) {
         int ntiles2 = (int)(NN / 256), pairs = sms / 2;
         int ranges2 = 1;
