@@ -107,8 +107,30 @@ class ConstrainedModuleList(torch.nn.ModuleList, ConstrainedModuleMixin):
     """ModuleList that takes part in `enforce_constraints` recursion (util.py:116-118)."""
 
 
+_PROJECT_GRADIENTS = True
+
+
+class raw_gradients:
+    """Context manager: inside it the `project_grad` hooks of `Prob` / `LogProb` pass gradients through unchanged.
+    With `LogProb`, the raw gradient of sum_b log Z_b w.r.t. `log_p` IS the expected rule count,
+    which the EM step (rbn_b200/em.py) needs; the reference's hook would subtract its mean (util.py:200-202)."""
+
+    def __enter__(self):
+        global _PROJECT_GRADIENTS
+        self._saved = _PROJECT_GRADIENTS
+        _PROJECT_GRADIENTS = False
+        return self
+
+    def __exit__(self, *exc):
+        global _PROJECT_GRADIENTS
+        _PROJECT_GRADIENTS = self._saved
+        return False
+
+
 def _project_to_tangent(grad, dims):
     """g - mean of g over the normalised dims: the reference's gradient projection (util.py:147-156, 200-202)."""
+    if not _PROJECT_GRADIENTS:
+        return grad
     count = math.prod(grad.shape[d] for d in dims)
     return grad - grad.sum(dim=dims, keepdim=True) / count
 
