@@ -320,10 +320,24 @@ def run_ours(args, wl):
     f_step, f_rule_step, f_rule_fwd = (x * B for x in flops_per_sequence(N, L, wl["outside"]))
     peaks = load_peaks()
     rule_ms, rule_launches = prof["rule_gemm"]
+    rule_ms += prof["rule_finalize"][0]          # the max-shift epilogue of K-split tiles is part of the rule contraction
     achieved = (f_rule_fwd * args.steps / (rule_ms * 1e-3) / 1e12) if rule_ms > 0 else None
-    roofline = dict(bound="tensor", kernel="k_tc_gemm<rule> (rule contraction, tcgen05)",
+    # launches of the class = GEMM launches + (for K-split tails) the small finalize kernels; per GEMM launch figures use
+    # the number of (diagonal, chunk) units.  DRAM traffic per span comes from the committed ncu capture of this kernel.
+    spans_per_step = B * (L * (L - 1) // 2)
+    traffic = alg_bytes = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and N in (256, 512):
+        with open(tpath) as f:
+            tj = json.load(f)[f"k2_n{N}"]
+        gemm_launches = max(1, int(rule_launches) // args.steps)
+        traffic = tj["dram_bytes_per_span"] * spans_per_step / gemm_launches
+        alg_bytes = (2.0 * N * N * spans_per_step + 2.0 * N ** 3 * gemm_launches) / gemm_launches   # Y once + W once per launch
+    roofline = dict(bound="tensor", kernel="k_tc_gemm2<rule> (rule contraction, tcgen05 cta_group::2)",
                     achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
-                    frac=(achieved / peaks["tflops"]) if achieved else None, traffic=None,
+                    frac=(achieved / peaks["tflops"]) if achieved else None, traffic=traffic,
+                    traffic_source=("profiles/r01_traffic.json (ncu --set full, one launch, scaled per span)" if traffic else None),
+                    algorithmic_bytes_per_launch=alg_bytes,
                     peak_source=f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                     launches=int(rule_launches), avg_launch_ms=(rule_ms / rule_launches) if rule_launches else None,
                     algorithmic_flops_per_step=f_rule_fwd,

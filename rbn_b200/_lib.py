@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "librbn_b200.so")
 
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 KERNEL_CLASSES = ["emission", "split_sum", "rule_gemm", "gy_gemm", "count_gemm", "child_grad", "grad_prep",
-                  "simt_inside", "simt_outside", "other"]
+                  "simt_inside", "simt_outside", "other", "rule_finalize"]
 
 
 class RbnDesc(ctypes.Structure):

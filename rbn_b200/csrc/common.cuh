@@ -88,7 +88,7 @@ int device_sm_count();
 
 // ---- per-kernel-class launch accounting (always) and CUDA-event timing (when enabled) ------------------------------
 enum KernelClass { KC_EMISSION = 0, KC_SPLITSUM, KC_RULE, KC_GY, KC_COUNTS, KC_CHILD, KC_PREP, KC_SIMT_INSIDE,
-                   KC_SIMT_OUTSIDE, KC_OTHER, KC_NUM };
+                   KC_SIMT_OUTSIDE, KC_OTHER, KC_RULE_FIN, KC_NUM };
 struct ProfScope {          // brackets ONE kernel launch on `st`
     int cls;
     cudaStream_t st;

@@ -1570,7 +1570,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
             RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot), 0, (size_t)cnt * c.N * sizeof(float), st));
             rc = launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
-            { ProfScope ps(KC_RULE, st);
+            { ProfScope ps(KC_RULE_FIN, st);
               k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
@@ -1582,7 +1582,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
             RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot) + (size_t)t_begin * c.N, 0, (size_t)(cnt - t_begin) * c.N * sizeof(float), st));
             rc = launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
-            { ProfScope ps(KC_RULE, st);
+            { ProfScope ps(KC_RULE_FIN, st);
               k_rule_finalize<<<cnt - t_begin, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
