@@ -171,16 +171,31 @@ k_gauss_diag(int L, int w, const int* __restrict__ lengths, const double* __rest
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
     __syncthreads();
     const double log_norm = mx + log(red[0] + red[1]);
-    for (int u = 1 + threadIdx.x; u < w; u += blockDim.x) {
-        const double* l = seq + (size_t)(cell_off(u, L) + i) * G;
-        const double* r = seq + (size_t)(cell_off(w - u, L) + i + u) * G;
-        split_product<D, true>(l, r, cL, cR, mean, A, cov);
-        const double wt = exp(lw[u] - log_norm);
+    // weighted first and second moments: every quantity is summed over the lanes of a warp with shuffles and added to
+    // shared memory once per warp (64-way contended fp64 shared-memory atomics were the bottleneck of this kernel)
+    const int lane = threadIdx.x & 31;
+    for (int base = 1; base < w; base += blockDim.x) {
+        if (base + (int)(threadIdx.x & ~31u) >= w) continue;          // no split left for this warp
+        const int u = base + threadIdx.x;
+        const bool active = u < w;
+        double wt = 0.0;
+        if (active) {
+            const double* l = seq + (size_t)(cell_off(u, L) + i) * G;
+            const double* r = seq + (size_t)(cell_off(w - u, L) + i + u) * G;
+            split_product<D, true>(l, r, cL, cR, mean, A, cov);
+            wt = exp(lw[u] - log_norm);
+        }
 #pragma unroll
         for (int a = 0; a < D; ++a) {
-            atomicAdd(&acc[a], wt * mean[a]);
+            double v = active ? wt * mean[a] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(&acc[a], v);
 #pragma unroll
-            for (int c = 0; c < D; ++c) atomicAdd(&acc[D + a * D + c], wt * (cov[a][c] + mean[a] * mean[c]));
+            for (int c = 0; c < D; ++c) {
+                double q = active ? wt * (cov[a][c] + mean[a] * mean[c]) : 0.0;
+                for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                if (lane == 0) atomicAdd(&acc[D + a * D + c], q);
+            }
         }
     }
     __syncthreads();
@@ -265,10 +280,10 @@ int gauss_forward(int D, int B, int L, const double* y, const int* lengths, cons
 // outside pass of the Gaussian RBN: reverse-mode through moment matching and the pairwise products
 // =====================================================================================================================
 // Adjoint chart cell = [a_bar | mu_bar[D] | Sigma_bar[D][D]] of sum_b coef_b log Z_b.  One warp per span, one lane per
-// split; the D x D work matrices of a lane live in shared memory, lane-interleaved (entry e of lane t at [e*32 + t]).
+// split; the D x D work matrices of a lane are thread-private.
 namespace rbn {
 
-#define SMAT(M, r, c) M[((r) * D + (c)) * 32 + lane]
+#define SMAT(M, r, c) M[(r) * D + (c)]
 
 template <int D>
 __global__ void k_gauss_bwd_root(int L, int B, const int* __restrict__ lengths, const double* __restrict__ prior_mean,
@@ -323,13 +338,10 @@ k_gauss_bwd_diag(int L, int w, const int* __restrict__ lengths, const double* __
     constexpr int G = GCell<D>::kStride;
     constexpr int DD = D * D;
     extern __shared__ double sm[];
-    double* mA = sm;                 // lane-interleaved work matrices
-    double* mP = mA + DD * 32;
-    double* mK = mP + DD * 32;
-    double* mQ = mK + DD * 32;
-    double* mAb = mQ + DD * 32;
-    double* mSb = mAb + DD * 32;
-    double* lw = mSb + DD * 32;      // [L]
+    // D x D work matrices of this lane's split: thread-private (registers / local memory, which the hardware interleaves
+    // per lane and caches in L1).  Keeping them in shared memory cost 98 KB per warp at D = 8, i.e. two warps per SM.
+    double mA[DD], mP[DD], mK[DD], mQ[DD], mAb[DD], mSb[DD];
+    double* lw = sm;                 // [L]
     double* ob = lw + L;             // [L]  omega_bar
     double* par = ob + L;            // parent: [0] a_bar, [1..D] mu_bar_tot, [1+D..] M2_bar (symmetric)
     double* pmu = par + G;           // parent mean [D]
@@ -375,6 +387,9 @@ k_gauss_bwd_diag(int L, int w, const int* __restrict__ lengths, const double* __
     __syncwarp();
 
     double mean[D], Areg[D][D], cov[D][D];
+    double tL[DD], tR[DD];           // this lane's share of the covariance gradients
+#pragma unroll
+    for (int t = 0; t < DD; ++t) tL[t] = tR[t] = 0.0;
     // pass 1: log weights and omega_bar
     double mx = -INFINITY;
     for (int u = 1 + lane; u < w; u += 32) {
@@ -510,15 +525,24 @@ k_gauss_bwd_diag(int L, int w, const int* __restrict__ lengths, const double* __
                 const double ss = 0.5 * (SMAT(mSb, a, c) + SMAT(mSb, c, a));
                 atomicAdd(&la[1 + D + a * D + c], sa);
                 atomicAdd(&ra[1 + D + a * D + c], ss);
-                atomicAdd(&gL[a * D + c], sa);
-                atomicAdd(&gR[a * D + c], ss);
+                tL[a * D + c] += sa;
+                tR[a * D + c] += ss;
             }
         }
     }
-    __syncwarp();
-    for (int t = lane; t < DD; t += 32) {
-        if (gL[t] != 0.0) atomicAdd(&g_cov_left[t], gL[t]);
-        if (gR[t] != 0.0) atomicAdd(&g_cov_right[t], gR[t]);
+    // sum the lanes' covariance gradients with shuffles (fp64 shared-memory atomics serialise 32-way), then one global
+    // atomic per entry and span
+#pragma unroll
+    for (int t = 0; t < DD; ++t) {
+        double vl = tL[t], vr = tR[t];
+        for (int o = 16; o > 0; o >>= 1) {
+            vl += __shfl_xor_sync(0xffffffffu, vl, o);
+            vr += __shfl_xor_sync(0xffffffffu, vr, o);
+        }
+        if (lane == 0) {
+            if (vl != 0.0) atomicAdd(&g_cov_left[t], vl);
+            if (vr != 0.0) atomicAdd(&g_cov_right[t], vr);
+        }
     }
 }
 
@@ -561,7 +585,7 @@ static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_
     { ProfScope ps(KC_OTHER, st);
       k_gauss_bwd_root<D><<<(B + 63) / 64, 64, 0, st>>>(L, B, lengths, prior_mean, prior_cov, chart, coef, adj, g_prior_mean, g_prior_cov); }
     RBN_LAUNCH_CHECK("k_gauss_bwd_root");
-    size_t smem = ((size_t)6 * DD * 32 + 2 * L + G + D + 4 * DD) * sizeof(double);
+    size_t smem = ((size_t)2 * L + G + D + 4 * DD) * sizeof(double);
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_gauss_bwd_diag<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int w = L; w >= 2; --w) {
         { ProfScope ps(KC_SIMT_OUTSIDE, st);
