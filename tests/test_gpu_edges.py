@@ -1,0 +1,77 @@
+"""Edge cases of the chart pass on the GPU: length-1 sequences, ragged batches that contain them, positions without a
+terminal (None / -1, /root/reference/rbnet/pcfg.py:346-349) which make a sequence ungrammatical (Z = 0, log Z = -inf,
+no NaN in any gradient, tests/test_base.py:293 in the reference), and a batch of one."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _grads(N, V, tok, lengths, path, seed=0):
+    from oracle import inside_oracle as O
+    from rbn_b200 import inside_logZ
+    W, T, pr = O.synthetic_grammar(N, V, seed=seed)
+    Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+    lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), path=path)
+    finite = torch.isfinite(lz)
+    torch.where(finite, lz, torch.zeros_like(lz)).sum().backward()
+    return (W, T, pr), lz.detach().cpu().numpy(), [g.grad.cpu().numpy() for g in (Wt, Tt, pt)]
+
+
+@pytest.mark.parametrize("N", [10, 64])
+def test_length_one_sequences(N):
+    """Only width-1 cells exist: Z = sum_a prior[a] T[y, a]; binary rules get no count."""
+    from rbn_b200 import _lib
+    V = 7
+    tok = np.array([[3], [0], [6]], dtype=np.int32)
+    (W, T, pr), lz, (gW, gT, gP) = _grads(N, V, tok, np.array([1, 1, 1]), _lib.PATH_AUTO)
+    ref = np.log((T[tok[:, 0]] * pr[None, :]).sum(1))
+    np.testing.assert_allclose(lz, ref, rtol=1e-5)
+    assert np.abs(gW).max() == 0.0
+    assert abs((gT * T).sum() - 3) < 1e-3 and abs((gP * pr).sum() - 3) < 1e-3
+
+
+@pytest.mark.parametrize("N,path", [(10, "simt"), (64, "tc"), (128, "tc")])
+def test_ragged_batch_with_length_one_and_two_members(N, path):
+    from oracle import inside_oracle as O
+    from rbn_b200 import _lib
+    V, L = 6, 9
+    tok, _ = O.synthetic_tokens(5, L, V, seed=3)
+    lengths = np.array([1, 9, 2, 5, 1])
+    for b in range(5):
+        tok[b, lengths[b]:] = -1
+    p = _lib.PATH_SIMT if path == "simt" else _lib.PATH_TCGEN05
+    (W, T, pr), lz, (gW, gT, gP) = _grads(N, V, tok, lengths, p, seed=4)
+    ref, rW, rT, rP = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths)
+    np.testing.assert_allclose(lz, ref.numpy(), rtol=1e-4)
+    for g, r in ((gW, rW), (gT, rT), (gP, rP)):
+        assert np.abs(g - r.numpy()).max() <= 1e-3 * np.abs(r.numpy()).max()
+
+
+@pytest.mark.parametrize("N,path", [(10, "simt"), (64, "tc")])
+def test_missing_terminal_makes_the_sequence_ungrammatical_without_nans(N, path):
+    from oracle import inside_oracle as O
+    from rbn_b200 import _lib
+    V, L = 5, 8
+    tok, lengths = O.synthetic_tokens(3, L, V, seed=5)
+    tok[1, 4] = -1                                       # None inside sequence 1: its cell (4,5) has no mass
+    p = _lib.PATH_SIMT if path == "simt" else _lib.PATH_TCGEN05
+    (W, T, pr), lz, grads = _grads(N, V, tok, lengths, p, seed=6)
+    assert np.isneginf(lz[1]) and np.isfinite(lz[[0, 2]]).all()
+    for g in grads:
+        assert np.isfinite(g).all()
+    ref, rW, rT, rP = O.flat_inside_with_grads(W, T, pr, tok[[0, 2]][:, :, None], lengths[[0, 2]])
+    np.testing.assert_allclose(lz[[0, 2]], ref.numpy(), rtol=1e-4)
+    assert np.abs(grads[0] - rW.numpy()).max() <= 1e-3 * np.abs(rW.numpy()).max()      # the dead sequence adds nothing
+
+
+def test_batch_of_one_on_the_tensor_core_path():
+    from oracle import inside_oracle as O
+    from rbn_b200 import _lib
+    N, V, L = 64, 8, 17
+    tok, lengths = O.synthetic_tokens(1, L, V, seed=8)
+    (W, T, pr), lz, (gW, gT, gP) = _grads(N, V, tok, lengths, _lib.PATH_TCGEN05, seed=9)
+    ref, rW, rT, rP = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths)
+    np.testing.assert_allclose(lz, ref.numpy(), rtol=1e-4)
+    assert np.abs(gW - rW.numpy()).max() <= 1e-3 * np.abs(rW.numpy()).max()
