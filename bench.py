@@ -343,6 +343,32 @@ def run_ours(args, wl):
                     algorithmic_flops_per_step=f_rule_fwd,
                     step_tflops=f_step / (ms_step * 1e-3) / 1e12, step_frac=f_step / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
                     kernels_ms_per_step={k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]})
+    # every kernel class of the tensor-core path against the roofline that bounds it:
+    # algorithmic bytes or flops per step / summed CUDA-event time of the class
+    if N >= 64 and prof["split_sum"][1]:
+        spans = B * (L * (L - 1) // 2)                         # spans of width >= 2 per pass
+        splits = B * ((L ** 3 - L) // 6)
+        passes = 2 if wl["outside"] else 1
+        y_bytes = 2.0 * N * N * spans
+        row_bytes = 2.0 * splits * 2 * N                       # fp16 child rows streamed once per diagonal
+        per = {}
+
+        def entry(cls, bound, amount, peak, unit):
+            ms = prof[cls][0] / args.steps
+            if ms <= 0:
+                return
+            ach = amount / (ms * 1e-3) / (1e12 if unit == "TFLOP/s" else 1e9)
+            per[cls] = dict(bound=bound, ms_per_step=round(ms, 3), achieved=round(ach, 1), peak=peak, unit=unit, frac=round(ach / peak, 3))
+        entry("split_sum", "hbm (write-limited: 3.9 TB/s pure-write ceiling measured)", passes * (y_bytes + row_bytes), peaks["hbm"], "GB/s")
+        per_rule_ms = rule_ms / args.steps
+        if per_rule_ms > 0:
+            per["rule_gemm"] = dict(bound="tensor", ms_per_step=round(per_rule_ms, 3), achieved=round(f_rule_fwd / (per_rule_ms * 1e-3) / 1e12, 1),
+                                    peak=peaks["tflops"], unit="TFLOP/s", frac=round(f_rule_fwd / (per_rule_ms * 1e-3) / 1e12 / peaks["tflops"], 3))
+        if wl["outside"]:
+            entry("gy_gemm", "hbm (write) / tensor", y_bytes, peaks["hbm"], "GB/s")
+            entry("count_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
+            entry("child_grad", "hbm (read + L2 reduce-add)", y_bytes + row_bytes + 2.0 * splits * 2 * N * 4, peaks["hbm"], "GB/s")
+        roofline["by_kernel"] = per
     launches = int(sum(v[1] for v in prof.values()))
     cpu_v, cpu_t, cpu_samp, cores = cpu_sample(wl) if (world == 1 and not args.skip_cpu) else (None, None, None, None)
     line = dict(metric="inside+outside sequences/sec" if wl["outside"] else "inside sequences/sec",

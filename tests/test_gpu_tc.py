@@ -144,13 +144,13 @@ def test_n256_vs_oracle_medium_length():
 
 def test_n512_count_identities_and_chunk_invariance():
     """N = 512 (BASELINE configs[4] grammar size; sub-blocked split-sum, n-tiled rule / count GEMMs): expected-count
-    identities at L = 72 (two split slabs) and independence of the chunking."""
+    identities at the full length L = 128 (two split slabs) and independence of the chunking."""
     from oracle import inside_oracle as O
     from rbn_b200 import inside_logZ, _lib
-    N, V, L = 512, 32, 72
+    N, V, L = 512, 32, 128                       # the full BASELINE configs[4] shape
     W, T, pr = O.synthetic_grammar(N, V, seed=3)
     tok, _ = O.synthetic_tokens(3, L, V, seed=4)
-    lengths = np.array([72, 40, 9])
+    lengths = np.array([128, 72, 9])
     for b in range(3):
         tok[b, lengths[b]:] = -1
     Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
