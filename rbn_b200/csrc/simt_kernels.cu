@@ -11,8 +11,10 @@
 // in per-cell power-of-two scaled form: beta = m * 2^e with max_a m = [0.5, 1); an all-zero cell keeps the finite
 // exponent of its best split so that derivatives w.r.t. zero-probability entries survive (oracle: flat_forward).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace rbn {
 
@@ -81,7 +83,7 @@ __global__ void k_emission(int N, int L, int nt, const float* __restrict__ T, co
 }
 
 // split coefficients of span (i, i+w): c_u = 2^(e_left(u) + e_right(u) - E), E = max_u (...)
-__device__ __forceinline__ int split_coefs(int L, int w, int i, const int* __restrict__ ce_seq, float* cj, int* sE) {
+__device__ __forceinline__ int split_coefs(int L, int w, int i, const int* ce_seq, float* cj, int* sE) {
     if (threadIdx.x == 0) *sE = INT_MIN;
     __syncthreads();
     int mine = INT_MIN;
@@ -102,7 +104,7 @@ __device__ __forceinline__ int split_coefs(int L, int w, int i, const int* __res
 
 // Y[bb][c] = sum_u c_u * left_u[b0+bb] * right_u[c]   (the split-sum, taken before the rule contraction)
 __device__ __forceinline__ void split_sum_block(int N, int L, int w, int i, int b0, int tb,
-                                                const float* __restrict__ cv_seq, const float* cj, float* Y) {
+                                                const float* cv_seq, const float* cj, float* Y) {
     for (int idx = threadIdx.x; idx < tb * N; idx += blockDim.x) {
         int bb = idx / N, c = idx - bb * N;
         float acc = 0.f;
@@ -116,20 +118,27 @@ __device__ __forceinline__ void split_sum_block(int N, int L, int w, int i, int 
 }
 
 // ---- inside: one span diagonal ----------------------------------------------------------------------------------
-__global__ void k_inside_diag(int N, int L, int w, int TB, const float* __restrict__ W,
-                              const int* __restrict__ lengths, float* __restrict__ cv, int* __restrict__ ce) {
-    extern __shared__ float sm[];
+// body of one span (CTA-uniform control flow); `blk` = b * (L - w + 1) + i
+__device__ __forceinline__ void inside_span(int N, int L, int w, int TB, const float* __restrict__ W,
+                                            const int* __restrict__ lengths, float* cv, int* ce, int blk, float* sm) {
     __shared__ float red[32];
     __shared__ int sE;
     int nI = L - w + 1;
-    int b = blockIdx.x / nI, i = blockIdx.x % nI;
+    int b = blk / nI, i = blk % nI;
     if (i + w > lengths[b]) return;
     size_t seq = (size_t)b * cells_per_seq(L);
     const float* cv_seq = cv + seq * N;
     const int* ce_seq = ce + seq;
     float* cj = sm;               // [L+1]
     float* Y = sm + (L + 1);      // [TB][N]
+    float* oacc = Y + (size_t)TB * N;   // [N]  (small N only)
     int E = split_coefs(L, w, i, ce_seq, cj, &sE);
+
+    // small grammars: kThreads / N groups of N threads share the (b, c) range, partial sums meet in shared memory
+    const bool grouped = (N * 4 <= kThreads);
+    const int ng = grouped ? kThreads / N : 1;
+    const int grp = threadIdx.x / N, ga = threadIdx.x - grp * N;
+    if (grouped && threadIdx.x < N) oacc[threadIdx.x] = 0.f;
 
     float out[kMaxAPerThread];
 #pragma unroll
@@ -138,18 +147,28 @@ __global__ void k_inside_diag(int N, int L, int w, int TB, const float* __restri
         int tb = min(TB, N - b0);
         split_sum_block(N, L, w, i, b0, tb, cv_seq, cj, Y);
         __syncthreads();
+        if (grouped) {
+            if (grp < ng) {
+                float acc = 0.f;
+                const float* Wp = W + (size_t)b0 * N * N + ga;
+                for (int idx = grp; idx < tb * N; idx += ng) acc = fmaf(Y[idx], Wp[(size_t)idx * N], acc);
+                atomicAdd(&oacc[ga], acc);
+            }
+        } else {
 #pragma unroll
-        for (int q = 0; q < kMaxAPerThread; ++q) {
-            int a = threadIdx.x + q * kThreads;
-            if (a < N) {
-                float acc = out[q];
-                const float* Wp = W + (size_t)b0 * N * N + a;
-                for (int idx = 0; idx < tb * N; ++idx) acc = fmaf(Y[idx], Wp[(size_t)idx * N], acc);
-                out[q] = acc;
+            for (int q = 0; q < kMaxAPerThread; ++q) {
+                int a = threadIdx.x + q * kThreads;
+                if (a < N) {
+                    float acc = out[q];
+                    const float* Wp = W + (size_t)b0 * N * N + a;
+                    for (int idx = 0; idx < tb * N; ++idx) acc = fmaf(Y[idx], Wp[(size_t)idx * N], acc);
+                    out[q] = acc;
+                }
             }
         }
         __syncthreads();
     }
+    if (grouped && threadIdx.x < N) out[0] = oacc[threadIdx.x];
     float mx = 0.f;
 #pragma unroll
     for (int q = 0; q < kMaxAPerThread; ++q) mx = fmaxf(mx, out[q]);
@@ -162,6 +181,28 @@ __global__ void k_inside_diag(int N, int L, int w, int TB, const float* __restri
         if (a < N) cv[cell * N + a] = ldexpf(out[q], -e);
     }
     if (threadIdx.x == 0) ce[cell] = E + e;
+}
+
+__global__ void k_inside_diag(int N, int L, int w, int TB, const float* __restrict__ W,
+                              const int* __restrict__ lengths, float* cv, int* ce) {
+    extern __shared__ float sm[];
+    inside_span(N, L, w, TB, W, lengths, cv, ce, blockIdx.x, sm);
+}
+
+// Small problems (a handful of short sequences, the reference's own use): ALL diagonals in one cooperative launch,
+// grid-wide barrier between widths instead of L - 1 kernel launches.
+__global__ void k_inside_all(int N, int L, int B, int TB, const float* __restrict__ W, const int* __restrict__ lengths,
+                             float* cv, int* ce) {
+    extern __shared__ float sm[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int w = 2; w <= L; ++w) {
+        const int items = B * (L - w + 1);
+        for (int blk = blockIdx.x; blk < items; blk += gridDim.x) {
+            inside_span(N, L, w, TB, W, lengths, cv, ce, blk, sm);
+            __syncthreads();
+        }
+        grid.sync();
+    }
 }
 
 // ---- root / prior -----------------------------------------------------------------------------------------------
@@ -205,14 +246,13 @@ __global__ void k_outside_seed(int N, int L, const float* __restrict__ prior, co
     }
 }
 
-__global__ void k_outside_diag(int N, int L, int w, int TB, const float* __restrict__ W,
-                               const int* __restrict__ lengths, const float* __restrict__ cv,
-                               const int* __restrict__ ce, float* __restrict__ alpha, float* __restrict__ gW) {
-    extern __shared__ float sm[];
+__device__ __forceinline__ void outside_span(int N, int L, int w, int TB, const float* __restrict__ W,
+                                             const int* __restrict__ lengths, const float* __restrict__ cv,
+                                             const int* __restrict__ ce, float* alpha, float* gW, int blk, float* sm) {
     __shared__ int sE;
     __shared__ int sAny;
     int nI = L - w + 1;
-    int b = blockIdx.x / nI, i = blockIdx.x % nI;
+    int b = blk / nI, i = blk % nI;
     if (i + w > lengths[b]) return;
     size_t seq = (size_t)b * cells_per_seq(L);
     const float* cv_seq = cv + seq * N;
@@ -248,35 +288,56 @@ __global__ void k_outside_diag(int N, int L, int w, int TB, const float* __restr
             gY[idx] = acc;
         }
         __syncthreads();
-        // expected rule counts: gW[b][c][a] += Y[b][c] * G[a]
-        for (int idx = 0; idx < tb * N; ++idx) {
-            float y = Y[idx];
-            if (y == 0.f) continue;
-            float* gp = gW + ((size_t)b0 * N + idx) * N;
-            for (int a = threadIdx.x; a < N; a += blockDim.x) {
-                float g = G[a];
-                if (g != 0.f) atomicAdd(&gp[a], y * g);
-            }
+        // expected rule counts: gW[b][c][a] += Y[b][c] * G[a]   (all threads busy for any N: flat (b, c, a) index, a fastest)
+        for (int idx2 = threadIdx.x; idx2 < tb * N * N; idx2 += blockDim.x) {
+            const int idx = idx2 / N, a = idx2 - idx * N;
+            const float v = Y[idx] * G[a];
+            if (v != 0.f) atomicAdd(&gW[((size_t)b0 * N + idx) * N + a], v);
         }
         // children: alpha[i,j][b] += c_u sum_c gY[b][c] right_u[c];  alpha[j,k][c] += c_u sum_b gY[b][c] left_u[b]
-        for (int u = 1; u < w; ++u) {
-            float cu = cj[u];
+        // flat (split, nonterminal) index so that short grammars still use every thread
+        for (int idx = threadIdx.x; idx < (w - 1) * tb; idx += blockDim.x) {
+            const int u = 1 + idx / tb, bb = idx - (u - 1) * tb;
+            const float cu = cj[u];
             if (cu == 0.f) continue;
-            int lcell = cell_off(u, L) + i, rcell = cell_off(w - u, L) + i + u;
-            const float* l = cv_seq + (size_t)lcell * N;
+            const int lcell = cell_off(u, L) + i, rcell = cell_off(w - u, L) + i + u;
             const float* r = cv_seq + (size_t)rcell * N;
-            for (int bb = threadIdx.x; bb < tb; bb += blockDim.x) {
-                float acc = 0.f;
-                for (int c = 0; c < N; ++c) acc = fmaf(gY[bb * N + c], r[c], acc);
-                if (acc != 0.f) atomicAdd(&al_seq[(size_t)lcell * N + b0 + bb], cu * acc);
-            }
-            for (int c = threadIdx.x; c < N; c += blockDim.x) {
-                float acc = 0.f;
-                for (int bb = 0; bb < tb; ++bb) acc = fmaf(gY[bb * N + c], l[b0 + bb], acc);
-                if (acc != 0.f) atomicAdd(&al_seq[(size_t)rcell * N + c], cu * acc);
-            }
+            float acc = 0.f;
+            for (int c = 0; c < N; ++c) acc = fmaf(gY[bb * N + c], r[c], acc);
+            if (acc != 0.f) atomicAdd(&al_seq[(size_t)lcell * N + b0 + bb], cu * acc);
+        }
+        for (int idx = threadIdx.x; idx < (w - 1) * N; idx += blockDim.x) {
+            const int u = 1 + idx / N, c = idx - (u - 1) * N;
+            const float cu = cj[u];
+            if (cu == 0.f) continue;
+            const int lcell = cell_off(u, L) + i, rcell = cell_off(w - u, L) + i + u;
+            const float* l = cv_seq + (size_t)lcell * N;
+            float acc = 0.f;
+            for (int bb = 0; bb < tb; ++bb) acc = fmaf(gY[bb * N + c], l[b0 + bb], acc);
+            if (acc != 0.f) atomicAdd(&al_seq[(size_t)rcell * N + c], cu * acc);
         }
         __syncthreads();
+    }
+}
+
+__global__ void k_outside_diag(int N, int L, int w, int TB, const float* __restrict__ W,
+                               const int* __restrict__ lengths, const float* __restrict__ cv,
+                               const int* __restrict__ ce, float* alpha, float* gW) {
+    extern __shared__ float sm[];
+    outside_span(N, L, w, TB, W, lengths, cv, ce, alpha, gW, blockIdx.x, sm);
+}
+
+__global__ void k_outside_all(int N, int L, int B, int TB, const float* __restrict__ W, const int* __restrict__ lengths,
+                              const float* __restrict__ cv, const int* __restrict__ ce, float* alpha, float* gW) {
+    extern __shared__ float sm[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int w = L; w >= 2; --w) {
+        const int items = B * (L - w + 1);
+        for (int blk = blockIdx.x; blk < items; blk += gridDim.x) {
+            outside_span(N, L, w, TB, W, lengths, cv, ce, alpha, gW, blk, sm);
+            __syncthreads();
+        }
+        grid.sync();
     }
 }
 
@@ -332,6 +393,27 @@ __global__ void k_lognormalize(float* __restrict__ lp, long long gs, long long g
 }
 
 // ---- host-side drivers ----------------------------------------------------------------------------------------------
+// Grid of the single-launch (cooperative) kernels, or 0 when the problem is not small: the widest diagonal must fit
+// the co-resident CTAs with at most 4 spans per CTA (beyond that per-diagonal launches keep all SMs busier than a
+// fixed grid with barriers would).  RBN_SIMT_COOP=0 disables the path.
+static int coop_grid_for(const void* kern, size_t smem, int widest_items) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("RBN_SIMT_COOP");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+        int dev = 0, coop = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop)
+            enabled = 0;
+    }
+    if (!enabled || widest_items < 1) return 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return 0; }
+    const int resident = per_sm * device_sm_count();
+    if (widest_items > 4 * resident) return 0;
+    return widest_items < resident ? widest_items : resident;
+}
+
 static int pick_tb(int N, int n_arrays) {
     // rows of Y (and gY) kept in shared memory at once; <= 64 KB in total for the tiles
     int tb = (64 * 1024 / 4) / (N * n_arrays);
@@ -352,11 +434,19 @@ int simt_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* 
     { ProfScope ps(KC_EMISSION, st); k_emission<<<B * L, kThreads, 0, st>>>(N, L, d->n_tvars, T, tokens, lengths, cv, ce); }
     RBN_LAUNCH_CHECK("k_emission");
     int TB = pick_tb(N, 1);
-    size_t smem = ((size_t)(L + 1) + (size_t)TB * N) * sizeof(float);
+    size_t smem = ((size_t)(L + 1) + (size_t)TB * N + N) * sizeof(float);
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_inside_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (int w = 2; w <= L; ++w) {
-        { ProfScope ps(KC_SIMT_INSIDE, st); k_inside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce); }
-        RBN_LAUNCH_CHECK("k_inside_diag");
+    int coop_grid = coop_grid_for((const void*)k_inside_all, smem, B * (L - 1));
+    if (coop_grid > 0 && L >= 2) {
+        RBN_CUDA_CHECK(cudaFuncSetAttribute(k_inside_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void* args[] = {&N, &L, &B, &TB, (void*)&W, (void*)&lengths, &cv, &ce};
+        { ProfScope ps(KC_SIMT_INSIDE, st);
+          RBN_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_inside_all, dim3(coop_grid), dim3(kThreads), args, smem, st)); }
+    } else {
+        for (int w = 2; w <= L; ++w) {
+            { ProfScope ps(KC_SIMT_INSIDE, st); k_inside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce); }
+            RBN_LAUNCH_CHECK("k_inside_diag");
+        }
     }
     { ProfScope ps(KC_OTHER, st); k_root<<<B, 128, 0, st>>>(N, L, prior, lengths, cv, ce, logZ, zroot, rootexp, (float*)(base + ws.zroot),
                               (int*)(base + ws.rootexp)); }
@@ -382,9 +472,19 @@ int simt_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float*
     int TB = pick_tb(N, 2);
     size_t smem = ((size_t)(L + 1) + N + 2 * (size_t)TB * N) * sizeof(float);
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_outside_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (int w = L; w >= 2; --w) {
-        { ProfScope ps(KC_SIMT_OUTSIDE, st); k_outside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce, alpha, gW); }
-        RBN_LAUNCH_CHECK("k_outside_diag");
+    int coop_grid = coop_grid_for((const void*)k_outside_all, smem, B * (L - 1));
+    if (coop_grid > 0 && L >= 2) {
+        RBN_CUDA_CHECK(cudaFuncSetAttribute(k_outside_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const float* cvc = cv;
+        const int* cec = ce;
+        void* args[] = {&N, &L, &B, &TB, (void*)&W, (void*)&lengths, (void*)&cvc, (void*)&cec, &alpha, &gW};
+        { ProfScope ps(KC_SIMT_OUTSIDE, st);
+          RBN_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_outside_all, dim3(coop_grid), dim3(kThreads), args, smem, st)); }
+    } else {
+        for (int w = L; w >= 2; --w) {
+            { ProfScope ps(KC_SIMT_OUTSIDE, st); k_outside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce, alpha, gW); }
+            RBN_LAUNCH_CHECK("k_outside_diag");
+        }
     }
     { ProfScope ps(KC_EMISSION, st); k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, ce, alpha, nullptr, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");

@@ -75,3 +75,32 @@ def test_batch_of_one_on_the_tensor_core_path():
     ref, rW, rT, rP = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths)
     np.testing.assert_allclose(lz, ref.numpy(), rtol=1e-4)
     assert np.abs(gW - rW.numpy()).max() <= 1e-3 * np.abs(rW.numpy()).max()
+
+
+def test_two_passes_on_two_streams_with_distinct_workspaces():
+    """The C ABI is stream-ordered and keeps no state between calls (include/rbn_b200.h): two passes queued on two
+    streams at once, each with its own workspace, give the results of running them one after the other."""
+    from oracle import inside_oracle as O
+    from rbn_b200 import inside_logZ, _lib
+    N, V, L, B = 64, 8, 24, 16
+    W, T, pr = O.synthetic_grammar(N, V, seed=13)
+    toks = [O.synthetic_tokens(B, L, V, seed=14 + k, ragged=True) for k in range(2)]
+    base = []
+    for tok, ln in toks:
+        Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+        lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(ln), path=_lib.PATH_TCGEN05)
+        lz.sum().backward()
+        base.append((lz.detach().cpu().numpy(), Wt.grad.cpu().numpy()))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for (tok, ln), st in zip(toks, streams):
+        with torch.cuda.stream(st):
+            Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+            lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok).cuda(), torch.tensor(ln).cuda(), path=_lib.PATH_TCGEN05)
+            lz.sum().backward()
+            outs.append((lz, Wt))
+    torch.cuda.synchronize()
+    for (lz, Wt), (lz0, g0) in zip(outs, base):
+        np.testing.assert_allclose(lz.detach().cpu().numpy(), lz0, rtol=1e-6)
+        np.testing.assert_allclose(Wt.grad.cpu().numpy(), g0, rtol=1e-4, atol=1e-7 * np.abs(g0).max())
