@@ -23,8 +23,8 @@ def load_reference():
     """Return the reference's modules as a dict {name: module}; raises if /root/reference is absent."""
     if not reference_available():
         raise RuntimeError("/root/reference is not present (GPU box?) -- use the committed fixtures instead")
-    for p in (_SHIMS, REFERENCE_ROOT):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+    for p in (_SHIMS, REFERENCE_ROOT):          # appended, not prepended: /root/reference has a `tests` package of its
+        if p not in sys.path:                   # own that must not shadow this repo's (spawned test workers import ours)
+            sys.path.append(p)
     names = ["rbnet.base", "rbnet.util", "rbnet.sequential", "rbnet.pcfg", "rbnet.multivariate_normal"]
     return {n.split(".")[1]: importlib.import_module(n) for n in names}

@@ -55,7 +55,7 @@ def test_two_rank_step_equals_single_rank_over_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, W, T, pr, tok, lengths, q)) for r in range(2)]
     for p in procs:
         p.start()
-    lz, gW, gT, gP = q.get(timeout=900)
+    lz, gW, gT, gP = q.get(timeout=240)
     for p in procs:
         p.join(timeout=300)
         assert p.exitcode == 0
