@@ -369,6 +369,16 @@ def run_ours(args, wl):
             entry("count_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
             entry("child_grad", "hbm (read + L2 reduce-add)", y_bytes + row_bytes + 2.0 * splits * 2 * N * 4, peaks["hbm"], "GB/s")
         roofline["by_kernel"] = per
+        # the step as a whole against HBM: Y written by every split-sum pass and read by the rule / count GEMM, gY
+        # written and read once, child rows streamed by K1 and K5, outside-chart reduce-adds counted as read + write
+        step_bytes = passes * (y_bytes + row_bytes) + y_bytes
+        if wl["outside"]:
+            step_bytes += y_bytes + 2 * y_bytes + row_bytes + 2 * (2.0 * splits * 2 * N * 4)
+        ach = step_bytes / (ms_step * 1e-3) / 1e9
+        roofline["step_hbm"] = dict(algorithmic_bytes_per_step=step_bytes, achieved=round(ach, 1), peak=peaks["hbm"], unit="GB/s",
+                                    frac=round(ach / peaks["hbm"], 3),
+                                    note="every kernel of this path streams the N^2-per-span split-sum intermediate through HBM; "
+                                         "the step is bandwidth-bound (writes cap at 3.9 TB/s), see DESIGN.md section 3.4")
     launches = int(sum(v[1] for v in prof.values()))
     cpu_v, cpu_t, cpu_samp, cores = cpu_sample(wl) if (world == 1 and not args.skip_cpu) else (None, None, None, None)
     line = dict(metric="inside+outside sequences/sec" if wl["outside"] else "inside sequences/sec",
