@@ -279,6 +279,10 @@ def run_ours(args, wl):
     prof = _lib.profile_read(reset=True)
     _lib.profile_enable(False)
     lz_host = lz.detach().double().cpu().numpy()
+    del lz                                   # releases the last pass's workspace (88 GB at N = 512) before the e2e arm
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
     # ---- end-to-end arm: public API, host tokens in pinned memory, loss back to the host --------------------------------
     model = build_model(N, V, seed=0, device=dev)
@@ -469,7 +473,8 @@ def run_gauss(args, wl):
     cell_bytes = 8 * (1 + D + D * D)
     splits = (L ** 3 - L) // 6
     alg_bytes = 3.0 * B * 2 * splits * cell_bytes             # child-cell reads fwd + bwd + adjoint updates
-    diag_ms, diag_launches = prof["other"]
+    diag_ms = prof["simt_inside"][0] + prof["simt_outside"][0]      # k_gauss_diag + k_gauss_bwd_diag
+    diag_launches = prof["simt_inside"][1] + prof["simt_outside"][1]
     ach = alg_bytes * args.steps / (diag_ms * 1e-3) / 1e9 if diag_ms > 0 else None
     cpu = None
     if world == 1 and not args.skip_cpu:
