@@ -273,7 +273,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = (rank == 0);
-    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * BLOCK_N);
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(SEG > 0 ? 2 * BLOCK_N : BLOCK_N);   // SEG == 0 uses one accumulator
     constexpr int SEGD = SEG > 0 ? SEG : 1;
     constexpr int HALF_N = BLOCK_N / 2;
 

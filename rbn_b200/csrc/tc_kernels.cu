@@ -263,7 +263,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
               const __grid_constant__ CUtensorMap tmLC1, const __grid_constant__ CUtensorMap tmRC1,   // second K-slab (rows = Kpad - 64)
               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYtail,
               int N, int L, int Lp, int w, int m0, int cnt, int stages, const int* __restrict__ lengths,
-              const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e) {
+              const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e, int nslots) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int Kpad = ((w - 1) + 15) & ~15;
@@ -271,9 +271,15 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     // N > 256: the N x N split-sum is cut into (N/256)^2 sub-blocks of 256 x 256, each handled like a span of its own
     const int NS = N > 256 ? 256 : N;          // nonterminals per sub-block side
     const int nblk = N / NS;
-    const int nsub = nblk * nblk;
-    const int halves = (NS + 127) / 128;
-    const int a_atoms = halves * 2;            // A operand covers halves * 128 rows (zero beyond NS)
+    // nslots == 1 (one 256-column accumulator): the two 128-row halves of a sub-block cannot accumulate side by side
+    // over the K slabs, so every half becomes a sub-item of its own (its left-child slab has 128 nonterminals; the
+    // right-child slab is loaded once per half)
+    const bool hsplit = (nslots == 1) && (NS == 256);
+    const int RB = hsplit ? 128 : NS;          // left nonterminals (rows of Y) per sub-item
+    const int nsub = (N / RB) * nblk;
+    const int halves = hsplit ? 1 : (NS + 127) / 128;
+    const int a_atoms = halves * 2;            // A operand covers halves * 128 rows (zero beyond the loaded atoms)
+    const int l_atoms = RB / 64;               // left-child atoms actually loaded
     const int b_atoms = NS / 64;
     const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * 8192;
     uint8_t* ybuf = smem + (size_t)stages * stage_bytes;       // 2 x 16 KB staging tiles for the Y stores
@@ -288,7 +294,9 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     float* cj = (float*)(red + 4);                // [128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t TMEM_COLS = tmem_cols_pow2(2 * NS);      // two accumulators: the halves of a span, or (N <= 64... one half) consecutive spans
+    // nslots = 2: two accumulators (the halves of a span, or consecutive spans when a span has one half); nslots = 1:
+    // a single accumulator (256 TMEM columns), used when this kernel shares its SM with a GEMM CTA (co-resident schedule)
+    const uint32_t TMEM_COLS = tmem_cols_pow2(nslots * NS);
     const int nI = L - w + 1;
     const size_t C = cells_per_seq(L);
 
@@ -307,9 +315,9 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         ptx::tma_prefetch_desc(&tmRC);
     }
     // zero the A atoms that lie beyond N (N = 64 or 192) in every stage: TMA never writes them
-    if (a_atoms > b_atoms)
+    if (a_atoms > l_atoms)
         for (int sidx = 0; sidx < stages; ++sidx)
-            for (uint32_t off = (uint32_t)b_atoms * 8192 + threadIdx.x * 16; off < (uint32_t)a_atoms * 8192; off += kK1Threads * 16)
+            for (uint32_t off = (uint32_t)l_atoms * 8192 + threadIdx.x * 16; off < (uint32_t)a_atoms * 8192; off += kK1Threads * 16)
                 *reinterpret_cast<uint4*>(smem + (size_t)sidx * stage_bytes + off) = make_uint4(0, 0, 0, 0);
     if (warp == 9) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::fence_proxy_async_smem();
@@ -330,18 +338,18 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                 const int lc_row = (int)(((size_t)b * L + i) * Lp + (i + 1));
                 const int rc_row = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
                 for (int sub = 0; sub < nsub; ++sub) {
-                    const int bcol = (sub / nblk) * NS, ccol = (sub % nblk) * NS;
+                    const int bcol = (sub / nblk) * RB, ccol = (sub % nblk) * NS;
                     for (int part = 0; part < parts; ++part) {
                         ptx::mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sL = smem + (size_t)stage * stage_bytes;
                         uint8_t* sR = sL + (size_t)a_atoms * 8192;
                         // the box of this slab holds exactly Ks = min(64, Kpad - 64 part) chart rows (its atom stays 8 KB apart)
                         const int Ks = min(64, Kpad - part * 64);
-                        ptx::mbar_expect_tx(&tma_full[stage], (uint32_t)b_atoms * 2 * (uint32_t)Ks * 128);
-                        for (int a = 0; a < b_atoms; ++a) {
+                        ptx::mbar_expect_tx(&tma_full[stage], (uint32_t)(l_atoms + b_atoms) * (uint32_t)Ks * 128);
+                        for (int a = 0; a < l_atoms; ++a)
                             ptx::tma_load_2d(sL + a * 8192, part ? &tmLC1 : &tmLC, &tma_full[stage], bcol + a * 64, lc_row + part * 64);
+                        for (int a = 0; a < b_atoms; ++a)
                             ptx::tma_load_2d(sR + a * 8192, part ? &tmRC1 : &tmRC, &tma_full[stage], ccol + a * 64, rc_row + part * 64);
-                        }
                         if (++stage == stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -352,7 +360,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         const int p = threadIdx.x - 128;                // 0..127
         int stage = 0;
         uint32_t phase = 0;
-        const int chunks_per_row = NS / 8;              // 16-byte chunks per (sub-block) chart row
+        const int chunks_per_row = RB / 8;              // 16-byte chunks per left-child slab row
         // e_left + e_right of this thread's split of span t (INT_MIN: no such split / span beyond its sequence)
         // (kept as two registers and added at the point of use, so that the loads stay in flight across the iteration)
         auto fetch_sft = [&](int t, int& ea, int& eb) {
@@ -427,7 +435,8 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                     const uint32_t aL = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint32_t aR = aL + (uint32_t)a_atoms * 8192;
                     for (int h = 0; h < halves; ++h) {
-                        const uint32_t slot = (nacc + h) & 1, slot_phase = ((nacc + h) >> 1) & 1;
+                        const uint32_t na = nacc + h;
+                        const uint32_t slot = nslots == 2 ? (na & 1) : 0, slot_phase = nslots == 2 ? ((na >> 1) & 1) : (na & 1);
                         if (part == 0) {
                             ptx::mbar_wait(&acc_empty[slot], slot_phase ^ 1);
                             ptx::tc_fence_after();
@@ -456,9 +465,10 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
             const int b = m / nI, i = m - b * nI;
             if (i + w > lengths[b]) continue;
             for (int sub = 0; sub < nsub; ++sub) {
-                const int brow = (sub / nblk) * NS, ccol = (sub % nblk) * NS;
+                const int brow = (sub / nblk) * RB, ccol = (sub % nblk) * NS;
                 for (int h = 0; h < halves; ++h) {
-                    const uint32_t slot = (nacc + h) & 1, slot_phase = ((nacc + h) >> 1) & 1;
+                    const uint32_t na = nacc + h;
+                    const uint32_t slot = nslots == 2 ? (na & 1) : 0, slot_phase = nslots == 2 ? ((na >> 1) & 1) : (na & 1);
                     ptx::mbar_wait(&acc_full[slot], slot_phase);
                     ptx::tc_fence_after();
                     const uint32_t taddr = tmem_base + slot * NS + ((uint32_t)(warp * 32) << 16);
@@ -1297,7 +1307,8 @@ const TcTune& tc_tune() {
     static TcTune t;
     static std::once_flag once;
     std::call_once(once, [] {
-        t.overlap = env_int("RBN_TC_OVERLAP", 0) != 0;
+        t.overlap = env_int("RBN_TC_OVERLAP", 0);
+        if (t.overlap < 0 || t.overlap > 2) t.overlap = 0;
         t.groups = env_int("RBN_TC_GROUPS", 2);
         t.fwd_sms0 = env_int("RBN_TC_FWD_SMS0", 40) & ~1;
         t.bwd_sms0 = env_int("RBN_TC_BWD_SMS0", 74) & ~1;
@@ -1367,7 +1378,10 @@ struct Sched {
 
     Sched() : two(false), pair_launch(false), dev(0), err(RBN_OK) { st[0] = st[1] = nullptr; sms[0] = sms[1] = 0; }
 
-    int begin(cudaStream_t user, bool overlap, int sms0) {
+    // mode 1: disjoint SM partitions (sms0 | rest);  mode 2: both streams use every SM, their kernels are the
+    // 'half SM' variants that leave room for one CTA of the other stream (co-resident schedule)
+    int begin(cudaStream_t user, int mode, int sms0) {
+        const bool overlap = mode != 0;
         const int total = sm_count();
         st[0] = st[1] = user;
         sms[0] = sms[1] = total;
@@ -1385,9 +1399,11 @@ struct Sched {
             RBN_CUDA_CHECK(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
             two = true;
         }
-        pair_launch = true;
-        sms[0] = sms0;
-        sms[1] = (total - sms0) & ~1;
+        pair_launch = (mode == 1);
+        if (mode == 1) {
+            sms[0] = sms0;
+            sms[1] = (total - sms0) & ~1;
+        }
         cudaEvent_t e = record(0);            // fork: stream 1 starts after everything queued on the caller's stream
         wait(1, e);
         return err;
@@ -1484,7 +1500,7 @@ static int prep_weights(TcCtx& c, const float* W, cudaStream_t st) {
     return RBN_OK;
 }
 
-static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired) {
+static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired, bool half_sm = false) {
     int N = c.N, L = c.L, B = c.B;
     const int w = u.w, m0 = u.m0, cnt = u.cnt;
     const int Kpad = ((w - 1) + 15) & ~15;
@@ -1513,13 +1529,23 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     int stages = (int)((232448 / ctas - 1024 * ctas - 2048 - 32768) / stage_bytes);
     if (stages > 6) stages = 6;
     if (stages < 1) { stages = 1; ctas = 1; }
+    int nslots = 2;
+    if (half_sm) {              // leave half of the SM (shared memory, TMEM, registers) to a co-resident GEMM CTA
+        if (NS == 256) stage_bytes = (size_t)(2 + NS / 64) * 8192;      // halves become sub-items (one accumulator)
+        stages = (int)((113 * 1024 - 2048 - 32768) / stage_bytes);
+        if (stages < 1) stages = 1;
+        if (stages > 3) stages = 3;
+        nslots = 1;
+        ctas = 2;               // selects the register-capped instantiation; the grid stays one CTA per SM
+    }
     size_t smem = stages * stage_bytes + 32768 /*Y staging*/ + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
     auto kern = ctas > 1 ? k_tc_splitsum<2> : k_tc_splitsum<1>;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < sms * ctas ? cnt : sms * ctas;
+    if (half_sm && grid > sms) grid = sms;
     { ProfScope ps(KC_SPLITSUM, st);
       RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, kK1Threads, smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
-                                         c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y(u.slot), c.item_e(u.slot))); }
+                                         c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y(u.slot), c.item_e(u.slot), nslots)); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
 }
@@ -1540,7 +1566,7 @@ static int tail_splits_for(int r, int pairs, int k_blocks) {
 }
 
 template <int BN>
-static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
+static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool half_sm) {
     const int w = u.w, m0 = u.m0, cnt = u.cnt;
     size_t NN = (size_t)c.N * c.N;
     CUtensorMap tmA, tmB;
@@ -1553,6 +1579,24 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
     if (n_tiles > 1 && !use_pairs()) {
         set_error("N = %d needs the CTA-pair kernels (unset RBN_TC_1CTA)", c.N);
         return RBN_E_UNSUPPORTED;
+    }
+    if (half_sm && use_pairs() && n_tiles == 1) {
+        // co-resident schedule: 3 stages (96 KB), ONE 256-column accumulator.  Every tile is cut along K into chains of
+        // <= 64 k-blocks (no in-TMEM segmentation needed); the partial sums meet in the fp32 buffer, k_rule_finalize
+        // turns them into chart cells.
+        CUtensorMap tmB2;
+        rc = make_tmap_2d(&tmB2, c.wt, NN, (uint64_t)c.N, NN * 2, BN / 2);
+        if (rc) return rc;
+        const int kb = (int)(NN / 64);
+        GemmShape shape2{(cnt + 255) / 256, 1, kb, 0, (kb + kSegBlocks - 1) / kSegBlocks, 1};
+        if (shape2.tail_splits < 2) shape2.tail_splits = 1;
+        RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot), 0, (size_t)cnt * c.N * sizeof(float), st));
+        rc = launch_tc_gemm2<false, false, BN, 3, 0, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule,half>", KC_RULE);
+        if (rc) return rc;
+        { ProfScope ps(KC_RULE_FIN, st);
+          k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+        RBN_LAUNCH_CHECK("k_rule_finalize");
+        return RBN_OK;
     }
     if (use_pairs()) {
         CUtensorMap tmB2;
@@ -1592,12 +1636,12 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
     GemmShape shape{(cnt + 127) / 128, 1, (int)(NN / 64), 0, 1, 0};
     return launch_tc_gemm<false, false, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiRule>(tmA, tmB, shape, epi, sms, st, "k_tc_gemm<rule>", KC_RULE);
 }
-static int launch_k2(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
+static int launch_k2(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool half_sm = false) {
     switch (c.N) {
-        case 64: return launch_k2_bn<64>(c, u, st, sms);
-        case 128: return launch_k2_bn<128>(c, u, st, sms);
-        case 192: return launch_k2_bn<192>(c, u, st, sms);
-        default: return launch_k2_bn<256>(c, u, st, sms);
+        case 64: return launch_k2_bn<64>(c, u, st, sms, false);
+        case 128: return launch_k2_bn<128>(c, u, st, sms, false);
+        case 192: return launch_k2_bn<192>(c, u, st, sms, false);
+        default: return launch_k2_bn<256>(c, u, st, sms, half_sm);
     }
 }
 
@@ -1751,10 +1795,11 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
     { ProfScope ps(KC_EMISSION, st); k_copy_width1<<<B * L, 128, 0, st>>>(N, L, c.Lp, lengths, c.cv, c.lc, c.rc); }
     RBN_LAUNCH_CHECK("k_copy_width1");
 
-    const bool overlap = tune.overlap && ws.nslot >= 2 && B >= 2 * tune.groups;
+    const int mode = (tune.overlap && ws.nslot >= 2 && B >= 2 * tune.groups) ? tune.overlap : 0;
+    const bool overlap = mode != 0, half_sm = (mode == 2);
     const int groups = overlap ? tune.groups : 1;
     Sched S;
-    if ((rc = S.begin(st, overlap, tune.fwd_sms0))) return rc;
+    if ((rc = S.begin(st, mode, tune.fwd_sms0))) return rc;
     const int wave = (S.sms[1] / 2) * 256;                     // rule-GEMM rows per wave of CTA pairs
     std::vector<Unit> units;
     std::vector<cudaEvent_t> evK2;
@@ -1768,9 +1813,9 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
             const Unit& u = units[ui];
             if (last_prev[u.g] >= 0) S.wait(0, evK2[last_prev[u.g]]);            // narrower cells of this group are written
             if ((int)ui - ws.nslot >= 0) S.wait(0, evK2[ui - ws.nslot]);         // the slot's previous reader is done
-            if ((rc = launch_k1(c, u, S.st[0], S.sms[0], S.pair_launch))) break;
+            if ((rc = launch_k1(c, u, S.st[0], S.sms[0], S.pair_launch, half_sm))) break;
             S.wait(1, S.record(0));
-            if ((rc = launch_k2(c, u, S.st[1], S.sms[1]))) break;
+            if ((rc = launch_k2(c, u, S.st[1], S.sms[1], half_sm))) break;
             evK2[ui] = S.record(1);
             last_cur[u.g] = (int)ui;
         }
@@ -1805,11 +1850,12 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     { ProfScope ps(KC_OTHER, st); k_tc_outside_seed<<<B, 128, 0, st>>>(N, L, c.Lp, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior); }
     RBN_LAUNCH_CHECK("k_tc_outside_seed");
 
-    const bool overlap = tune.overlap && ws.nslot >= 2 && B >= 2 * tune.groups;
+    const int mode = (tune.overlap == 1 && ws.nslot >= 2 && B >= 2 * tune.groups) ? 1 : 0;   // co-resident mode: inside pass only (so far)
+    const bool overlap = mode != 0;
     const int groups = overlap ? tune.groups : 1;
     Sched S;
     int rc;
-    if ((rc = S.begin(st, overlap, tune.bwd_sms0))) return rc;
+    if ((rc = S.begin(st, mode, tune.bwd_sms0))) return rc;
     const int s3 = (overlap && tune.k3_stream) ? 1 : 0;        // stream of the gY GEMM
     const int wave = (S.sms[s3] / 2) * 256;
     std::vector<Unit> units;
