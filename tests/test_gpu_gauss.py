@@ -72,3 +72,42 @@ def test_gaussian_rbn_module_end_to_end():
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
     z = m.inside(g["y"][0])
     assert abs(float(torch.log(z)) - float(ref[0])) < 1e-8
+
+
+def test_full_size_config4_properties():
+    """BASELINE configs[3] shape (D = 8, L = 64) through size-independent properties: a directional finite difference of
+    sum_b log Z_b along a random perturbation of every parameter agrees with the CUDA gradient, the structural
+    log-probability gradients count the rule uses (L terminal, L - 1 binary per sequence), and log Z of a sequence does
+    not depend on what else is in the batch."""
+    from oracle import gauss_oracle as G
+    from rbn_b200.gaussian import gauss_logZ
+    D, B, L = 8, 6, 64
+    g = G.synthetic_gauss(D, B, L, seed=77)
+    names = ["y", "cov_term", "cov_left", "cov_right", "prior_mean", "prior_cov", "log_struct"]
+    C = {k: torch.tensor(g[k], device="cuda", requires_grad=True) for k in names}
+
+    def f(t):
+        return gauss_logZ(t["y"], t["cov_term"], t["cov_left"], t["cov_right"], t["prior_mean"], t["prior_cov"], t["log_struct"])
+
+    lz = f(C)
+    assert torch.isfinite(lz).all()
+    lz.sum().backward()
+    assert abs(float(C["log_struct"].grad[0]) - B * L) < 1e-6 * B * L
+    assert abs(float(C["log_struct"].grad[1]) - B * (L - 1)) < 1e-6 * B * L
+    rng = np.random.default_rng(3)
+    direction, dot = {}, 0.0
+    for k in names:
+        d = rng.standard_normal(g[k].shape)
+        if k.startswith("cov") or k == "prior_cov":
+            d = 0.5 * (d + d.T)                       # stay symmetric
+        direction[k] = torch.tensor(d, device="cuda")
+        dot += float((C[k].grad * direction[k]).sum())
+    eps = 1e-6
+    with torch.no_grad():
+        plus = f({k: C[k] + eps * direction[k] for k in names}).sum()
+        minus = f({k: C[k] - eps * direction[k] for k in names}).sum()
+    fd = float(plus - minus) / (2 * eps)
+    assert abs(fd - dot) <= 1e-5 * max(abs(dot), 1.0), (fd, dot)
+    with torch.no_grad():
+        sub = f({k: (C[k][[4, 1]] if k == "y" else C[k]) for k in names})
+    np.testing.assert_allclose(sub.cpu().numpy(), lz.detach().cpu().numpy()[[4, 1]], rtol=1e-12)

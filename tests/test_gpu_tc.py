@@ -192,3 +192,21 @@ print("two-stream OK")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "two-stream OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_full_size_config2_shape_inside_only():
+    """BASELINE configs[1] shape (N = 64, L = 64, inside only) on a slice of the batch: log Z against the fp32 CUDA-core
+    path for every sequence, and invariance to where a sequence sits in the batch."""
+    from oracle import inside_oracle as O
+    from rbn_b200 import inside_logZ, _lib
+    N, V, L, B = 64, 32, 64, 48
+    W, T, pr = O.synthetic_grammar(N, V, seed=0)
+    tok, lengths = O.synthetic_tokens(B, L, V, seed=1)
+    dev = [torch.tensor(x, device="cuda") for x in (W, T, pr)]
+    lz_t = inside_logZ(*dev, torch.tensor(tok), torch.tensor(lengths), path=_lib.PATH_TCGEN05).cpu().numpy()
+    lz_s = inside_logZ(*dev, torch.tensor(tok), torch.tensor(lengths), path=_lib.PATH_SIMT).cpu().numpy()
+    assert np.isfinite(lz_t).all()
+    np.testing.assert_allclose(lz_t, lz_s, rtol=LOGZ_RTOL)
+    perm = np.random.default_rng(5).permutation(B)
+    lz_p = inside_logZ(*dev, torch.tensor(tok[perm]), torch.tensor(lengths[perm]), path=_lib.PATH_TCGEN05, chunk_items=512).cpu().numpy()
+    np.testing.assert_allclose(lz_p, lz_t[perm], rtol=2e-6)
