@@ -131,8 +131,29 @@ class _InsideFn(torch.autograd.Function):
         return outs[0], outs[1], outs[2], None, None, None, None, None, None
 
 
+def _padded_cardinality(N, batch_spans):
+    """Nonterminal count the tensor-core kernels take (64, 128, 192, 256, 512) when padding N up to it pays: the pad
+    symbols get probability zero everywhere, so every result is unchanged.  Small problems stay on the CUDA-core path
+    (they are latency-bound, padding would only add work)."""
+    if N % 64 == 0 or N > 512 or N < 24 or batch_spans < 4096:
+        return N
+    if N > 256:
+        return 512 if N >= 400 else N          # 257..399 would waste > 2.2x of the contraction: stay on the CUDA-core path
+    return (N + 63) // 64 * 64
+
+
+def _pad_grammar(W, T, prior, Np):
+    N = W.shape[0]
+    if Np == N:
+        return W, T, prior
+    Wp = torch.nn.functional.pad(W, (0, Np - N, 0, Np - N, 0, Np - N))
+    return Wp, torch.nn.functional.pad(T, (0, Np - N)), torch.nn.functional.pad(prior, (0, Np - N))
+
+
 def inside_logZ(W, T, prior, tokens, lengths=None, linear=False, path=_lib.PATH_AUTO, chunk_items=0, holder=None):
-    """Functional entry: flat grammar tensors (any float dtype / device) + integer tokens -> log Z [B] (or Z)."""
+    """Functional entry: flat grammar tensors (any float dtype / device) + integer tokens -> log Z [B] (or Z).
+    With `path=AUTO`, a nonterminal count that is not one the tensor-core kernels take is zero-padded up to the next one
+    when the batch is large enough for that to pay (differentiable: the pad is sliced off the gradients by autograd)."""
     tokens = torch.as_tensor(tokens)
     if tokens.dim() == 2:
         tokens = tokens[:, :, None]
@@ -141,6 +162,10 @@ def inside_logZ(W, T, prior, tokens, lengths=None, linear=False, path=_lib.PATH_
     lengths = torch.as_tensor(lengths)
     if int(lengths.min()) < 1 or int(lengths.max()) > tokens.shape[1]:
         raise ValueError("lengths must satisfy 1 <= lengths[b] <= tokens.shape[1]")
+    if path == _lib.PATH_AUTO:
+        L = int(tokens.shape[1])
+        Np = _padded_cardinality(int(W.shape[0]), int(tokens.shape[0]) * L * (L - 1) // 2)
+        W, T, prior = _pad_grammar(W, T, prior, Np)
     return _InsideFn.apply(W, T, prior, tokens, lengths, linear, holder if holder is not None else [], path, chunk_items)
 
 

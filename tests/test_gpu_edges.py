@@ -104,3 +104,25 @@ def test_two_passes_on_two_streams_with_distinct_workspaces():
     for (lz, Wt), (lz0, g0) in zip(outs, base):
         np.testing.assert_allclose(lz.detach().cpu().numpy(), lz0, rtol=1e-6)
         np.testing.assert_allclose(Wt.grad.cpu().numpy(), g0, rtol=1e-4, atol=1e-7 * np.abs(g0).max())
+
+
+def test_nonterminal_count_is_padded_onto_the_tensor_core_path():
+    """N = 100 with a large enough batch: AUTO zero-pads the grammar to N = 128 (tcgen05 kernels); results and gradient
+    shapes are those of the unpadded grammar."""
+    from oracle import inside_oracle as O
+    from rbn_b200 import inside_logZ, engine
+    N, V, L, B = 100, 9, 13, 64
+    assert engine._padded_cardinality(N, B * L * (L - 1) // 2) == 128
+    assert engine._padded_cardinality(10, 10 ** 6) == 10 and engine._padded_cardinality(N, 100) == N
+    W, T, pr = O.synthetic_grammar(N, V, seed=40)
+    tok, lengths = O.synthetic_tokens(B, L, V, seed=41, ragged=True)
+    Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+    holder = []
+    lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), holder=holder)
+    assert holder[0].desc.N == 128
+    lz.sum().backward()
+    assert Wt.grad.shape == (N, N, N) and Tt.grad.shape == (V, N) and pt.grad.shape == (N,)
+    ref, rW, rT, rP = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths)
+    np.testing.assert_allclose(lz.detach().cpu().numpy(), ref.numpy(), rtol=1e-4)
+    for g, r in ((Wt.grad, rW), (Tt.grad, rT), (pt.grad, rP)):
+        assert float((g.cpu() - r).abs().max() / r.abs().max()) <= 1e-3
