@@ -103,6 +103,25 @@ int rbn_inside_backward(const RbnDesc* desc,
                         float* gW, float* gT, float* gPrior,
                         void* stream);
 
+/* Ragged batches.  The same two passes with one more argument: a HOST array active[0..L], active[w] = number of
+ * sequences whose length is >= w.  It may only be given when the batch is sorted by length, longest first
+ * (lengths[0] >= lengths[1] >= ...); diagonal w then visits only the first active[w] sequences instead of padding
+ * every sequence to L (the reference parses one sequence at a time and never pads, sequential.py:23-26).
+ * host_active == NULL is rbn_inside_forward / rbn_inside_backward.  Forward and backward must get the same array. */
+int rbn_inside_forward_sorted(const RbnDesc* desc,
+                              const float* W, const float* T, const float* prior,
+                              const int32_t* tokens, const int32_t* lengths,
+                              void* workspace, size_t workspace_bytes,
+                              float* logZ, float* zroot, float* rootexp,
+                              const int32_t* host_active, void* stream);
+int rbn_inside_backward_sorted(const RbnDesc* desc,
+                               const float* W, const float* T, const float* prior,
+                               const int32_t* tokens, const int32_t* lengths,
+                               void* workspace, size_t workspace_bytes,
+                               const float* coef,
+                               float* gW, float* gT, float* gPrior,
+                               const int32_t* host_active, void* stream);
+
 /* Chart of one sequence in the reference's layout: rows ordered as triangularmap.TMap orders them (root first:
  * row = d(d+1)/2 + start with d = n - (end - start); pinned by /root/reference/tests/test_pcfg.py:14-19),
  * linear probability space, float64 [n(n+1)/2][N] with n = lengths[seq].  Serves SequentialRBN.inside_chart

@@ -16,15 +16,15 @@ void set_error(const char* fmt, ...) {
 }
 
 int simt_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*, const int*,
-                 float*, float*, float*, cudaStream_t);
+                 float*, float*, float*, const int*, cudaStream_t);
 int simt_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
-                  const int*, const float*, float*, float*, float*, cudaStream_t);
+                  const int*, const float*, float*, float*, float*, const int*, cudaStream_t);
 int export_chart(const RbnDesc*, const WsLayout&, const char*, const int*, int, double*, cudaStream_t);
 int lognormalize(float*, long long, long long, int*, cudaStream_t);
 int tc_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*, const int*,
-               float*, float*, float*, cudaStream_t);
+               float*, float*, float*, const int*, cudaStream_t);
 int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
-                const int*, const float*, float*, float*, float*, cudaStream_t);
+                const int*, const float*, float*, float*, float*, const int*, cudaStream_t);
 int debug_gemm(int, int, int, const __half*, const __half*, float*, int, int, int, cudaStream_t);
 size_t gauss_workspace_bytes(int, int, int);
 int gauss_backward(int, int, int, const int*, const double*, const double*, const double*, const double*, const double*,
@@ -156,14 +156,30 @@ size_t rbn_workspace_bytes(const RbnDesc* desc) {
     return ws.total;
 }
 
-int rbn_inside_forward(const RbnDesc* desc, const float* W, const float* T, const float* prior, const int32_t* tokens,
-                       const int32_t* lengths, void* workspace, size_t workspace_bytes, float* logZ, float* zroot,
-                       float* rootexp, void* stream) {
+static bool active_ok(const RbnDesc* d, const int32_t* a) {
+    if (!a) return true;
+    for (int w = 0; w <= d->L; ++w) {
+        if (a[w] < 0 || a[w] > d->B || (w > 0 && a[w] > a[w - 1])) {
+            set_error("host_active must be non-increasing with 0 <= active[w] <= B (w = %d: %d)", w, a[w]);
+            return false;
+        }
+    }
+    if (a[0] != d->B || a[1] != d->B) {
+        set_error("host_active[0] and host_active[1] must equal B (every sequence has length >= 1)");
+        return false;
+    }
+    return true;
+}
+
+int rbn_inside_forward_sorted(const RbnDesc* desc, const float* W, const float* T, const float* prior, const int32_t* tokens,
+                              const int32_t* lengths, void* workspace, size_t workspace_bytes, float* logZ, float* zroot,
+                              float* rootexp, const int32_t* host_active, void* stream) {
     if (!desc_ok(desc)) return RBN_E_BADARG;
     if (!W || !T || !prior || !tokens || !lengths || !workspace || !logZ || !zroot || !rootexp) {
         set_error("rbn_inside_forward: NULL pointer argument");
         return RBN_E_BADARG;
     }
+    if (!active_ok(desc, host_active)) return RBN_E_BADARG;
     WsLayout ws;
     if (!make_layout(desc, &ws)) return RBN_E_UNSUPPORTED;
     if (workspace_bytes < ws.total || ((uintptr_t)workspace & 1023)) {
@@ -172,18 +188,26 @@ int rbn_inside_forward(const RbnDesc* desc, const float* W, const float* T, cons
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (resolve_path(desc) == RBN_PATH_TCGEN05)
-        return tc_forward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, logZ, zroot, rootexp, st);
-    return simt_forward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, logZ, zroot, rootexp, st);
+        return tc_forward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, logZ, zroot, rootexp, host_active, st);
+    return simt_forward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, logZ, zroot, rootexp, host_active, st);
 }
 
-int rbn_inside_backward(const RbnDesc* desc, const float* W, const float* T, const float* prior, const int32_t* tokens,
-                        const int32_t* lengths, void* workspace, size_t workspace_bytes, const float* coef, float* gW,
-                        float* gT, float* gPrior, void* stream) {
+int rbn_inside_forward(const RbnDesc* desc, const float* W, const float* T, const float* prior, const int32_t* tokens,
+                       const int32_t* lengths, void* workspace, size_t workspace_bytes, float* logZ, float* zroot,
+                       float* rootexp, void* stream) {
+    return rbn_inside_forward_sorted(desc, W, T, prior, tokens, lengths, workspace, workspace_bytes, logZ, zroot, rootexp,
+                                     nullptr, stream);
+}
+
+int rbn_inside_backward_sorted(const RbnDesc* desc, const float* W, const float* T, const float* prior, const int32_t* tokens,
+                               const int32_t* lengths, void* workspace, size_t workspace_bytes, const float* coef, float* gW,
+                               float* gT, float* gPrior, const int32_t* host_active, void* stream) {
     if (!desc_ok(desc)) return RBN_E_BADARG;
     if (!W || !T || !prior || !tokens || !lengths || !workspace || !coef || !gW || !gT || !gPrior) {
         set_error("rbn_inside_backward: NULL pointer argument");
         return RBN_E_BADARG;
     }
+    if (!active_ok(desc, host_active)) return RBN_E_BADARG;
     WsLayout ws;
     if (!make_layout(desc, &ws)) return RBN_E_UNSUPPORTED;
     if (workspace_bytes < ws.total || ((uintptr_t)workspace & 1023)) {
@@ -192,8 +216,15 @@ int rbn_inside_backward(const RbnDesc* desc, const float* W, const float* T, con
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (resolve_path(desc) == RBN_PATH_TCGEN05)
-        return tc_backward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, coef, gW, gT, gPrior, st);
-    return simt_backward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, coef, gW, gT, gPrior, st);
+        return tc_backward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, coef, gW, gT, gPrior, host_active, st);
+    return simt_backward(desc, ws, (char*)workspace, W, T, prior, tokens, lengths, coef, gW, gT, gPrior, host_active, st);
+}
+
+int rbn_inside_backward(const RbnDesc* desc, const float* W, const float* T, const float* prior, const int32_t* tokens,
+                        const int32_t* lengths, void* workspace, size_t workspace_bytes, const float* coef, float* gW,
+                        float* gT, float* gPrior, void* stream) {
+    return rbn_inside_backward_sorted(desc, W, T, prior, tokens, lengths, workspace, workspace_bytes, coef, gW, gT, gPrior,
+                                      nullptr, stream);
 }
 
 int rbn_export_chart(const RbnDesc* desc, const int32_t* lengths, const void* workspace, size_t workspace_bytes,

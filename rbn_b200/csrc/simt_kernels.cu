@@ -423,7 +423,8 @@ static int pick_tb(int N, int n_arrays) {
 }
 
 int simt_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
-                 const int* tokens, const int* lengths, float* logZ, float* zroot, float* rootexp, cudaStream_t st) {
+                 const int* tokens, const int* lengths, float* logZ, float* zroot, float* rootexp, const int* active,
+                 cudaStream_t st) {
     if (d->N > kThreads * kMaxAPerThread) {
         set_error("shared-memory path supports N <= %d (got %d)", kThreads * kMaxAPerThread, d->N);
         return RBN_E_UNSUPPORTED;
@@ -444,7 +445,9 @@ int simt_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* 
           RBN_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_inside_all, dim3(coop_grid), dim3(kThreads), args, smem, st)); }
     } else {
         for (int w = 2; w <= L; ++w) {
-            { ProfScope ps(KC_SIMT_INSIDE, st); k_inside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce); }
+            const int Bw = active ? active[w] : B;          // sorted ragged batch: sequences that reach this width
+            if (Bw == 0) break;
+            { ProfScope ps(KC_SIMT_INSIDE, st); k_inside_diag<<<Bw * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce); }
             RBN_LAUNCH_CHECK("k_inside_diag");
         }
     }
@@ -456,7 +459,7 @@ int simt_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* 
 
 int simt_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
                   const int* tokens, const int* lengths, const float* coef, float* gW, float* gT, float* gPrior,
-                  cudaStream_t st) {
+                  const int* active, cudaStream_t st) {
     (void)T;
     float* cv = (float*)(base + ws.chart_val);
     int* ce = (int*)(base + ws.chart_exp);
@@ -482,7 +485,9 @@ int simt_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float*
           RBN_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_outside_all, dim3(coop_grid), dim3(kThreads), args, smem, st)); }
     } else {
         for (int w = L; w >= 2; --w) {
-            { ProfScope ps(KC_SIMT_OUTSIDE, st); k_outside_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce, alpha, gW); }
+            const int Bw = active ? active[w] : B;
+            if (Bw == 0) continue;
+            { ProfScope ps(KC_SIMT_OUTSIDE, st); k_outside_diag<<<Bw * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce, alpha, gW); }
             RBN_LAUNCH_CHECK("k_outside_diag");
         }
     }

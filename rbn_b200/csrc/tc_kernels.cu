@@ -1779,7 +1779,8 @@ static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
 // A split-sum of diagonal w needs every narrower cell of ITS sequences, i.e. the rule GEMMs of the same sequence
 // group on diagonal w - 1; the other group's kernels fill the gap.
 int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
-               const int* tokens, const int* lengths, float* logZ, float* zroot, float* rootexp, cudaStream_t st) {
+               const int* tokens, const int* lengths, float* logZ, float* zroot, float* rootexp, const int* active,
+               cudaStream_t st) {
     TcCtx c;
     fill_ctx(c, d, ws, base, lengths);
     int N = c.N, L = c.L, B = c.B;
@@ -1807,7 +1808,8 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
     int counter = 0;
     for (int w = 2; w <= L && !rc; ++w) {
         const size_t first = units.size();
-        diag_units(units, w, L, B, groups, c.chunk, wave, ws.nslot, counter);
+        // sorted ragged batch: only the first active[w] sequences reach width w (not combined with sequence groups)
+        diag_units(units, w, L, (active && !overlap) ? active[w] : B, groups, c.chunk, wave, ws.nslot, counter);
         evK2.resize(units.size(), nullptr);
         for (size_t ui = first; ui < units.size() && !rc; ++ui) {
             const Unit& u = units[ui];
@@ -1835,7 +1837,7 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
 // diagonal of ITS sequence group.
 int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
                 const int* tokens, const int* lengths, const float* coef, float* gW, float* gT, float* gPrior,
-                cudaStream_t st) {
+                const int* active, cudaStream_t st) {
     (void)W; (void)T;
     TcCtx c;
     fill_ctx(c, d, ws, base, lengths);
@@ -1864,7 +1866,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     int counter = 0;
     for (int w = L; w >= 2 && !rc; --w) {
         const size_t first = units.size();
-        diag_units(units, w, L, B, groups, c.chunk, wave, ws.nslot, counter);
+        diag_units(units, w, L, (active && !overlap) ? active[w] : B, groups, c.chunk, wave, ws.nslot, counter);
         evK5.resize(units.size(), nullptr);
         for (size_t ui = first; ui < units.size() && !rc; ++ui) {
             const Unit& u = units[ui];

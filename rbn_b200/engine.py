@@ -43,6 +43,18 @@ class _Pass:
         nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
         if nbytes == 0:
             _lib.check(-1, "rbn_workspace_bytes")
+        # ragged batch: sort by length (longest first) so that diagonal w only visits the sequences that reach it
+        # (rbn_inside_forward_sorted); `order[k]` = original index of the k-th sorted sequence, `pos[b]` its inverse
+        self.order = self.pos = self.active = None
+        len_host = lengths.detach().cpu().numpy().astype(np.int64)
+        if B > 1 and int(len_host.min()) != int(len_host.max()):
+            order = np.argsort(-len_host, kind="stable")
+            self.order = torch.as_tensor(order, device=dev)
+            self.pos = torch.as_tensor(np.argsort(order, kind="stable"), device=dev)
+            tokens = tokens.index_select(0, self.order).contiguous()
+            lengths = lengths.index_select(0, self.order).contiguous()
+            srt = len_host[order]
+            self.active = (ctypes.c_int32 * (L + 1))(*[int((srt >= w).sum()) for w in range(L + 1)])
         self.W, self.T, self.prior, self.tokens, self.lengths = W, T, prior, tokens, lengths
         self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
         self.ws_off = (-self.workspace.data_ptr()) % 1024
@@ -60,10 +72,14 @@ class _Pass:
     def forward(self):
         lib = _lib.load()
         with torch.cuda.device(self.W.device):
-            rc = lib.rbn_inside_forward(ctypes.byref(self.desc), _ptr(self.W), _ptr(self.T), _ptr(self.prior),
-                                        _ptr(self.tokens), _ptr(self.lengths), self._ws(), self.ws_bytes,
-                                        _ptr(self.logZ), _ptr(self.zroot), _ptr(self.rootexp), self._stream())
+            rc = lib.rbn_inside_forward_sorted(ctypes.byref(self.desc), _ptr(self.W), _ptr(self.T), _ptr(self.prior),
+                                               _ptr(self.tokens), _ptr(self.lengths), self._ws(), self.ws_bytes,
+                                               _ptr(self.logZ), _ptr(self.zroot), _ptr(self.rootexp),
+                                               ctypes.cast(self.active, ctypes.c_void_p) if self.active is not None else None,
+                                               self._stream())
         _lib.check(rc, "rbn_inside_forward")
+        if self.pos is not None:          # hand the outputs back in the caller's order
+            self.logZ, self.zroot, self.rootexp = (t.index_select(0, self.pos) for t in (self.logZ, self.zroot, self.rootexp))
 
     def backward(self, coef):
         lib = _lib.load()
@@ -72,16 +88,22 @@ class _Pass:
         gT = torch.empty_like(self.T)
         gP = torch.empty_like(self.prior)
         coef = coef.to(device=dev, dtype=torch.float32).contiguous()
+        if self.order is not None:
+            coef = coef.index_select(0, self.order).contiguous()
         with torch.cuda.device(dev):
-            rc = lib.rbn_inside_backward(ctypes.byref(self.desc), _ptr(self.W), _ptr(self.T), _ptr(self.prior),
-                                         _ptr(self.tokens), _ptr(self.lengths), self._ws(), self.ws_bytes,
-                                         _ptr(coef), _ptr(gW), _ptr(gT), _ptr(gP), self._stream())
+            rc = lib.rbn_inside_backward_sorted(ctypes.byref(self.desc), _ptr(self.W), _ptr(self.T), _ptr(self.prior),
+                                                _ptr(self.tokens), _ptr(self.lengths), self._ws(), self.ws_bytes,
+                                                _ptr(coef), _ptr(gW), _ptr(gT), _ptr(gP),
+                                                ctypes.cast(self.active, ctypes.c_void_p) if self.active is not None else None,
+                                                self._stream())
         _lib.check(rc, "rbn_inside_backward")
         return gW, gT, gP
 
     def export_chart(self, seq):
         """float64 [n(n+1)/2, N] linear-space chart of sequence `seq` in TMap row order (device tensor)."""
         lib = _lib.load()
+        if self.pos is not None:
+            seq = int(self.pos[seq])          # position of the caller's sequence in the length-sorted batch
         n = int(self.lengths[seq])
         out = torch.empty((n * (n + 1) // 2, self.desc.N), dtype=torch.float64, device=self.W.device)
         with torch.cuda.device(self.W.device):

@@ -237,6 +237,15 @@ def test_library_loads_and_exports_every_declared_symbol():
     ok = _lib.RbnDesc(N=10, V=19, B=1, L=20, n_tvars=1, path=0, chunk_items=0, flags=0)
     assert lib.rbn_workspace_bytes(ctypes.byref(ok)) > 0
     assert lib.rbn_resolve_path(ctypes.byref(ok)) == _lib.PATH_SIMT
+    # the sorted-ragged entry point validates its HOST array before touching a device: active[w] must be non-increasing,
+    # within [0, B], and B at w = 0, 1
+    desc = _lib.RbnDesc(N=10, V=19, B=3, L=4, n_tvars=1, path=0, chunk_items=0, flags=0)
+    fake = ctypes.c_void_p(1024)                     # never dereferenced: validation fails first
+    for bad_active, msg in (([3, 3, 2, 3, 1], b"non-increasing"), ([3, 2, 2, 1, 0], b"must equal B"), ([3, 3, 4, 1, 0], b"non-increasing")):
+        arr = (ctypes.c_int32 * 5)(*bad_active)
+        rc = lib.rbn_inside_forward_sorted(ctypes.byref(desc), fake, fake, fake, fake, fake, fake, 1 << 40, fake, fake, fake,
+                                           ctypes.cast(arr, ctypes.c_void_p), None)
+        assert rc == -1 and msg in lib.rbn_last_error(), (bad_active, lib.rbn_last_error())
 
 
 def test_engine_flattens_unmodified_reference_objects():

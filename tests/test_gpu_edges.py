@@ -126,3 +126,33 @@ def test_nonterminal_count_is_padded_onto_the_tensor_core_path():
     np.testing.assert_allclose(lz.detach().cpu().numpy(), ref.numpy(), rtol=1e-4)
     for g, r in ((Wt.grad, rW), (Tt.grad, rT), (pt.grad, rP)):
         assert float((g.cpu() - r).abs().max() / r.abs().max()) <= 1e-3
+
+
+@pytest.mark.parametrize("N,path", [(10, "simt"), (64, "tc")])
+def test_ragged_batch_is_sorted_internally_and_results_come_back_in_caller_order(N, path):
+    """The engine sorts a ragged batch by length and tells the library how many sequences reach each width
+    (rbn_inside_forward_sorted); log Z, gradients and exported charts are those of the caller's order."""
+    from oracle import inside_oracle as O
+    from rbn_b200 import inside_logZ, _lib
+    V, L, B = 6, 21, 40                       # SIMT: B (L - 1) large enough to leave the single-launch path
+    tok, _ = O.synthetic_tokens(B, L, V, seed=50)
+    lengths = np.random.default_rng(51).integers(1, L + 1, B)
+    lengths[3], lengths[7] = L, 1
+    for b in range(B):
+        tok[b, lengths[b]:] = -1
+    W, T, pr = O.synthetic_grammar(N, V, seed=52)
+    coef = np.random.default_rng(53).uniform(0.5, 1.5, B)
+    p = _lib.PATH_SIMT if path == "simt" else _lib.PATH_TCGEN05
+    Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+    holder = []
+    lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), path=p, holder=holder)
+    assert holder[0].active is not None and list(holder[0].active)[:2] == [B, B] and holder[0].active[L] >= 1
+    (lz * torch.tensor(coef, device="cuda")).sum().backward()
+    ref, rW, rT, rP = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths, grad_logZ=coef)
+    np.testing.assert_allclose(lz.detach().cpu().numpy(), ref.numpy(), rtol=1e-4)
+    for g, r in ((Wt.grad, rW), (Tt.grad, rT), (pt.grad, rP)):
+        assert float((g.cpu() - r).abs().max() / r.abs().max()) <= 1e-3
+    # chart of caller-order sequence 5 == chart of that sequence parsed alone
+    alone = []
+    inside_logZ(Wt.detach(), Tt.detach(), pt.detach(), torch.tensor(tok[5:6, :lengths[5]]), torch.tensor(lengths[5:6]), path=p, holder=alone)
+    np.testing.assert_allclose(holder[0].export_chart(5).cpu().numpy(), alone[0].export_chart(0).cpu().numpy(), rtol=1e-5, atol=1e-300)
