@@ -77,7 +77,7 @@ struct WsLayout {
 // directions of the HBM interface and the tensor pipe are busy at the same time.
 struct TcTune {
     int overlap;        // RBN_TC_OVERLAP   0: one stream; 1: two streams, disjoint SM partitions; 2: two streams, co-resident
-                        //                  'half SM' kernel variants (inside pass)
+                        //                  'half SM' kernel variants (inside pass); 3: two streams, ordinary kernels (tail filling)
     int groups;         // RBN_TC_GROUPS    sequence groups that pipeline against each other (default 2)
     int fwd_sms0;       // RBN_TC_FWD_SMS0  SMs of the split-sum partition in the inside pass (even)
     int bwd_sms0;       // RBN_TC_BWD_SMS0  SMs of the {split-sum, prep, gY} partition in the outside pass (even)

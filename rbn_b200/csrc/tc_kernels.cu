@@ -1308,7 +1308,7 @@ const TcTune& tc_tune() {
     static std::once_flag once;
     std::call_once(once, [] {
         t.overlap = env_int("RBN_TC_OVERLAP", 0);
-        if (t.overlap < 0 || t.overlap > 2) t.overlap = 0;
+        if (t.overlap < 0 || t.overlap > 3) t.overlap = 0;
         t.groups = env_int("RBN_TC_GROUPS", 2);
         t.fwd_sms0 = env_int("RBN_TC_FWD_SMS0", 40) & ~1;
         t.bwd_sms0 = env_int("RBN_TC_BWD_SMS0", 74) & ~1;
@@ -1379,7 +1379,9 @@ struct Sched {
     Sched() : two(false), pair_launch(false), dev(0), err(RBN_OK) { st[0] = st[1] = nullptr; sms[0] = sms[1] = 0; }
 
     // mode 1: disjoint SM partitions (sms0 | rest);  mode 2: both streams use every SM, their kernels are the
-    // 'half SM' variants that leave room for one CTA of the other stream (co-resident schedule)
+    // 'half SM' variants that leave room for one CTA of the other stream (co-resident schedule);  mode 3: both streams
+    // use every SM with the ordinary kernels -- they cannot share an SM, so only the tail of one kernel overlaps the
+    // head of the other stream's next kernel
     int begin(cudaStream_t user, int mode, int sms0) {
         const bool overlap = mode != 0;
         const int total = sm_count();
@@ -1852,7 +1854,8 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     { ProfScope ps(KC_OTHER, st); k_tc_outside_seed<<<B, 128, 0, st>>>(N, L, c.Lp, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior); }
     RBN_LAUNCH_CHECK("k_tc_outside_seed");
 
-    const int mode = (tune.overlap == 1 && ws.nslot >= 2 && B >= 2 * tune.groups) ? 1 : 0;   // co-resident mode: inside pass only (so far)
+    // co-resident mode (2): inside pass only so far
+    const int mode = ((tune.overlap == 1 || tune.overlap == 3) && ws.nslot >= 2 && B >= 2 * tune.groups) ? tune.overlap : 0;
     const bool overlap = mode != 0;
     const int groups = overlap ? tune.groups : 1;
     Sched S;
