@@ -159,10 +159,39 @@ def cpu_sample(wl, seconds_budget=25.0):
     return 1.0 / t_full, t_full, sample, torch.get_num_threads()
 
 
+def run_reference_gauss(args, wl):
+    """--impl reference for configs[3]: the fp64 torch composition of rbnet.multivariate_normal's algebra (oracle/
+    gauss_oracle.py) with autograd as the outside pass, whole sequences of the workload, on the host cores."""
+    import torch
+    from oracle import gauss_oracle as GO
+    D, L = wl["D"], wl["L"]
+    syn = GO.synthetic_gauss(D, 4, L, seed=10)
+    tt = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != "y")) for k, v in syn.items()}
+    times = []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        lz = GO.gauss_inside(tt["y"][s % 4:s % 4 + 1], [L], tt["cov_term"], tt["cov_left"], tt["cov_right"], tt["prior_mean"],
+                             tt["prior_cov"], tt["log_struct"])
+        lz.sum().backward()
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    v = 1.0 / t
+    cores = torch.get_num_threads()
+    sample = f"1 sequence per step, D={D}, L={L}, fp64 torch composition of rbnet.multivariate_normal + autograd"
+    print(json.dumps(dict(metric="inside+gradient sequences/sec", value=v, unit="seq/s", n_gpus=args.gpus, steps=args.steps,
+                          warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                          dtype="f64", data="synthetic", impl="reference", config=dict(workload=wl["name"], D=D, L=L),
+                          cpu_baseline=dict(value=v, unit="seq/s", cores=cores, kind="port", sample=sample),
+                          e2e=dict(value=v, unit="seq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)), flush=True)
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if wl.get("gauss"):
+        return run_reference_gauss(args, wl)
     import torch
     vals = []
     sample, cores = "", torch.get_num_threads()
