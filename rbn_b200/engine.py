@@ -249,6 +249,18 @@ class InsideEngine:
         from . import pcfg
         cells, off, toff = self._structure()
         N = int(off[-1])
+        if len(cells) == 1:
+            # single-cell grammar (AbstractedPCFG and most uses): W and T are plain products, no block assembly
+            trs = list(cells[0].transitions())
+            kinds = [hasattr(t, "term_idx") for t in trs]
+            if len(trs) == 2 and sorted(kinds) == [False, True] and len(toff) == 2:
+                S = cells[0].transition_probabilities.p
+                kt, kb = kinds.index(True), kinds.index(False)
+                Pt, Pb = trs[kt].transition_probabilities.p, trs[kb].transition_probabilities.p
+                if tuple(Pb.shape) == (N, N, N) and Pt.shape[1] == N and int(trs[kb].left_idx) == 0 and int(trs[kb].right_idx) == 0:
+                    omega = self.model.prior.structural_distribution.p
+                    return (S[kb][None, None, :] * Pb, S[kt][None, :] * Pt,
+                            omega[0] * self.model.prior.prior_distributions[0].p)
         ref = self.model.prior.structural_distribution.p
         W = torch.zeros((N, N, N), dtype=ref.dtype, device=ref.device)
         T = torch.zeros((max(int(toff[-1]), 1), N), dtype=ref.dtype, device=ref.device)
