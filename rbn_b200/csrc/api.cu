@@ -113,9 +113,9 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->chunk = (int)chunk;
         const size_t ns = (size_t)(tune.overlap ? tune.nslot : 1);
         o->nslot = (int)ns;
-        // outside charts of the tensor-core path: start-major (left-child sums + root seed) and end-major (right-child sums)
+        // outside chart of the tensor-core path: start-major; the left children of a span are consecutive rows of it, the
+        // right children one column of consecutive row blocks (reached through a 3-D tensor map)
         o->alpha = take(B * L * Lp * N * sizeof(float));
-        o->alpha2 = take(B * (L + 1) * Lp * N * sizeof(float));
         o->lc = take(B * L * Lp * N * sizeof(__half));
         o->rc = take(B * (L + 1) * Lp * N * sizeof(__half));
         o->wt = take(N * N * N * sizeof(__half));

@@ -44,8 +44,7 @@ struct WsLayout {
     size_t chart_val;   // float  [B][C][N]   mantissas, max 1 per cell (power-of-two scaled => exact)
     size_t chart_exp;   // int32  [B][C]      beta = mantissa * 2^exp
     size_t alpha;       // float  scaled outside values (backward only): CUDA-core path [B][C][N]; tensor-core path
-                        //        start-major [B][L][Lp][N] (left-child sums + root seed), cell (i,j) at row (b*L+i)*Lp + j
-    size_t alpha2;      // float  tensor-core path: end-major [B][L+1][Lp][N] (right-child sums), cell (j,k) at row (b*(L+1)+k)*Lp + j
+                        //        start-major [B][L][Lp][N] (root seed + left- and right-child sums), cell (i,j) at row (b*L+i)*Lp + j
     size_t zroot;       // float  [B]
     size_t rootexp;     // int32  [B]
     // tensor-core path

@@ -454,6 +454,10 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t out
 int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                      uint32_t box_inner, uint32_t box_outer);
 
+// 3-D fp32 view [d2][d1][d0] (d0 contiguous), box = {box0, 1, box2}, no swizzle: rows that are a fixed column of
+// consecutive d2 slices (the right children of a span in the start-major outside chart).
+int make_tmap_3d_f32(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box2);
+
 template <bool A_MN, bool B_MN, int BLOCK_N, int STAGES, int SEG, class Epi>
 int launch_tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape shape, const Epi& epi, int num_sms,
                    cudaStream_t st, const char* name, int kclass) {

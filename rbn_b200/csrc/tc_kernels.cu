@@ -83,6 +83,26 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t
     return RBN_OK;
 }
 
+int make_tmap_3d_f32(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box2) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return RBN_E_CUDA;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+    cuuint32_t box[3] = {box0, 1, box2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(3d f32) failed (%d)", (int)r);
+        return RBN_E_CUDA;
+    }
+    return RBN_OK;
+}
+
 // CTA-pair (cta_group::2) GEMMs for the rule contraction and the count GEMM; RBN_TC_1CTA=1 selects the 1-CTA kernels
 static bool use_pairs() {
     static int v = -1;
@@ -506,9 +526,9 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                const __grid_constant__ CUtensorMap tmRC,    // RC rows, box {64, Npad}
                const __grid_constant__ CUtensorMap tmLC,    // LC rows, box {64, Npad}
                int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths,
-               const __grid_constant__ CUtensorMap tmAL,    // alphaL (start-major outside chart, fp32), box {128, 32}
-               const __grid_constant__ CUtensorMap tmAR,    // alphaR (end-major), box {128, 32}
-               const __grid_constant__ CUtensorMap tmALt,   // same charts, box {128, tail_rows}: last chunk of a span's splits
+               const __grid_constant__ CUtensorMap tmAL,    // start-major outside chart (fp32) [rows (b,start,end)][N], box {128, 32}
+               const __grid_constant__ CUtensorMap tmAR,    // the SAME chart as [b*L + start][end][N], box {128, 1, 32}: right children
+               const __grid_constant__ CUtensorMap tmALt,   // same views, tail_rows instead of 32: last chunk of a span's splits
                const __grid_constant__ CUtensorMap tmARt,
                const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp) {
     extern __shared__ uint8_t smem_raw[];
@@ -656,7 +676,6 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
             facb[p] = f_cur;
             ptx::named_bar_sync(2 + grp, 128);
             const int rowL = (int)(((size_t)b * L + i) * Lp + (i + 1));
-            const int rowR = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
             for (int u = grp; u < units; u += 2) {
                 const int kind = u / halves, h = u - kind * halves;
                 const uint32_t slot = (nunit0 + u) & 3, slot_phase = ((nunit0 + u) >> 2) & 1;
@@ -677,8 +696,11 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                     ptx::named_bar_sync(2 + grp, 128);
                     if (issuer) {
                         const bool last = (c0 + 32 >= w - 1);       // the tail box covers only the rows that hold splits
-                        const CUtensorMap* tm = kind ? (last ? &tmARt : &tmAR) : (last ? &tmALt : &tmAL);
-                        ptx::tma_reduce_add_2d(tm, tile, h * 128, (kind ? rowR : rowL) + c0);
+                        // left children (i, j): consecutive rows of start i.  Right children (j, k): row `end = k` of the
+                        // consecutive starts j -- both land in ONE chart, so the two contributions a cell receives per
+                        // diagonal meet in L2 (they are issued within a few microseconds of each other)
+                        if (kind == 0) ptx::tma_reduce_add_2d(last ? &tmALt : &tmAL, tile, h * 128, rowL + c0);
+                        else ptx::tma_reduce_add_3d(last ? &tmARt : &tmAR, tile, h * 128, k, b * L + (i + 1) + c0);
                         ptx::bulk_commit();
                     }
                     ++nred;
@@ -1244,15 +1266,14 @@ __global__ void k_tc_outside_seed(int N, int L, int Lp, const float* __restrict_
 }
 __global__ void k_tc_emission_bwd(int N, int L, int Lp, int nt, const int* __restrict__ tokens,
                                   const int* __restrict__ lengths, const int* __restrict__ ce,
-                                  const float* __restrict__ alphaL, const float* __restrict__ alphaR,
-                                  float* __restrict__ gT) {
+                                  const float* __restrict__ alphaL, float* __restrict__ gT) {
     int b = blockIdx.x / L, i = blockIdx.x % L;
     if (i >= lengths[b]) return;
     size_t cell = (size_t)b * cells_per_seq(L) + i;
-    size_t rl = ((size_t)b * L + i) * Lp + (i + 1), rr = ((size_t)b * (L + 1) + (i + 1)) * Lp + i;
+    size_t rl = ((size_t)b * L + i) * Lp + (i + 1);
     int e = ce[cell];
     for (int a = threadIdx.x; a < N; a += blockDim.x) {
-        float g = ldexpf(alphaL[rl * N + a] + alphaR[rr * N + a], -e);
+        float g = ldexpf(alphaL[rl * N + a], -e);
         if (g == 0.f) continue;
         for (int t = 0; t < nt; ++t) {
             int y = tokens[((size_t)b * L + i) * nt + t];
@@ -1263,7 +1284,7 @@ __global__ void k_tc_emission_bwd(int N, int L, int Lp, int nt, const int* __res
 // upstream gradient of one chunk:  G = alpha * 2^-e_new ;  Ghat = G * 2^wexp[a] normalised per item ; Gabs = G * 2^-8
 __global__ void k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths, const int* __restrict__ ce,
                          const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
-                         const float* __restrict__ alpha2, __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
+                         __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
     __shared__ float red[32];
     const int t = blockIdx.x;
     const int nI = L - w + 1;
@@ -1276,8 +1297,8 @@ __global__ void k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, const int
         const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
         const int e_new = ce[cell] - item_e[t];
         const int k = i + w;
-        const size_t rl = ((size_t)b * L + i) * Lp + k, rr = ((size_t)b * (L + 1) + k) * Lp + i;
-        g = ldexpf(alpha[rl * N + a] + alpha2[rr * N + a], -e_new);
+        const size_t rl = ((size_t)b * L + i) * Lp + k;
+        g = ldexpf(alpha[rl * N + a], -e_new);
         gs = ldexpf(g, wexp[a]);
     }
     float mx = fabsf(gs);
@@ -1328,8 +1349,7 @@ struct TcCtx {
     int N, L, B, Lp, chunk;
     float* cv;
     int* ce;
-    float* alpha;    // left-child contributions (+ root seed)
-    float* alpha2;   // right-child contributions
+    float* alpha;    // start-major outside chart: root seed + left- and right-child contributions
     __half *lc, *rc, *wt, *wk;
     int *wexp, *wbits;
     float* wscale;
@@ -1346,7 +1366,7 @@ struct TcCtx {
 
 static void fill_ctx(TcCtx& c, const RbnDesc* d, const WsLayout& ws, char* base, const int* lengths) {
     c.d = d; c.ws = &ws; c.base = base; c.N = d->N; c.L = d->L; c.B = d->B; c.Lp = ws.Lp; c.chunk = ws.chunk;
-    c.cv = (float*)(base + ws.chart_val); c.ce = (int*)(base + ws.chart_exp); c.alpha = (float*)(base + ws.alpha); c.alpha2 = (float*)(base + ws.alpha2);
+    c.cv = (float*)(base + ws.chart_val); c.ce = (int*)(base + ws.chart_exp); c.alpha = (float*)(base + ws.alpha);
     c.lc = (__half*)(base + ws.lc); c.rc = (__half*)(base + ws.rc); c.wt = (__half*)(base + ws.wt);
     c.wk = (__half*)(base + ws.wk);
     c.wexp = (int*)(base + ws.wexp); c.wbits = (int*)(base + ws.wbits); c.wscale = (float*)(base + ws.wscale);
@@ -1760,11 +1780,11 @@ static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     const uint32_t tail_rows = (uint32_t)(((w - 1) % 32) ? ((w - 1) % 32) : 32);
     rc = make_tmap_2d_f32(&tmAL, c.alpha, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 4, 128, 32);
     if (rc) return rc;
-    rc = make_tmap_2d_f32(&tmAR, c.alpha2, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 4, 128, 32);
+    rc = make_tmap_3d_f32(&tmAR, c.alpha, (uint64_t)N, (uint64_t)c.Lp, (uint64_t)B * L, 128, 32);
     if (rc) return rc;
     rc = make_tmap_2d_f32(&tmALt, c.alpha, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 4, 128, tail_rows);
     if (rc) return rc;
-    rc = make_tmap_2d_f32(&tmARt, c.alpha2, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 4, 128, tail_rows);
+    rc = make_tmap_3d_f32(&tmARt, c.alpha, (uint64_t)N, (uint64_t)c.Lp, (uint64_t)B * L, 128, tail_rows);
     if (rc) return rc;
     size_t smem = (size_t)kK5Stages * kK5StageBytes + 65536 + 256 + 2048 + 1024;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1846,7 +1866,6 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     int N = c.N, L = c.L, B = c.B;
     const TcTune& tune = tc_tune();
     RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha, 0, (size_t)B * L * c.Lp * N * sizeof(float), st));
-    RBN_CUDA_CHECK(cudaMemsetAsync(c.alpha2, 0, (size_t)B * (L + 1) * c.Lp * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gW, 0, (size_t)N * N * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
@@ -1879,7 +1898,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
             if (last_prev[u.g] >= 0) S.wait(0, evK5[last_prev[u.g]]);            // alpha of this diagonal is complete
             int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
             { ProfScope ps(KC_PREP, S.st[0]);
-              k_prep_g<<<pg, N, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, lengths, c.ce, c.item_e(u.slot), c.wexp, c.alpha, c.alpha2,
+              k_prep_g<<<pg, N, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, lengths, c.ce, c.item_e(u.slot), c.wexp, c.alpha,
                                              c.ghat(u.slot), c.gabs(u.slot), c.gexp(u.slot)); }
             RBN_LAUNCH_CHECK("k_prep_g");
             S.wait(1, S.record(0));
@@ -1901,7 +1920,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     int rc2 = S.end();
     if (rc) return rc;
     if (rc2) return rc2;
-    { ProfScope ps(KC_EMISSION, st); k_tc_emission_bwd<<<B * L, 128, 0, st>>>(N, L, c.Lp, d->n_tvars, tokens, lengths, c.ce, c.alpha, c.alpha2, gT); }
+    { ProfScope ps(KC_EMISSION, st); k_tc_emission_bwd<<<B * L, 128, 0, st>>>(N, L, c.Lp, d->n_tvars, tokens, lengths, c.ce, c.alpha, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");
     return RBN_OK;
 }
