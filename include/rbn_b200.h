@@ -122,6 +122,19 @@ int rbn_inside_backward_sorted(const RbnDesc* desc,
                                float* gW, float* gT, float* gPrior,
                                const int32_t* host_active, void* stream);
 
+/* Most probable derivation (max-semiring variant of the inside pass; NOT in the reference -- SURVEY.md 8(f).4).
+ * CUDA-core kernels, any N <= 1024, L <= 2047; workspace = rbn_workspace_bytes() of the same descriptor with
+ * path = RBN_PATH_SIMT.  Outputs (device): logP [B] natural log of the best derivation's probability (-inf: none),
+ * root_symbol [B] its root nonterminal (-1: none), backptr int32 [B][L(L+1)/2][N]: for the cell of span (i, i+w) at
+ * index cell = (w-1)(L+1) - (w-1)w/2 + i and nonterminal a, (u << 20) | (b << 10) | c = best split i+u with left
+ * symbol b and right symbol c, or -1 (width-1 cell / no derivation). */
+int rbn_viterbi(const RbnDesc* desc,
+                const float* W, const float* T, const float* prior,
+                const int32_t* tokens, const int32_t* lengths,
+                void* workspace, size_t workspace_bytes,
+                float* logP, int32_t* backptr, int32_t* root_symbol,
+                void* stream);
+
 /* Chart of one sequence in the reference's layout: rows ordered as triangularmap.TMap orders them (root first:
  * row = d(d+1)/2 + start with d = n - (end - start); pinned by /root/reference/tests/test_pcfg.py:14-19),
  * linear probability space, float64 [n(n+1)/2][N] with n = lengths[seq].  Serves SequentialRBN.inside_chart

@@ -295,3 +295,73 @@ def synthetic_tokens(B, L, V, seed=1, ragged=False):
         for b in range(B):
             tok[b, lengths[b]:] = -1
     return tok, lengths
+
+
+def flat_viterbi(W, T, prior, tokens, lengths=None):
+    """Most probable derivation of every sequence under the flat grammar (max-semiring CYK, log space, float64 numpy).
+
+    Not part of the reference (it has no MAP parse); checker for rbn_viterbi.  Returns (logP [B], trees): a tree is
+    (a, i, k, left_tree, right_tree) for a binary node over span (i, k) or (a, i, i + 1) for a leaf; None when the
+    sequence has no derivation.  The emission of a position is the SUM over its terminal variables, as in the inside
+    pass (pcfg.py:344-352)."""
+    W, T, prior = (np.asarray(x, dtype=np.float64) for x in (W, T, prior))
+    tokens = np.asarray(tokens)
+    if tokens.ndim == 2:
+        tokens = tokens[:, :, None]
+    B, L, nt = tokens.shape
+    lengths = np.full(B, L) if lengths is None else np.asarray(lengths)
+    N = W.shape[0]
+    with np.errstate(divide="ignore"):
+        lW, lp = np.log(W), np.log(prior)
+    out_lp, out_tree = np.full(B, -np.inf), []
+    for b in range(B):
+        n = int(lengths[b])
+        best, back = {}, {}
+        for i in range(n):
+            e = np.zeros(N)
+            for t in range(nt):
+                if tokens[b, i, t] >= 0:
+                    e += T[tokens[b, i, t]]
+            with np.errstate(divide="ignore"):
+                best[i, i + 1] = np.log(e)
+        for w in range(2, n + 1):
+            for i in range(n - w + 1):
+                k = i + w
+                cand = np.full((w - 1, N), -np.inf)
+                arg = np.zeros((w - 1, N), dtype=np.int64)
+                for u in range(1, w):
+                    s = lW + best[i, i + u][:, None, None] + best[i + u, k][None, :, None]      # [b, c, a]
+                    flat = s.reshape(N * N, N)
+                    arg[u - 1] = flat.argmax(0)
+                    cand[u - 1] = flat.max(0)
+                us = cand.argmax(0)
+                best[i, k] = cand.max(0)
+                back[i, k] = [(int(us[a]) + 1, int(arg[us[a], a]) // N, int(arg[us[a], a]) % N) for a in range(N)]
+        root = best[0, n] + lp
+        a0 = int(root.argmax())
+        out_lp[b] = root[a0]
+
+        def build(a, i, k):
+            if k - i == 1:
+                return (a, i, k)
+            u, bl, cr = back[i, k][a]
+            return (a, i, k, build(bl, i, i + u), build(cr, i + u, k))
+        out_tree.append(build(a0, 0, n) if np.isfinite(root[a0]) else None)
+    return out_lp, out_tree
+
+
+def tree_log_prob(tree, W, T, prior, tokens_b):
+    """log probability of one derivation tree (as returned by flat_viterbi / rbn_b200's viterbi) under the flat grammar."""
+    W, T, prior = (np.asarray(x, dtype=np.float64) for x in (W, T, prior))
+    tokens_b = np.asarray(tokens_b)
+    if tokens_b.ndim == 1:
+        tokens_b = tokens_b[:, None]
+
+    def rec(t):
+        if len(t) == 3:
+            a, i, _ = t
+            return np.log(sum(T[y, a] for y in tokens_b[i] if y >= 0))
+        a, _, _, lt, rt = t
+        return np.log(W[lt[0], rt[0], a]) + rec(lt) + rec(rt)
+    with np.errstate(divide="ignore"):
+        return float(np.log(prior[tree[0]]) + rec(tree))

@@ -20,6 +20,8 @@ int simt_forward(const RbnDesc*, const WsLayout&, char*, const float*, const flo
 int simt_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
                   const int*, const float*, float*, float*, float*, const int*, cudaStream_t);
 int export_chart(const RbnDesc*, const WsLayout&, const char*, const int*, int, double*, cudaStream_t);
+int simt_viterbi(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*, const int*,
+                 float*, int*, int*, cudaStream_t);
 int lognormalize(float*, long long, long long, int*, cudaStream_t);
 int tc_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*, const int*,
                float*, float*, float*, const int*, cudaStream_t);
@@ -225,6 +227,25 @@ int rbn_inside_backward(const RbnDesc* desc, const float* W, const float* T, con
                         float* gT, float* gPrior, void* stream) {
     return rbn_inside_backward_sorted(desc, W, T, prior, tokens, lengths, workspace, workspace_bytes, coef, gW, gT, gPrior,
                                       nullptr, stream);
+}
+
+int rbn_viterbi(const RbnDesc* desc, const float* W, const float* T, const float* prior, const int32_t* tokens,
+                const int32_t* lengths, void* workspace, size_t workspace_bytes, float* logP, int32_t* backptr,
+                int32_t* root_symbol, void* stream) {
+    if (!desc_ok(desc)) return RBN_E_BADARG;
+    if (!W || !T || !prior || !tokens || !lengths || !workspace || !logP || !backptr || !root_symbol) {
+        set_error("rbn_viterbi: NULL pointer argument");
+        return RBN_E_BADARG;
+    }
+    RbnDesc d = *desc;
+    d.path = RBN_PATH_SIMT;                       // the max-semiring kernels exist on the CUDA-core path only
+    WsLayout ws;
+    if (!make_layout(&d, &ws)) return RBN_E_UNSUPPORTED;
+    if (workspace_bytes < ws.total || ((uintptr_t)workspace & 1023)) {
+        set_error("workspace too small or misaligned: have %zu need %zu (1024-byte aligned)", workspace_bytes, ws.total);
+        return RBN_E_WORKSPACE;
+    }
+    return simt_viterbi(&d, ws, (char*)workspace, W, T, prior, tokens, lengths, logP, backptr, root_symbol, (cudaStream_t)stream);
 }
 
 int rbn_export_chart(const RbnDesc* desc, const int32_t* lengths, const void* workspace, size_t workspace_bytes,

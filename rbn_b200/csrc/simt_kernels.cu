@@ -205,6 +205,106 @@ __global__ void k_inside_all(int N, int L, int B, int TB, const float* __restric
     }
 }
 
+// ---- Viterbi (max-semiring) variant of the inside pass -------------------------------------------------------------
+// best[i,k,a] = max_{j,b,c} W[b,c,a] best[i,j,b] best[j,k,c]  with the same per-cell power-of-two scaling; the
+// argmax (split, left, right) is packed as (u << 20) | (b << 10) | c into back[cell][a] (-1: no derivation / width 1).
+// Not part of the reference; needs N <= 1024 and L <= 2048 for the packing.
+__global__ void k_viterbi_diag(int N, int L, int w, int TB, const float* __restrict__ W, const int* __restrict__ lengths,
+                               float* __restrict__ cv, int* __restrict__ ce, int* __restrict__ back) {
+    extern __shared__ float sm[];
+    __shared__ float red[32];
+    __shared__ int sE;
+    const int nI = L - w + 1;
+    const int b = blockIdx.x / nI, i = blockIdx.x % nI;
+    if (i + w > lengths[b]) return;
+    const size_t seq = (size_t)b * cells_per_seq(L);
+    const float* cv_seq = cv + seq * N;
+    const int* ce_seq = ce + seq;
+    float* cj = sm;                          // [L+1]
+    float* Y = sm + (L + 1);                 // [TB][N]  max over splits
+    int* Yu = (int*)(Y + (size_t)TB * N);    // [TB][N]  arg max split
+    const int E = split_coefs(L, w, i, ce_seq, cj, &sE);
+
+    float best[kMaxAPerThread];
+    int arg[kMaxAPerThread];
+#pragma unroll
+    for (int q = 0; q < kMaxAPerThread; ++q) { best[q] = 0.f; arg[q] = -1; }
+    for (int b0 = 0; b0 < N; b0 += TB) {
+        const int tb = min(TB, N - b0);
+        for (int idx = threadIdx.x; idx < tb * N; idx += blockDim.x) {
+            const int bb = idx / N, c = idx - bb * N;
+            float m = 0.f;
+            int mu = -1;
+            for (int u = 1; u < w; ++u) {
+                const float* l = cv_seq + (size_t)(cell_off(u, L) + i) * N;
+                const float* r = cv_seq + (size_t)(cell_off(w - u, L) + i + u) * N;
+                const float v = cj[u] * l[b0 + bb] * r[c];
+                if (v > m) { m = v; mu = u; }
+            }
+            Y[idx] = m;
+            Yu[idx] = mu;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kMaxAPerThread; ++q) {
+            const int a = threadIdx.x + q * kThreads;
+            if (a < N) {
+                const float* Wp = W + (size_t)b0 * N * N + a;
+                for (int idx = 0; idx < tb * N; ++idx) {
+                    const float v = Y[idx] * Wp[(size_t)idx * N];
+                    if (v > best[q]) {
+                        best[q] = v;
+                        const int bb = idx / N, c = idx - bb * N;
+                        arg[q] = (Yu[idx] << 20) | ((b0 + bb) << 10) | c;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float mx = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxAPerThread; ++q) mx = fmaxf(mx, best[q]);
+    mx = block_max(mx, red);
+    const int e = norm_exp(mx);
+    const size_t cell = seq + cell_off(w, L) + i;
+#pragma unroll
+    for (int q = 0; q < kMaxAPerThread; ++q) {
+        const int a = threadIdx.x + q * kThreads;
+        if (a < N) {
+            cv[cell * N + a] = ldexpf(best[q], -e);
+            back[cell * N + a] = best[q] > 0.f ? arg[q] : -1;
+        }
+    }
+    if (threadIdx.x == 0) ce[cell] = E + e;
+}
+
+// best root symbol and the natural log of the best derivation's probability (-inf if there is none)
+__global__ void k_viterbi_root(int N, int L, const float* __restrict__ prior, const int* __restrict__ lengths,
+                               const float* __restrict__ cv, const int* __restrict__ ce, float* __restrict__ logP,
+                               int* __restrict__ root_sym) {
+    __shared__ float sv[kThreads];
+    __shared__ int sa[kThreads];
+    const int b = blockIdx.x;
+    const int n = lengths[b];
+    const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(n, L);
+    float m = 0.f;
+    int ma = -1;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        const float v = prior[a] * cv[cell * N + a];
+        if (v > m) { m = v; ma = a; }
+    }
+    sv[threadIdx.x] = m;
+    sa[threadIdx.x] = ma;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < blockDim.x; ++t)
+            if (sv[t] > m || (sv[t] == m && sa[t] >= 0 && (ma < 0 || sa[t] < ma))) { m = sv[t]; ma = sa[t]; }
+        logP[b] = (m > 0.f) ? logf(m) + (float)ce[cell] * 0.69314718055994531f : -INFINITY;
+        root_sym[b] = ma;
+    }
+}
+
 // ---- root / prior -----------------------------------------------------------------------------------------------
 __global__ void k_root(int N, int L, const float* __restrict__ prior, const int* __restrict__ lengths,
                        const float* __restrict__ cv, const int* __restrict__ ce,
@@ -493,6 +593,30 @@ int simt_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float*
     }
     { ProfScope ps(KC_EMISSION, st); k_emission_bwd<<<B * L, 128, 0, st>>>(N, L, d->n_tvars, tokens, lengths, ce, alpha, nullptr, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");
+    return RBN_OK;
+}
+
+int simt_viterbi(const RbnDesc* d, const WsLayout& ws, char* base, const float* W, const float* T, const float* prior,
+                 const int* tokens, const int* lengths, float* logP, int* back, int* root_sym, cudaStream_t st) {
+    if (d->N > 1024 || d->L > 2047) {
+        set_error("viterbi needs N <= 1024 and L <= 2047 (back-pointer packing); got N=%d L=%d", d->N, d->L);
+        return RBN_E_UNSUPPORTED;
+    }
+    float* cv = (float*)(base + ws.chart_val);
+    int* ce = (int*)(base + ws.chart_exp);
+    int N = d->N, L = d->L, B = d->B;
+    RBN_CUDA_CHECK(cudaMemsetAsync(back, 0xff, (size_t)B * cells_per_seq(L) * N * sizeof(int), st));
+    { ProfScope ps(KC_EMISSION, st); k_emission<<<B * L, kThreads, 0, st>>>(N, L, d->n_tvars, T, tokens, lengths, cv, ce); }
+    RBN_LAUNCH_CHECK("k_emission");
+    int TB = pick_tb(N, 2);
+    size_t smem = ((size_t)(L + 1) + 2 * (size_t)TB * N) * sizeof(float);
+    RBN_CUDA_CHECK(cudaFuncSetAttribute(k_viterbi_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int w = 2; w <= L; ++w) {
+        { ProfScope ps(KC_SIMT_INSIDE, st); k_viterbi_diag<<<B * (L - w + 1), kThreads, smem, st>>>(N, L, w, TB, W, lengths, cv, ce, back); }
+        RBN_LAUNCH_CHECK("k_viterbi_diag");
+    }
+    { ProfScope ps(KC_OTHER, st); k_viterbi_root<<<B, kThreads, 0, st>>>(N, L, prior, lengths, cv, ce, logP, root_sym); }
+    RBN_LAUNCH_CHECK("k_viterbi_root");
     return RBN_OK;
 }
 

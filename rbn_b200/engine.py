@@ -191,6 +191,54 @@ def inside_logZ(W, T, prior, tokens, lengths=None, linear=False, path=_lib.PATH_
     return _InsideFn.apply(W, T, prior, tokens, lengths, linear, holder if holder is not None else [], path, chunk_items)
 
 
+def viterbi(W, T, prior, tokens, lengths=None):
+    """Most probable derivation per sequence (max-semiring variant of the inside pass on the CUDA-core kernels; an
+    addition, the reference has no MAP parse).  Returns (logP [B] float64 tensor, trees): a tree is the nested tuple
+    (a, i, k, left, right) / (a, i, i + 1) over FLAT nonterminal indices, None for a sequence without a derivation."""
+    lib = _lib.load()
+    dev = _cuda_device() if not W.is_cuda else W.device
+    tokens = torch.as_tensor(tokens)
+    if tokens.dim() == 2:
+        tokens = tokens[:, :, None]
+    B, L, nt = tokens.shape
+    if lengths is None:
+        lengths = torch.full((B,), L, dtype=torch.int32)
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    Wd, Td, pd = f32(W), f32(T), f32(prior)
+    tok = tokens.to(device=dev, dtype=torch.int32).contiguous()
+    ln = torch.as_tensor(lengths).to(device=dev, dtype=torch.int32).contiguous()
+    N = int(Wd.shape[0])
+    desc = _lib.RbnDesc(N=N, V=int(Td.shape[0]), B=B, L=L, n_tvars=nt, path=_lib.PATH_SIMT, chunk_items=0, flags=0)
+    nbytes = lib.rbn_workspace_bytes(ctypes.byref(desc))
+    if nbytes == 0:
+        _lib.check(-1, "rbn_workspace_bytes")
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 1024
+    C = L * (L + 1) // 2
+    logP = torch.empty(B, dtype=torch.float32, device=dev)
+    back = torch.empty((B, C, N), dtype=torch.int32, device=dev)
+    root = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.rbn_viterbi(ctypes.byref(desc), _ptr(Wd), _ptr(Td), _ptr(pd), _ptr(tok), _ptr(ln),
+                             ctypes.c_void_p(ws.data_ptr() + off), nbytes, _ptr(logP), _ptr(back), _ptr(root),
+                             ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "rbn_viterbi")
+    back_h, root_h, len_h = back.cpu().numpy(), root.cpu().numpy(), ln.cpu().numpy()
+
+    def cell(i, w):
+        return (w - 1) * (L + 1) - ((w - 1) * w) // 2 + i
+
+    def build(b, a, i, k):
+        if k - i == 1:
+            return (a, i, k)
+        p = int(back_h[b, cell(i, k - i), a])
+        u, bl, cr = p >> 20, (p >> 10) & 1023, p & 1023
+        return (a, i, k, build(b, bl, i, i + u), build(b, cr, i + u, k))
+
+    trees = [build(b, int(root_h[b]), 0, int(len_h[b])) if root_h[b] >= 0 else None for b in range(B)]
+    return logP.double(), trees
+
+
 class LazyChart:
     """Stands in for `SequentialRBN._inside_chart` after a fused pass: the per-variable TMap list is exported from
     the device (rbn_export_chart) the first time somebody looks at it (sequential.py:38-40, pcfg.py:30-41)."""
@@ -333,6 +381,22 @@ class InsideEngine:
                           holder=holder)
         self.last_pass = holder[0]
         return out
+
+    def viterbi(self, sequences):
+        """Best derivation of reference-style sequences under the model: (logP [B], trees over (variable, value) symbols)."""
+        tokens, lengths = self.pack_sequences(sequences)
+        with torch.no_grad():
+            W, T, prior = self.flatten()
+        logP, trees = viterbi(W, T, prior, tokens, lengths)
+        _, off, _ = self._structure()
+
+        def name(t):
+            if t is None:
+                return None
+            v = int(np.searchsorted(off, t[0], side="right") - 1)
+            sym = (v, int(t[0] - off[v]))
+            return (sym, t[1], t[2]) if len(t) == 3 else (sym, t[1], t[2], name(t[3]), name(t[4]))
+        return logP, [name(t) for t in trees]
 
     def inside_single(self, sequence):
         """One reference-style sequence -> (Z as 0-dim float64 tensor with grad_fn, LazyChart)."""

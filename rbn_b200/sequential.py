@@ -100,6 +100,12 @@ class SequentialRBN(RBN, torch.nn.Module):
     def log_inside(self, sequence):
         return self.log_inside_batch(sequences=[sequence])[0]
 
+    def viterbi(self, sequences):
+        """Most probable derivation of each sequence (additive API, not in the reference): (log probability [B], trees).
+        A tree is ((variable, value), start, end, left, right) for a binary node and ((variable, value), start, end) for a
+        leaf; None when the sequence has no derivation."""
+        return self._get_engine().viterbi([self._prepare_sequence(s) for s in sequences])
+
 
 class SequentialBinaryTransition(Transition):
 

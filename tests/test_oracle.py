@@ -184,3 +184,32 @@ def test_flat_equals_bricks_longer_sequences():
                                          torch.as_tensor(tok)[:, :, None], return_chart=True)
         assert math.isclose(float(logZ[0]), math.log(Z), rel_tol=1e-12)
         assert _rel(O.chart_to_tmap(vals, logs, 0, L), charts[0]) <= 1e-11
+
+
+def test_viterbi_oracle_equals_brute_force_enumeration():
+    """The numpy max-semiring CYK (checker of rbn_viterbi) against enumeration of every derivation on a tiny grammar."""
+    import numpy as np
+    from oracle import inside_oracle as O
+
+    def all_trees(N, i, k):
+        if k - i == 1:
+            for a in range(N):
+                yield (a, i, k)
+            return
+        for j in range(i + 1, k):
+            for lt in all_trees(N, i, j):
+                for rt in all_trees(N, j, k):
+                    for a in range(N):
+                        yield (a, i, k, lt, rt)
+
+    N, V, L = 2, 3, 4
+    W, T, pr = O.synthetic_grammar(N, V, seed=9)
+    W[0, 1, 0] = 0.0                                    # a zero-probability rule
+    tok = np.array([[2, 0, 1, 1], [1, 1, 0, -1]])
+    lengths = np.array([4, 3])
+    lp, trees = O.flat_viterbi(W, T, pr, tok, lengths)
+    for b in range(2):
+        n = lengths[b]
+        brute = max(O.tree_log_prob(t, W, T, pr, tok[b, :n]) for t in all_trees(N, 0, n))
+        assert abs(lp[b] - brute) < 1e-12
+        assert abs(O.tree_log_prob(trees[b], W, T, pr, tok[b, :n]) - brute) < 1e-12
