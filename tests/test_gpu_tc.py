@@ -167,8 +167,11 @@ def test_n512_count_identities_and_chunk_invariance():
     np.testing.assert_allclose(lz2.cpu().numpy(), lz.detach().cpu().numpy(), rtol=2e-6)
 
 
-def test_two_stream_schedule_matches_oracle():
-    """RBN_TC_OVERLAP=1 (two launch streams, SM partitions, sequence groups, slot ring) in a fresh process."""
+@pytest.mark.parametrize("mode,shape", [("1", (128, 8, 14, 9)), ("2", (128, 8, 14, 9)), ("2", (256, 8, 8, 5)), ("3", (128, 8, 14, 9))])
+def test_two_stream_schedule_matches_oracle(mode, shape):
+    """RBN_TC_OVERLAP = 1 (two launch streams, SM partitions, sequence groups, slot ring), 2 (co-resident half-SM
+    kernels: single-accumulator split-sum, rule GEMM without in-TMEM segmentation) and 3 (tail filling), each in a
+    fresh process (the schedule is read once per process)."""
     import os
     import subprocess
     import sys
@@ -176,7 +179,7 @@ def test_two_stream_schedule_matches_oracle():
 import numpy as np, torch
 from oracle import inside_oracle as O
 from rbn_b200 import inside_logZ, _lib
-N, V, L, B = 128, 8, 14, 9
+N, V, L, B = SHAPE
 W, T, pr = O.synthetic_grammar(N, V, seed=5)
 tok, lengths = O.synthetic_tokens(B, L, V, seed=6, ragged=True)
 Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
@@ -187,11 +190,12 @@ assert np.abs(lz.detach().cpu().numpy() - ref.numpy()).max() <= 1e-4 * np.abs(re
 for a, b in ((Wt.grad, gW), (Tt.grad, gT), (pt.grad, gP)):
     assert float((a.cpu() - b).abs().max() / b.abs().max()) <= 1e-3
 print("two-stream OK")
-"""
-    env = dict(os.environ, RBN_TC_OVERLAP="1", RBN_TC_GROUPS="2", RBN_TC_SLOTS="2")
+""".replace("SHAPE", repr(shape))
+    env = dict(os.environ, RBN_TC_OVERLAP=mode, RBN_TC_GROUPS="2", RBN_TC_SLOTS="2")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and "two-stream OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
 
 
 def test_full_size_config2_shape_inside_only():
