@@ -233,8 +233,7 @@ def run_ours(args, wl):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from oracle import inside_oracle as O     # synthetic workload generator only (shared with the tests)
-    from rbn_b200 import _lib, inside_logZ
+    from rbn_b200 import _lib, inside_logZ, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,8 +245,8 @@ def run_ours(args, wl):
     _lib.load()
 
     N, V, L, B = wl["N"], wl["V"], wl["L"], args.batch or wl["B"]
-    W, T, pr = O.synthetic_grammar(N, V, seed=0)
-    tok_np, len_np = O.synthetic_tokens(B, L, V, seed=1 + rank)
+    W, T, pr = synth.synthetic_grammar(N, V, seed=0)
+    tok_np, len_np = synth.synthetic_tokens(B, L, V, seed=1 + rank)
     Wd = torch.tensor(W, dtype=torch.float32, device=dev, requires_grad=wl["outside"])
     Td = torch.tensor(T, dtype=torch.float32, device=dev, requires_grad=wl["outside"])
     pd = torch.tensor(pr, dtype=torch.float32, device=dev, requires_grad=wl["outside"])
@@ -439,7 +438,7 @@ def run_gauss(args, wl):
     read-modify-writes of the same cells (3x)."""
     import numpy as np
     import torch
-    from oracle import gauss_oracle as GO      # synthetic workload generator + the cpu_baseline leg only
+    from rbn_b200 import synth
     from rbn_b200 import _lib
     from rbn_b200.gaussian import GaussianRBN
     rank = int(os.environ.get("RANK", "0"))
@@ -452,7 +451,7 @@ def run_gauss(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     D, L, B = wl["D"], wl["L"], args.batch or wl["B"]
-    syn = GO.synthetic_gauss(D, B, L, seed=10 + rank)
+    syn = synth.synthetic_gauss(D, B, L, seed=10 + rank)
     y_np = syn["y"]
     model = GaussianRBN(D, cov_term=syn["cov_term"], cov_left=syn["cov_left"], cov_right=syn["cov_right"],
                         prior_mean=syn["prior_mean"], prior_cov=syn["prior_cov"], struct_weights=(0.4, 0.6)).to(dev)
@@ -507,6 +506,7 @@ def run_gauss(args, wl):
     ach = alg_bytes * args.steps / (diag_ms * 1e-3) / 1e9 if diag_ms > 0 else None
     cpu = None
     if world == 1 and not args.skip_cpu:
+        from oracle import gauss_oracle as GO      # cpu_baseline leg only
         t0 = time.perf_counter()
         n_cpu = 0
         tt = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != "y")) for k, v in syn.items()}

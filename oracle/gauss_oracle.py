@@ -83,16 +83,4 @@ def gauss_inside(y, lengths, cov_term, cov_left, cov_right, prior_mean, prior_co
     return torch.stack(out)
 
 
-def synthetic_gauss(D, B, L, seed=0):
-    """y = cumulative-sum random walk of N(0, I) steps; every covariance is
-    A A^T + 0.1 I with A ~ U(-1, 1)^{DxD} (the recipe of /root/reference/tests/test_multivariate_normal.py:89-91)."""
-    import numpy as np
-    rng = np.random.default_rng(seed)
-
-    def spd():
-        a = rng.uniform(-1, 1, (D, D))
-        return a @ a.T + 0.1 * np.eye(D)
-
-    y = np.cumsum(rng.standard_normal((B, L, D)), axis=1)
-    return dict(y=y, cov_term=spd(), cov_left=spd(), cov_right=spd(), prior_mean=rng.standard_normal(D),
-                prior_cov=spd(), log_struct=np.log(np.array([0.4, 0.6])))
+from rbn_b200.synth import synthetic_gauss  # noqa: E402,F401  (one generator for tests, oracle and bench)

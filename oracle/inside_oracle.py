@@ -270,31 +270,7 @@ def chart_to_tmap(vals, logs, b, n):
 # synthetic workloads -- shared by tests and bench so every leg sees the same inputs
 # --------------------------------------------------------------------------------------------------------------
 
-def synthetic_grammar(N, V, seed=0):
-    """Random dense grammar normalised the reference's way: W over (left,right) per parent (pcfg.py:299), T over
-    terminals per parent (pcfg.py:339), structural [terminal, binary] over transitions (pcfg.py:373), prior
-    over symbols; returned FLAT (S folded in) as float64 numpy: W[N,N,N], T[V,N], prior[N]."""
-    rng = np.random.default_rng(seed)
-    W = rng.random((N, N, N))
-    T = rng.random((V, N))
-    S = rng.random((2, N))
-    pi = rng.random(N)
-    W /= W.sum(axis=(0, 1), keepdims=True)
-    T /= T.sum(axis=0, keepdims=True)
-    S /= S.sum(axis=0, keepdims=True)
-    pi /= pi.sum()
-    return W * S[1][None, None, :], T * S[0][None, :], pi
-
-
-def synthetic_tokens(B, L, V, seed=1, ragged=False):
-    rng = np.random.default_rng(seed)
-    tok = rng.integers(0, V, (B, L)).astype(np.int64)
-    lengths = np.full((B,), L, dtype=np.int64)
-    if ragged:
-        lengths = rng.integers(max(L // 2, 1), L + 1, B).astype(np.int64)
-        for b in range(B):
-            tok[b, lengths[b]:] = -1
-    return tok, lengths
+from rbn_b200.synth import synthetic_grammar, synthetic_tokens  # noqa: E402,F401  (one generator for tests, oracle and bench)
 
 
 def flat_viterbi(W, T, prior, tokens, lengths=None):
