@@ -45,7 +45,7 @@ extern "C" {
 #define RBN_E_UNSUPPORTED -4  /* shape outside what the selected path supports */
 
 /* RbnDesc.path */
-#define RBN_PATH_AUTO     0   /* tensor-core path when N % 64 == 0 and 64 <= N <= 256, else the shared-memory path */
+#define RBN_PATH_AUTO     0   /* tensor-core path when N is 64, 128, 192, 256 or 512 (and L >= 2), else the shared-memory path */
 #define RBN_PATH_SIMT     1   /* shared-memory / CUDA-core path, fp32 end to end (small nonterminal counts) */
 #define RBN_PATH_TCGEN05  2   /* span-diagonal tcgen05 tensor-core path (fp16 operands, fp32 accumulate) */
 
