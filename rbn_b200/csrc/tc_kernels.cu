@@ -235,6 +235,7 @@ struct EpiGY {
 
 // K4: gW[(b,c)][a] += D * 2^kGabsShift
 static constexpr int kGabsShift = 8;
+static constexpr int kK2Stages = 7;      // TMA ring of the CTA-pair rule / count GEMMs: 7 x 32 KB is what fits (more bytes in flight)
 static constexpr int kSegBlocks = 64;   // k-blocks (of 64) per accumulation segment: K chain of 4096 -> bias ~2e-5
 struct EpiCounts {
     static constexpr int kSmem = 0;
@@ -867,7 +868,8 @@ k_tc_gy(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box 
 // K3, CTA-pair variant (cta_group::2): the pair keeps the gradient rows of 256 spans resident (128 per CTA) and every
 // CTA stages only HALF of each 256-row Wk tile, which halves both the TMA fill and the MMA operand reads per SM --
 // the 1-CTA kernel above is shared-memory-bandwidth bound (~250 B/cycle needed, 128 available).
-template <int NBUF>      // staging tiles per epilogue group (2; 1 when N = 512 leaves no room)
+template <int NBUF, int STG>      // staging tiles per epilogue group and Wk ring stages: whatever fits beside the resident
+                                  // gradient rows (N <= 256: 2 and 6, N = 512: 1 and 4)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box {64, 128}
          const __grid_constant__ CUtensorMap tmW,     // Wk [N*N rows][N], box {64, 128}
@@ -880,10 +882,10 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
     const int ntiles_per_range = ntiles_total / ranges;
     uint8_t* sAres = smem;                                        // [kblocks] x 16 KB (this CTA's 128 rows)
     uint8_t* sBring = sAres + (size_t)kblocks * 16384;            // [stages] x 16 KB (this CTA's half of a Wk tile)
-    uint8_t* ebuf = sBring + kGYStages * 16384;                   // [2 groups][NBUF] x 16 KB staging tiles
+    uint8_t* ebuf = sBring + STG * 16384;                   // [2 groups][NBUF] x 16 KB staging tiles
     uint64_t* full = (uint64_t*)(ebuf + 2 * NBUF * 16384);
-    uint64_t* empty = full + kGYStages;
-    uint64_t* tfull = empty + kGYStages;      // [2]
+    uint64_t* empty = full + STG;
+    uint64_t* tfull = empty + STG;      // [2]
     uint64_t* tempty = tfull + 2;             // [2]
     uint64_t* a_full = tempty + 2;
     uint64_t* a_empty = a_full + 1;
@@ -893,7 +895,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
     const bool leader = (rank == 0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGYStages; ++s) {
+        for (int s = 0; s < STG; ++s) {
             ptx::mbar_init(&full[s], 1);
             ptx::mbar_init(&empty[s], 1);
         }
@@ -933,7 +935,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
                         ptx::mbar_wait(&empty[stage], phase ^ 1);
                         if (leader) ptx::mbar_expect_tx(&full[stage], 2 * 16384);
                         ptx::tma_load_2d_pair(sBring + stage * 16384, &tmW, &full[stage], kb * 64, nt * 256 + (int)rank * 128);
-                        if (++stage == kGYStages) { stage = 0; phase ^= 1; }
+                        if (++stage == STG) { stage = 0; phase ^= 1; }
                     }
             }
         }
@@ -962,7 +964,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
                             ptx::mma_f16_ss_pair(tmem_base + buf * 256, ptx::make_smem_desc(sA + k * 32, 16, 1024),
                                                  ptx::make_smem_desc(sB + k * 32, 16, 1024), idesc, (uint32_t)((kb | k) != 0));
                         ptx::mma_commit_pair(&empty[stage]);
-                        if (++stage == kGYStages) { stage = 0; phase ^= 1; }
+                        if (++stage == STG) { stage = 0; phase ^= 1; }
                     }
                     ptx::mma_commit_pair(&tfull[buf]);
                     if (++buf == 2) { buf = 0; bphase ^= 1; }
@@ -1634,7 +1636,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             shape2.all_partial = 1;
             if (splits > 1) { shape2.full_tiles = full; shape2.tail_splits = splits; }
             RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot), 0, (size_t)cnt * c.N * sizeof(float), st));
-            rc = launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
+            rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
               k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
@@ -1646,14 +1648,14 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             shape2.tail_splits = splits;
             const int t_begin = full * 256;
             RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot) + (size_t)t_begin * c.N, 0, (size_t)(cnt - t_begin) * c.N * sizeof(float), st));
-            rc = launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
+            rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
               k_rule_finalize<<<cnt - t_begin, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
-        return launch_tc_gemm2<false, false, BN, 6, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
+        return launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
     }
     GemmShape shape{(cnt + 127) / 128, 1, (int)(NN / 64), 0, 1, 0};
     return launch_tc_gemm<false, false, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiRule>(tmA, tmB, shape, epi, sms, st, "k_tc_gemm<rule>", KC_RULE);
@@ -1698,9 +1700,12 @@ static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
         int ntiles2 = (int)(NN / 256), pairs = sms / 2;
         int ranges2 = 1;
         while (ranges2 < 16 && supertiles * ranges2 < 2 * pairs && ntiles2 % (ranges2 * 2) == 0 && ntiles2 / (ranges2 * 2) >= 8) ranges2 *= 2;
-        const int nbuf = c.N > 256 ? 1 : 2;
-        size_t smem2 = (size_t)(c.N / 64) * 16384 + kGYStages * 16384 + (size_t)2 * nbuf * 16384 + 256 + 1024;
-        auto kern = nbuf == 2 ? k_tc_gy2<2> : k_tc_gy2<1>;
+        static const int deep = env_int("RBN_TC_GY_STAGES", 6);       // N <= 256: 6 ring stages (4: the former setting)
+        const bool big = c.N > 256;
+        const int nbuf = big ? 1 : 2;
+        const int stg = big ? 4 : (deep >= 6 ? 6 : 4);
+        size_t smem2 = (size_t)(c.N / 64) * 16384 + (size_t)stg * 16384 + (size_t)2 * nbuf * 16384 + 256 + 1024;
+        auto kern = big ? k_tc_gy2<1, 4> : (stg == 6 ? k_tc_gy2<2, 6> : k_tc_gy2<2, 4>);
         RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         int units2 = supertiles * ranges2;
         int np = units2 < pairs ? units2 : pairs;
@@ -1749,7 +1754,7 @@ static int launch_k4_bn(TcCtx& c, const Unit& u, float* gW, cudaStream_t st, int
             }
             shape2.tail_splits = best;
         }
-        return launch_tc_gemm2<true, true, (BN % 128 == 0 ? BN : 128), 6, kSegBlocks, EpiCounts>(tmA, tmB, shape2, epi, sms, st, "k_tc_gemm2<counts>", KC_COUNTS);
+        return launch_tc_gemm2<true, true, (BN % 128 == 0 ? BN : 128), kK2Stages, kSegBlocks, EpiCounts>(tmA, tmB, shape2, epi, sms, st, "k_tc_gemm2<counts>", KC_COUNTS);
     }
     GemmShape shape{(int)(NN / 128), 1, (cnt + 63) / 64, 0, 1, 0};
     return launch_tc_gemm<true, true, BN, (BN > 128 ? 4 : 6), kSegBlocks, EpiCounts>(tmA, tmB, shape, epi, sms, st, "k_tc_gemm<counts>", KC_COUNTS);
