@@ -1284,38 +1284,53 @@ __global__ void k_tc_emission_bwd(int N, int L, int Lp, int nt, const int* __res
     }
 }
 // upstream gradient of one chunk:  G = alpha * 2^-e_new ;  Ghat = G * 2^wexp[a] normalised per item ; Gabs = G * 2^-8
-__global__ void k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, const int* __restrict__ lengths, const int* __restrict__ ce,
-                         const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
-                         __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
-    __shared__ float red[32];
-    const int t = blockIdx.x;
+// One WARP per span (8 spans per CTA), N / 32 values per lane: no block-level synchronisation, an eighth of the CTAs.
+static constexpr int kPrepWarps = 8;
+__global__ void __launch_bounds__(kPrepWarps * 32)
+k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, const int* __restrict__ lengths, const int* __restrict__ ce,
+         const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
+         __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);
+    if (t >= rows) return;                          // rows = cnt rounded up to 64: the pad rows are written as zeros
     const int nI = L - w + 1;
     const int m = m0 + t;
     const int b = m / nI, i = m - b * nI;
-    const bool valid = (t < cnt) && (i + w <= lengths[b]);
-    float g = 0.f, gs = 0.f;
-    const int a = threadIdx.x;     // blockDim.x == N (<= 256)
+    const bool valid = (t < cnt) && (i + w <= lengths[t < cnt ? b : 0]);
+    constexpr int kMaxPerLane = 16;                 // N <= 512
+    float g[kMaxPerLane], gs[kMaxPerLane];
+    float mx = 0.f;
+    const int per = N >> 5;
     if (valid) {
         const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
         const int e_new = ce[cell] - item_e[t];
-        const int k = i + w;
-        const size_t rl = ((size_t)b * L + i) * Lp + k;
-        g = ldexpf(alpha[rl * N + a], -e_new);
-        gs = ldexpf(g, wexp[a]);
+        const float* row = alpha + (((size_t)b * L + i) * Lp + (i + w)) * N;
+#pragma unroll
+        for (int q = 0; q < kMaxPerLane; ++q) {
+            if (q < per) {
+                const int a = q * 32 + lane;
+                g[q] = ldexpf(row[a], -e_new);
+                gs[q] = ldexpf(g[q], wexp[a]);
+                mx = fmaxf(mx, fabsf(gs[q]));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < kMaxPerLane; ++q) g[q] = gs[q] = 0.f;
     }
-    float mx = fabsf(gs);
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = red[0];
-    for (int q = 1; q < (blockDim.x >> 5); ++q) mx = fmaxf(mx, red[q]);
     int eg = 0;
     if (mx > 0.f) frexpf(mx, &eg);
-    ghat[(size_t)t * N + a] = __float2half_rn(ldexpf(gs, -eg));
-    float ga = ldexpf(g, -kGabsShift);
-    ga = fminf(fmaxf(ga, -65504.f), 65504.f);
-    gabs[(size_t)t * N + a] = __float2half_rn(ga);
-    if (a == 0) gexp[t] = eg;
+#pragma unroll
+    for (int q = 0; q < kMaxPerLane; ++q) {
+        if (q < per) {
+            const int a = q * 32 + lane;
+            ghat[(size_t)t * N + a] = __float2half_rn(ldexpf(gs[q], -eg));
+            const float ga = fminf(fmaxf(ldexpf(g[q], -kGabsShift), -65504.f), 65504.f);
+            gabs[(size_t)t * N + a] = __float2half_rn(ga);
+        }
+    }
+    if (lane == 0) gexp[t] = eg;
 }
 
 // =======================================================================================================================
@@ -1903,7 +1918,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
             if (last_prev[u.g] >= 0) S.wait(0, evK5[last_prev[u.g]]);            // alpha of this diagonal is complete
             int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
             { ProfScope ps(KC_PREP, S.st[0]);
-              k_prep_g<<<pg, N, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, lengths, c.ce, c.item_e(u.slot), c.wexp, c.alpha,
+              k_prep_g<<<(pg + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, pg, lengths, c.ce, c.item_e(u.slot), c.wexp, c.alpha,
                                              c.ghat(u.slot), c.gabs(u.slot), c.gexp(u.slot)); }
             RBN_LAUNCH_CHECK("k_prep_g");
             S.wait(1, S.record(0));
