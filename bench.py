@@ -29,7 +29,9 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (N, V, L, B per GPU, with outside pass)
-    "c3": dict(N=256, V=32, L=128, B=512, outside=True,
+    # batch 512 per GPU, run as micro-batches of 128: the split-sums of 128 sequences (136 GB of fp16 N x N blocks) fit
+    # HBM beside the charts, so the outside pass reads them back instead of recomputing them
+    "c3": dict(N=256, V=32, L=128, B=512, micro=128, outside=True,
                name="PCFG N=256 L=128 batch 512/GPU inside+outside (BASELINE configs[2])"),
     "c2": dict(N=64, V=32, L=64, B=1024, outside=False,
                name="discrete RBN N=64 L=64 batch 1024/GPU inside only (BASELINE configs[1])"),
@@ -121,6 +123,56 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
+CPU_SAMPLE_OUT = {}        # inputs / outputs of the last cpu_sample() run: the bench's parity check reuses them
+
+
+def _err_metrics(d, ref, floor=1e-4):
+    import numpy as np
+    d, ref = np.asarray(d, dtype=np.float64).ravel(), np.asarray(ref, dtype=np.float64).ravel()
+    mx = max(float(np.abs(ref).max()), 1e-300)
+    big = np.abs(ref) >= floor * mx
+    return (float(np.abs(d - ref).max() / mx), float(np.linalg.norm(d - ref) / max(float(np.linalg.norm(ref)), 1e-300)),
+            float((np.abs(d - ref)[big] / np.abs(ref)[big]).max()))
+
+
+def parity_check(wl, batch_logz0=None):
+    """The CUDA path on exactly the sample the cpu_baseline leg just ran through the oracle (sequence 0 of the benched
+    batch): log Z and, entry by entry, the gradients (max-norm, relative L2, per-entry relative above 1e-4 of the max)."""
+    import numpy as np
+    import torch
+    from rbn_b200 import inside_logZ
+    if not CPU_SAMPLE_OUT:
+        return None
+    W, T, pr, tok, le = CPU_SAMPLE_OUT["inputs"]
+    out = CPU_SAMPLE_OUT["outputs"]
+    Wt, Tt, pt = (torch.tensor(x, dtype=torch.float32, device="cuda", requires_grad=wl["outside"]) for x in (W, T, pr))
+    lz = inside_logZ(Wt, Tt, pt, torch.as_tensor(tok), torch.as_tensor(le))
+    res = dict(sample="sequence 0 of the benched batch through the CUDA path (batch of 1) vs the fp64 oracle run of cpu_baseline")
+    if wl["outside"]:
+        lz.sum().backward()
+        lz_ref, gW, gT, gP = (x.numpy() for x in out)
+        errs = [_err_metrics(a.grad.cpu().numpy(), b) for a, b in ((Wt, gW), (Tt, gT), (pt, gP))]
+        res.update(grad_max_rel=max(e[0] for e in errs), grad_l2_rel=max(e[1] for e in errs),
+                   grad_entry_rel=max(e[2] for e in errs), entry_floor="entries >= 1e-4 * max|ref|")
+    else:
+        lz_ref = out.detach().numpy()
+    lzv = lz.detach().double().cpu().numpy()
+    res["logZ_rel"] = float(np.max(np.abs(lzv - lz_ref) / np.abs(lz_ref)))
+    if batch_logz0 is not None and tok.shape[1] == wl["L"]:
+        res["logZ_rel_in_batch"] = float(abs(batch_logz0 - lz_ref[0]) / abs(lz_ref[0]))   # same sequence inside the benched batch
+    res["tolerance"] = "logZ 1e-4, gradients 1e-3 (north_star)"
+    res["ok"] = bool(res["logZ_rel"] <= 1e-4 and res.get("grad_max_rel", 0) <= 1e-3 and res.get("grad_l2_rel", 0) <= 1e-3)
+    return res
+
+
+def workload_config(wl, B, world):
+    """The `config` object of the JSON line: the workload only, identical for this repo's arm and the reference arm."""
+    if wl.get("gauss"):
+        return dict(workload=wl["name"], D=wl["D"], L=wl["L"], batch_per_gpu=B, global_batch=world * B, parallelism=f"dp{world}")
+    return dict(workload=wl["name"], N=wl["N"], V=wl["V"], L=wl["L"], batch_per_gpu=B, global_batch=world * B,
+                parallelism=f"dp{world}")
+
+
 def cpu_sample(wl, seconds_budget=25.0):
     """Time the fp64 oracle (oracle/inside_oracle.py, a restatement of rbnet's inside pass + autograd outside) on a
     bounded sample of the workload: whole sequences of the workload's N, with the length truncated so that one
@@ -136,7 +188,7 @@ def cpu_sample(wl, seconds_budget=25.0):
     t0 = time.perf_counter()
     run = (lambda tk, ln: O.flat_inside_with_grads(W, T, pr, tk[:, :, None], ln)) if wl["outside"] else \
           (lambda tk, ln: O.flat_inside(torch.as_tensor(W), torch.as_tensor(T), torch.as_tensor(pr), torch.as_tensor(tk)[:, :, None], ln))
-    run(tok, le)
+    out = run(tok, le)
     t_probe = time.perf_counter() - t0
     f_probe = flops_per_sequence(N, Lp, wl["outside"])[0]
     Ls = Lp
@@ -147,15 +199,17 @@ def cpu_sample(wl, seconds_budget=25.0):
     if Ls != Lp:
         tok, le = O.synthetic_tokens(1, Ls, V, seed=1)
         t0 = time.perf_counter()
-        run(tok, le)
+        out = run(tok, le)
         t_s = time.perf_counter() - t0
     else:
         t_s = t_probe
     scale = flops_per_sequence(N, L, wl["outside"])[0] / flops_per_sequence(N, Ls, wl["outside"])[0]
     t_full = t_s * scale
-    sample = (f"1 sequence, N={N}, L={Ls}" + ("" if Ls == L else f" (of {L}; time scaled x{scale:.2f} by algorithmic FLOPs)")
-              + f", fp64 torch restatement of rbnet inside{'+autograd outside' if wl['outside'] else ''}, "
+    sample = (f"1 sequence (sequence 0 of the benched batch" + ("" if Ls == L else f", first {Ls} of {L} tokens; time scaled x{scale:.2f} by algorithmic FLOPs")
+              + f"), N={N}, L={Ls}, fp64 torch restatement of rbnet inside{'+autograd outside' if wl['outside'] else ''}, "
               f"{t_s:.2f}s measured")
+    CPU_SAMPLE_OUT.clear()
+    CPU_SAMPLE_OUT.update(inputs=(W, T, pr, tok, le), outputs=out)
     return 1.0 / t_full, t_full, sample, torch.get_num_threads()
 
 
@@ -164,6 +218,7 @@ def run_reference_gauss(args, wl):
     gauss_oracle.py) with autograd as the outside pass, whole sequences of the workload, on the host cores."""
     import torch
     from oracle import gauss_oracle as GO
+    torch.set_num_threads(os.cpu_count() or 1)
     D, L = wl["D"], wl["L"]
     syn = GO.synthetic_gauss(D, 4, L, seed=10)
     tt = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != "y")) for k, v in syn.items()}
@@ -181,7 +236,8 @@ def run_reference_gauss(args, wl):
     sample = f"1 sequence per step, D={D}, L={L}, fp64 torch composition of rbnet.multivariate_normal + autograd"
     print(json.dumps(dict(metric="inside+gradient sequences/sec", value=v, unit="seq/s", n_gpus=args.gpus, steps=args.steps,
                           warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                          dtype="f64", data="synthetic", impl="reference", config=dict(workload=wl["name"], D=D, L=L),
+                          dtype="f64", data="synthetic", impl="reference",
+                          config=workload_config(wl, args.batch or wl["B"], int(os.environ.get("WORLD_SIZE", "1"))),
                           cpu_baseline=dict(value=v, unit="seq/s", cores=cores, kind="port", sample=sample),
                           e2e=dict(value=v, unit="seq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)), flush=True)
 
@@ -193,20 +249,19 @@ def run_reference(args, wl):
     if wl.get("gauss"):
         return run_reference_gauss(args, wl)
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: use the box's cores anyway
     vals = []
     sample, cores = "", torch.get_num_threads()
     for s in range(args.warmup + args.steps):
         v, t_full, sample, cores = cpu_sample(wl, seconds_budget=20.0)
         if s >= args.warmup:
             vals.append((v, t_full))
-        if s == 0 and args.warmup > 0 and t_full > 0:
-            pass
     v = sum(x[0] for x in vals) / len(vals)
     t = sum(x[1] for x in vals) / len(vals)
     line = dict(metric="inside+outside sequences/sec" if wl["outside"] else "inside sequences/sec", value=v,
                 unit="seq/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                impl="reference", config=dict(workload=wl["name"], N=wl["N"], V=wl["V"], L=wl["L"]),
+                impl="reference", config=workload_config(wl, args.batch or wl["B"], int(os.environ.get("WORLD_SIZE", "1"))),
                 cpu_baseline=dict(value=v, unit="seq/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit="seq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
                 note="the reference (pure Python rbnet) cannot travel to the GPU box; this arm times oracle/ (its "
@@ -229,22 +284,27 @@ def build_model(N, V, seed, device):
     return sequential.SequentialRBN(cells=[cell], prior=prior).to(device)
 
 
-def run_ours(args, wl):
+def run_ours(args, wl, secondary=False):
+    """This repo's arm.  `secondary`: called a second time inside a multi-GPU run for the C5 line (bounded steps; the
+    process group already exists); returns the line instead of printing it."""
+    import gc
     import numpy as np
     import torch
     import torch.distributed as dist
     from rbn_b200 import _lib, inside_logZ, synth
+    from rbn_b200.distributed import CountReducer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    steps, warmup = (min(args.steps, 2), min(args.warmup, 1)) if secondary else (args.steps, args.warmup)
 
-    N, V, L, B = wl["N"], wl["V"], wl["L"], args.batch or wl["B"]
+    N, V, L, B = wl["N"], wl["V"], wl["L"], (wl["B"] if secondary else (args.batch or wl["B"]))
     W, T, pr = synth.synthetic_grammar(N, V, seed=0)
     tok_np, len_np = synth.synthetic_tokens(B, L, V, seed=1 + rank)
     Wd = torch.tensor(W, dtype=torch.float32, device=dev, requires_grad=wl["outside"])
@@ -252,63 +312,63 @@ def run_ours(args, wl):
     pd = torch.tensor(pr, dtype=torch.float32, device=dev, requires_grad=wl["outside"])
     tok_d = torch.tensor(tok_np, dtype=torch.int32, device=dev)
     len_d = torch.tensor(len_np, dtype=torch.int32, device=dev)
+    len_h = torch.tensor(len_np, dtype=torch.int32)           # host copy of the lengths: the pass then never synchronises
 
-    from rbn_b200.distributed import allreduce_counts
-
-    def allreduce_grads(tensors):
-        if world > 1:
-            allreduce_counts(tensors)
-
-    micro = min(B, wl.get("micro", B))
+    micro = min(B, args.micro or wl.get("micro", B))
 
     def device_step():
-        if wl["outside"]:
-            for t in (Wd, Td, pd):
-                t.grad = None
+        """One pass of the hot path over the batch, inputs resident in HBM.  Micro-batches run inside + outside back to
+        back (the second pass reuses the first one's workspace); every micro-batch's count tensors go into an
+        asynchronous all-reduce that overlaps the next micro-batch (N > 1), and are summed at the end of the step."""
+        red = CountReducer()
         outs = []
-        for b0 in range(0, B, micro):       # micro-batches share the workspace; their counts accumulate in .grad
-            lz = inside_logZ(Wd, Td, pd, tok_d[b0:b0 + micro], len_d[b0:b0 + micro], chunk_items=args.chunk)
+        for b0 in range(0, B, micro):
+            lz = inside_logZ(Wd, Td, pd, tok_d[b0:b0 + micro], len_h[b0:b0 + micro], chunk_items=args.chunk)
             if wl["outside"]:
-                lz.sum().backward()
+                red.add(torch.autograd.grad(lz.sum(), (Wd, Td, pd)))
             outs.append(lz.detach())
-        if wl["outside"]:
-            allreduce_grads([Wd.grad, Td.grad, pd.grad])
-        return outs[0] if len(outs) == 1 else torch.cat(outs)
+            del lz                           # drops the pass (its workspace goes back to the allocator for the next one)
+        grads = red.result() if wl["outside"] else None
+        return (outs[0] if len(outs) == 1 else torch.cat(outs)), grads
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, nsteps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = None
-        for _ in range(steps):
+        for _ in range(nsteps):
             out = fn()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) / steps, out
+        return float(ms) / nsteps, out
 
     # ---- device-resident arm -------------------------------------------------------------------------------------------
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         device_step()
     _lib.profile_read(reset=True)
     _lib.profile_enable(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_step, lz = timed(device_step, args.steps)
+    ms_step, (lz, grads) = timed(device_step, steps)
     clocks = sampler.stop() if rank == 0 else None
     prof = _lib.profile_read(reset=True)
     _lib.profile_enable(False)
     lz_host = lz.detach().double().cpu().numpy()
-    del lz                                   # releases the last pass's workspace (88 GB at N = 512) before the e2e arm
-    import gc
+    count_check = None
+    if grads is not None:
+        # expected-count identity over the whole job: sum_{bca} gW * W = number of binary rule applications = sum (len - 1)
+        count_check = dict(binary_rules=float((grads[0].double() * Wd.detach().double()).sum()),
+                           expected=float(world * (len_np - 1).sum()))
+    del lz, grads
     gc.collect()
     torch.cuda.empty_cache()
 
@@ -319,115 +379,143 @@ def run_ours(args, wl):
     params = [p for p in model.parameters()]
 
     def e2e_step():
-        tk = tok_pin.to(dev, non_blocking=True)
-        ln = len_pin.to(dev, non_blocking=True)
+        """The call a user makes: SequentialRBN.log_inside_batch on a pinned host batch (the library copies it to the device,
+        asynchronously), loss.backward() through the Parameters, gradients all-reduced, the loss read back to the host."""
         if wl["outside"]:
             for p in params:
                 p.grad = None
         total = None
         for b0 in range(0, B, micro):
-            lz = model.log_inside_batch(tokens=tk[b0:b0 + micro], lengths=ln[b0:b0 + micro])
+            lz = model.log_inside_batch(tokens=tok_pin[b0:b0 + micro], lengths=len_pin[b0:b0 + micro])
             loss = -lz.sum()
             if wl["outside"]:
                 loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
-        if wl["outside"]:
-            allreduce_grads([p.grad for p in params])
+            del lz, loss
+        if wl["outside"] and world > 1:
+            from rbn_b200.distributed import allreduce_counts
+            allreduce_counts([p.grad for p in params])
         return float(total)         # device -> host read of the step's result
 
     if args.skip_e2e:
         ms_e2e = float('nan')
     else:
-        for _ in range(min(args.warmup, 2)):
+        for _ in range(min(warmup, 2)):
             e2e_step()
-        ms_e2e, _ = timed(e2e_step, args.steps)
+        ms_e2e, _ = timed(e2e_step, steps)
     h2d = tok_pin.numel() * 4 + len_pin.numel() * 4
     d2h = 8
+    del model, params
+    gc.collect()
+    torch.cuda.empty_cache()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     f_step, f_rule_step, f_rule_fwd = (x * B for x in flops_per_sequence(N, L, wl["outside"]))
     peaks = load_peaks()
-    rule_ms, rule_launches = prof["rule_gemm"]
-    rule_ms += prof["rule_finalize"][0]          # the max-shift epilogue of K-split tiles is part of the rule contraction
-    achieved = (f_rule_fwd * args.steps / (rule_ms * 1e-3) / 1e12) if rule_ms > 0 else None
-    # launches of the class = GEMM launches + (for K-split tails) the small finalize kernels; per GEMM launch figures use
-    # the number of (diagonal, chunk) units.  DRAM traffic per span comes from the committed ncu capture of this kernel.
-    spans_per_step = B * (L * (L - 1) // 2)
-    traffic = alg_bytes = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and N in (256, 512):
-        with open(tpath) as f:
-            tj = json.load(f)[f"k2_n{N}"]
-        gemm_launches = max(1, int(rule_launches) // args.steps)
-        traffic = tj["dram_bytes_per_span"] * spans_per_step / gemm_launches
-        alg_bytes = (2.0 * N * N * spans_per_step + 2.0 * N ** 3 * gemm_launches) / gemm_launches   # Y once + W once per launch
-    roofline = dict(bound="tensor", kernel="k_tc_gemm2<rule> (rule contraction, tcgen05 cta_group::2)",
-                    achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
-                    frac=(achieved / peaks["tflops"]) if achieved else None, traffic=traffic,
-                    traffic_source=("profiles/r01_traffic.json (ncu --set full, one launch, scaled per span)" if traffic else None),
-                    algorithmic_bytes_per_launch=alg_bytes,
-                    peak_source=f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                    launches=int(rule_launches), avg_launch_ms=(rule_ms / rule_launches) if rule_launches else None,
-                    algorithmic_flops_per_step=f_rule_fwd,
-                    step_tflops=f_step / (ms_step * 1e-3) / 1e12, step_frac=f_step / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
-                    kernels_ms_per_step={k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]})
-    # every kernel class of the tensor-core path against the roofline that bounds it:
-    # algorithmic bytes or flops per step / summed CUDA-event time of the class
+    kms = {k: v[0] / steps for k, v in prof.items() if v[1]}
+    kms["rule_gemm"] = kms.get("rule_gemm", 0.0) + kms.pop("rule_finalize", 0.0)   # the max-shift epilogue of K-split tiles
+    roofline = dict(step_tflops=f_step / (ms_step * 1e-3) / 1e12, step_frac=f_step / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
+                    step_peak=f"{peaks['source']} bf16_tflops_sustained {peaks['tflops']} TFLOP/s (kernels timed inside a long step)",
+                    algorithmic_flops_per_step=f_step,
+                    kernels_ms_per_step={k: round(v, 3) for k, v in kms.items()})
+    # Every kernel class of the tensor-core path against the roofline that bounds it (DESIGN.md section 3): algorithmic
+    # bytes or flops per step / summed CUDA-event time of the class.  The top-level entry is the class with the most time.
     if N >= 64 and prof["split_sum"][1]:
         spans = B * (L * (L - 1) // 2)                         # spans of width >= 2 per pass
         splits = B * ((L ** 3 - L) // 6)
-        passes = 2 if wl["outside"] else 1
+        units = max(1, prof["rule_gemm"][1] - prof["rule_finalize"][1])      # (diagonal, chunk) units of the inside passes
+        k1_passes = prof["split_sum"][1] / units               # 1 = every split-sum kept for the outside pass, 2 = all recomputed
         y_bytes = 2.0 * N * N * spans
         row_bytes = 2.0 * splits * 2 * N                       # fp16 child rows streamed once per diagonal
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"n{N}", {})
+        names = dict(split_sum="k_tc_splitsum (split-sum Y = sum_j c_j L_j^T R_j, tcgen05 + TMA store)",
+                     rule_gemm="k_tc_gemm2<rule> (rule contraction, tcgen05 cta_group::2)",
+                     gy_gemm="k_tc_gy2 (gY = G Wk^T, tcgen05 cta_group::2, TMA store)",
+                     count_gemm="k_tc_gemm2<counts> (expected rule counts gW += Y^T G, tcgen05 cta_group::2)",
+                     child_grad="k_tc_childgrad (child gradients, tcgen05 + TMA reduce-add into the outside chart)")
         per = {}
 
         def entry(cls, bound, amount, peak, unit):
-            ms = prof[cls][0] / args.steps
+            ms = kms.get(cls, 0.0)
             if ms <= 0:
                 return
+            launches = prof[cls][1] / steps
             ach = amount / (ms * 1e-3) / (1e12 if unit == "TFLOP/s" else 1e9)
-            per[cls] = dict(bound=bound, ms_per_step=round(ms, 3), achieved=round(ach, 1), peak=peak, unit=unit, frac=round(ach / peak, 3))
-        entry("split_sum", "hbm (write-limited: 3.9 TB/s pure-write ceiling measured)", passes * (y_bytes + row_bytes), peaks["hbm"], "GB/s")
-        per_rule_ms = rule_ms / args.steps
-        if per_rule_ms > 0:
-            per["rule_gemm"] = dict(bound="tensor", ms_per_step=round(per_rule_ms, 3), achieved=round(f_rule_fwd / (per_rule_ms * 1e-3) / 1e12, 1),
-                                    peak=peaks["tflops"], unit="TFLOP/s", frac=round(f_rule_fwd / (per_rule_ms * 1e-3) / 1e12 / peaks["tflops"], 3))
+            tr = traffic.get(cls, {}).get("dram_bytes_per_span")
+            per[cls] = dict(bound=bound, kernel=names[cls], ms_per_step=round(ms, 3), achieved=round(ach, 1), peak=peak, unit=unit,
+                            frac=round(ach / peak, 3), launches_per_step=launches, avg_launch_ms=ms / launches,
+                            algorithmic_per_launch=amount / launches,
+                            traffic=(tr * spans * (k1_passes if cls == "split_sum" else 1.0) / launches) if tr else None)
+        entry("split_sum", "hbm", k1_passes * (y_bytes + row_bytes), peaks["hbm"], "GB/s")
+        entry("rule_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
         if wl["outside"]:
-            entry("gy_gemm", "hbm (write) / tensor", y_bytes, peaks["hbm"], "GB/s")
+            entry("gy_gemm", "hbm", y_bytes, peaks["hbm"], "GB/s")
             entry("count_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
-            entry("child_grad", "hbm (read + L2 reduce-add)", y_bytes + row_bytes + 2.0 * splits * 2 * N * 4, peaks["hbm"], "GB/s")
+            entry("child_grad", "hbm", y_bytes + row_bytes + 2.0 * splits * 2 * N * 4, peaks["hbm"], "GB/s")
+        if per:
+            top = max(per, key=lambda k: per[k]["ms_per_step"])
+            t = per[top]
+            roofline.update(bound=t["bound"], kernel=t["kernel"], achieved=t["achieved"], peak=t["peak"], unit=t["unit"],
+                            frac=t["frac"], traffic=t["traffic"],
+                            traffic_source=("profiles/r02_traffic.json (ncu --set full, one launch, scaled per span)" if t["traffic"] else None),
+                            launches=int(t["launches_per_step"] * steps), avg_launch_ms=t["avg_launch_ms"],
+                            algorithmic_per_launch=t["algorithmic_per_launch"],
+                            peak_source=f"{peaks['source']} " + ("hbm_gbs" if t["bound"] == "hbm" else "bf16_tflops_sustained"),
+                            selected="the kernel class with the largest share of the step")
         roofline["by_kernel"] = per
+        roofline["split_sum_passes"] = round(k1_passes, 3)
         # the step as a whole against HBM: Y written by every split-sum pass and read by the rule / count GEMM, gY
         # written and read once, child rows streamed by K1 and K5, outside-chart reduce-adds counted as read + write
-        step_bytes = passes * (y_bytes + row_bytes) + y_bytes
+        step_bytes = k1_passes * (y_bytes + row_bytes) + y_bytes
         if wl["outside"]:
             step_bytes += y_bytes + 2 * y_bytes + row_bytes + 2 * (2.0 * splits * 2 * N * 4)
         ach = step_bytes / (ms_step * 1e-3) / 1e9
         roofline["step_hbm"] = dict(algorithmic_bytes_per_step=step_bytes, achieved=round(ach, 1), peak=peaks["hbm"], unit="GB/s",
                                     frac=round(ach / peaks["hbm"], 3),
                                     note="every kernel of this path streams the N^2-per-span split-sum intermediate through HBM; "
-                                         "the step is bandwidth-bound (writes cap at 3.9 TB/s), see DESIGN.md section 3.4")
+                                         "the step is bandwidth-bound, see DESIGN.md section 3.4")
     launches = int(sum(v[1] for v in prof.values()))
-    cpu_v, cpu_t, cpu_samp, cores = cpu_sample(wl) if (world == 1 and not args.skip_cpu) else (None, None, None, None)
+    cpu_v = parity = None
+    if world == 1 and not args.skip_cpu and not secondary:
+        cpu_v, cpu_t, cpu_samp, cores = cpu_sample(wl)
+        parity = parity_check(wl, batch_logz0=float(lz_host[0]))
     line = dict(metric="inside+outside sequences/sec" if wl["outside"] else "inside sequences/sec",
-                value=world * B / (ms_step * 1e-3), unit="seq/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                value=world * B / (ms_step * 1e-3), unit="seq/s", n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
-                data="synthetic",
-                config=dict(workload=wl["name"], N=N, V=V, L=L, batch_per_gpu=B, global_batch=world * B,
-                            parallelism=f"dp{world}", l2="inputs larger than L2 (chart + split-sum buffers are GBs)",
-                            accumulate="fp32 (tcgen05, segmented)", operands="fp16 mantissas + per-cell exponents"),
+                data="synthetic", config=workload_config(wl, B, world),
+                impl_notes=dict(micro_batch=micro, l2="inputs larger than L2 (chart + split-sum buffers are GBs)",
+                                accumulate="fp32 (tcgen05, segmented)", operands="fp16 mantissas + per-cell exponents",
+                                split_sum_cache="inside pass keeps Y in HBM for the outside pass where it fits (RbnDesc.cache_bytes)"),
                 e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="seq/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h),
                 gpu_launches=launches, roofline=roofline, clocks=clocks,
-                logZ_mean=float(np.mean(lz_host)))
+                logZ_mean=float(np.mean(lz_host)), count_check=count_check)
     if cpu_v is not None:
         line["cpu_baseline"] = dict(value=cpu_v, unit="seq/s", cores=cores, kind="port", sample=cpu_samp)
-    print(json.dumps(line), flush=True)
-    if world > 1:
+    if parity is not None:
+        line["parity_check"] = parity
+    return line
+
+
+def finish_ours(args, wl):
+    """Print this arm's ONE JSON line.  With more than one GPU the line also carries, under `secondary`, the C5 step
+    (BASELINE configs[4]: N = 512, 1024 sequences per GPU, EM E-step + count all-reduce) measured in the same run."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = run_ours(args, wl)
+    if world > 1 and args.workload == "c3" and not args.no_secondary:
+        sec = run_ours(args, WORKLOADS["c5"], secondary=True)
+        if line is not None and sec is not None:
+            line["secondary"] = sec
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1 and dist.is_initialized():
         dist.destroy_process_group()
 
 
@@ -521,8 +609,8 @@ def run_gauss(args, wl):
     line = dict(metric="inside+gradient sequences/sec", value=world * B / (ms_step * 1e-3), unit="seq/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=wl["name"], D=D, L=L, batch_per_gpu=B, global_batch=world * B, parallelism=f"dp{world}",
-                            l2="chart (80 MB) fits L2: latency-bound launch train, no flush"),
+                config=workload_config(wl, B, world),
+                impl_notes=dict(l2="chart (80 MB) fits L2: latency-bound launch train, no flush"),
                 e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="seq/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(y_pin.numel() * 8),
                          d2h_bytes_per_step=8),
                 gpu_launches=int(sum(v[1] for v in prof.values())),
@@ -547,6 +635,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="sequences per GPU (default: the workload's)")
     ap.add_argument("--chunk", type=int, default=0, help="spans per launch group (0 = library default)")
+    ap.add_argument("--micro", type=int, default=0, help="sequences per micro-batch (default: the workload's)")
+    ap.add_argument("--no-secondary", action="store_true", help="N > 1: skip the C5 line under `secondary`")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the end-to-end arm")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the CPU baseline")
     args = ap.parse_args()
@@ -556,7 +646,7 @@ def main():
     elif wl.get("gauss"):
         run_gauss(args, wl)
     else:
-        run_ours(args, wl)
+        finish_ours(args, wl)
 
 
 if __name__ == "__main__":

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define RBN_ABI_VERSION 1
+#define RBN_ABI_VERSION 2
 
 /* error codes */
 #define RBN_OK            0
@@ -45,9 +45,10 @@ extern "C" {
 #define RBN_E_UNSUPPORTED -4  /* shape outside what the selected path supports */
 
 /* RbnDesc.path */
-#define RBN_PATH_AUTO     0   /* tensor-core path when N is 64, 128, 192, 256 or 512 (and L >= 2), else the shared-memory path */
+#define RBN_PATH_AUTO     0   /* tensor-core path when N is 64, 128, 192, 256 or 512 and 2 <= L <= 129, else the shared-memory path */
 #define RBN_PATH_SIMT     1   /* shared-memory / CUDA-core path, fp32 end to end (small nonterminal counts) */
-#define RBN_PATH_TCGEN05  2   /* span-diagonal tcgen05 tensor-core path (fp16 operands, fp32 accumulate) */
+#define RBN_PATH_TCGEN05  2   /* span-diagonal tcgen05 tensor-core path (fp16 operands, fp32 accumulate); L <= 129 (at most 128
+                                 splits per span), longer inputs: RBN_E_UNSUPPORTED here, the shared-memory path under AUTO */
 
 typedef struct RbnDesc {
     int32_t N;            /* number of (flattened) nonterminal values */
@@ -58,6 +59,11 @@ typedef struct RbnDesc {
     int32_t path;         /* RBN_PATH_* */
     int32_t chunk_items;  /* tensor-core path: spans processed per launch group (0 = default) */
     int32_t flags;        /* reserved, must be 0 */
+    int64_t cache_bytes;  /* tensor-core path: bytes of EXTRA workspace the inside pass may fill with the per-span
+                             split-sums Y (N*N fp16 each) so that the outside pass reads them back instead of
+                             recomputing them (widest diagonals first; clamped to what the batch can use).
+                             0 = keep nothing.  rbn_workspace_bytes() includes it; forward and backward must be
+                             given the same value.  Pure speed/space trade: results do not depend on it. */
 } RbnDesc;
 
 /* ABI version of the loaded library (== RBN_ABI_VERSION of the header it was built from). */

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librbn_b200.so")
 
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+ABI_VERSION = 2          # RBN_ABI_VERSION of include/rbn_b200.h this binding was written against
 KERNEL_CLASSES = ["emission", "split_sum", "rule_gemm", "gy_gemm", "count_gemm", "child_grad", "grad_prep",
                   "simt_inside", "simt_outside", "other", "rule_finalize"]
 
@@ -17,7 +18,7 @@ KERNEL_CLASSES = ["emission", "split_sum", "rule_gemm", "gy_gemm", "count_gemm",
 class RbnDesc(ctypes.Structure):
     _fields_ = [("N", ctypes.c_int32), ("V", ctypes.c_int32), ("B", ctypes.c_int32), ("L", ctypes.c_int32),
                 ("n_tvars", ctypes.c_int32), ("path", ctypes.c_int32), ("chunk_items", ctypes.c_int32),
-                ("flags", ctypes.c_int32)]
+                ("flags", ctypes.c_int32), ("cache_bytes", ctypes.c_int64)]
 
 
 class GaussDesc(ctypes.Structure):
@@ -74,6 +75,9 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if lib.rbn_abi_version() != ABI_VERSION:
+            raise RbnError(f"{LIB_PATH} has ABI version {lib.rbn_abi_version()}, this binding needs {ABI_VERSION}: "
+                           f"rebuild it with `make -C rbn_b200/csrc`")
         _lib = lib
     return _lib
 

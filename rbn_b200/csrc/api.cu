@@ -67,20 +67,26 @@ static bool desc_ok(const RbnDesc* d) {
         set_error("bad descriptor: N=%d V=%d B=%d L=%d n_tvars=%d", d->N, d->V, d->B, d->L, d->n_tvars);
         return false;
     }
-    if (d->path < RBN_PATH_AUTO || d->path > RBN_PATH_TCGEN05 || d->flags != 0 || d->chunk_items < 0) {
-        set_error("bad descriptor: path=%d flags=%d chunk_items=%d", d->path, d->flags, d->chunk_items);
+    if (d->path < RBN_PATH_AUTO || d->path > RBN_PATH_TCGEN05 || d->flags != 0 || d->chunk_items < 0 || d->cache_bytes < 0) {
+        set_error("bad descriptor: path=%d flags=%d chunk_items=%d cache_bytes=%lld", d->path, d->flags, d->chunk_items,
+                  (long long)d->cache_bytes);
         return false;
     }
     return true;
 }
 
-static bool tc_shape_ok(const RbnDesc* d) { return ((d->N % 64 == 0 && d->N >= 64 && d->N <= 256) || d->N == 512) && d->L >= 2; }
+// The split-sum and child-gradient kernels hold the splits of a span in two K-slabs of 64 (128 fix-up threads, 128-row
+// stage buffers): a span has at most 128 splits, i.e. L <= 129.
+static constexpr int kTcMaxL = 129;
+static bool tc_shape_ok(const RbnDesc* d) {
+    return ((d->N % 64 == 0 && d->N >= 64 && d->N <= 256) || d->N == 512) && d->L >= 2 && d->L <= kTcMaxL;
+}
 
 int resolve_path(const RbnDesc* d) {
     if (d->path == RBN_PATH_SIMT) return RBN_PATH_SIMT;
     if (d->path == RBN_PATH_TCGEN05) {
         if (!tc_shape_ok(d)) {
-            set_error("tensor-core path needs N in {64,128,192,256,512} and L >= 2 (got N=%d L=%d)", d->N, d->L);
+            set_error("tensor-core path needs N in {64,128,192,256,512} and 2 <= L <= %d (got N=%d L=%d)", kTcMaxL, d->N, d->L);
             return RBN_E_UNSUPPORTED;
         }
         return RBN_PATH_TCGEN05;
@@ -132,6 +138,15 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->gabs = take(ns * chunk * N * sizeof(__half));
         o->gexp = take(ns * chunk * sizeof(int));
         o->acc = take(ns * chunk * N * sizeof(float));
+        // split-sum cache: whole spans only, never more than the batch has, off in the two-stream schedules (their
+        // forward and backward passes cut the diagonals differently)
+        const size_t per_span = N * N * sizeof(__half) + sizeof(int);
+        size_t cap = tune.overlap ? 0 : (size_t)d->cache_bytes / per_span;
+        const size_t all_spans = B * (L * (L - 1) / 2);
+        if (cap > all_spans) cap = all_spans;
+        o->cache_spans = (long long)cap;
+        o->ycache = take(cap * N * N * sizeof(__half));
+        o->ycache_e = take(cap * sizeof(int));
     }
     o->total = off;
     return true;

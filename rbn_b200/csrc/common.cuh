@@ -64,6 +64,11 @@ struct WsLayout {
     size_t gabs;        // half [nslot][chunk][N]       absolutely scaled upstream gradient (for the count GEMM)
     size_t gexp;        // int32 [nslot][chunk]
     size_t acc;         // float [nslot][chunk][N]  K-split partial sums of the rule GEMM's tail tiles
+    // split-sum cache (RbnDesc.cache_bytes): the inside pass writes the Y of `cache_spans` spans here (widest diagonals
+    // first) and the outside pass reads them back instead of recomputing them; E_m of the same spans beside it
+    size_t ycache;      // half [cache_spans][N*N]
+    size_t ycache_e;    // int32 [cache_spans]
+    long long cache_spans;
     size_t total;
     int Lp;
     int chunk;

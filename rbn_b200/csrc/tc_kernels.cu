@@ -484,7 +484,14 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI;
-            if (i + w > lengths[b]) continue;
+            if (i + w > lengths[b]) {
+                // span beyond its sequence (ragged batch): its Y rows are still read (as A rows of the rule GEMM whose
+                // output row is dropped, as K rows of the count GEMM against a zero gradient row), so they must be
+                // finite -- write zeros; nothing else ever clears these buffers
+                uint4* dst = reinterpret_cast<uint4*>(Y + (size_t)t * N * N);
+                for (int q = threadIdx.x; q < N * N / 8; q += 128) dst[q] = make_uint4(0, 0, 0, 0);
+                continue;
+            }
             for (int sub = 0; sub < nsub; ++sub) {
                 const int brow = (sub / nblk) * RB, ccol = (sub % nblk) * NS;
                 for (int h = 0; h < halves; ++h) {
@@ -1359,6 +1366,12 @@ const TcTune& tc_tune() {
     return t;
 }
 
+// work unit of a pass: one chunk of spans of one diagonal and one group of sequences
+struct Unit {
+    int w, g, m0, cnt, slot;
+    long long coff;      // first span of this unit in the split-sum cache, -1: not cached (Y lives in the slot buffer)
+};
+
 struct TcCtx {
     const RbnDesc* d;
     const WsLayout* ws;
@@ -1379,6 +1392,9 @@ struct TcCtx {
     float* acc(int s) const { return (float*)(base + ws->acc) + (size_t)s * chunk * N; }
     int* item_e(int s) const { return (int*)(base + ws->item_e) + (size_t)s * chunk; }
     int* gexp(int s) const { return (int*)(base + ws->gexp) + (size_t)s * chunk; }
+    // split-sum and span exponents E_m of a unit: in the cache when the unit has a place there, else in its slot
+    __half* y_of(const Unit& u) const { return u.coff >= 0 ? (__half*)(base + ws->ycache) + (size_t)u.coff * N * N : y(u.slot); }
+    int* e_of(const Unit& u) const { return u.coff >= 0 ? (int*)(base + ws->ycache_e) + (size_t)u.coff : item_e(u.slot); }
 };
 
 static void fill_ctx(TcCtx& c, const RbnDesc* d, const WsLayout& ws, char* base, const int* lengths) {
@@ -1414,6 +1430,7 @@ struct Sched {
     std::vector<cudaEvent_t> taken;
 
     Sched() : two(false), pair_launch(false), dev(0), err(RBN_OK) { st[0] = st[1] = nullptr; sms[0] = sms[1] = 0; }
+    ~Sched() { if (two) end(); }      // error returns inside a pass still join stream 1 and hand the pool resources back
 
     // mode 1: disjoint SM partitions (sms0 | rest);  mode 2: both streams use every SM, their kernels are the
     // 'half SM' variants that leave room for one CTA of the other stream (co-resident schedule);  mode 3: both streams
@@ -1483,8 +1500,6 @@ struct Sched {
     }
 };
 
-// work unit of a pass: one chunk of spans of one diagonal and one group of sequences
-struct Unit { int w, g, m0, cnt, slot; };
 
 // Diagonal w of sequence group g covers items [b0 * nI, b1 * nI); it is cut into chunks of at most `chunk` items
 // (whole waves of `wave` items when possible).
@@ -1497,11 +1512,28 @@ static void diag_units(std::vector<Unit>& out, int w, int L, int B, int groups, 
         const int i0 = b0 * nI, i1 = b1 * nI;
         for (int m0 = i0; m0 < i1; m0 += per) {
             Unit u;
-            u.w = w; u.g = g; u.m0 = m0; u.cnt = (i1 - m0 < per) ? i1 - m0 : per; u.slot = counter % nslot;
+            u.w = w; u.g = g; u.m0 = m0; u.cnt = (i1 - m0 < per) ? i1 - m0 : per; u.slot = counter % nslot; u.coff = -1;
             ++counter;
             out.push_back(u);
         }
     }
+}
+
+// Every unit of a pass, per diagonal.  The inside and the outside pass of one workspace build the SAME plan (same
+// descriptor, same `active`), so a unit's place in the split-sum cache is known to both without any device state.
+// The cache goes to the widest diagonals first: their recompute is the most expensive one (most splits per span).
+static void plan_units(std::vector<std::vector<Unit>>& by_w, int L, int B, const int* active, int groups, int chunk, int wave,
+                       long long cache_spans) {
+    by_w.assign((size_t)L + 1, std::vector<Unit>());
+    int counter = 0;
+    for (int w = 2; w <= L; ++w) diag_units(by_w[w], w, L, active ? active[w] : B, groups, chunk, wave, 1, counter);
+    long long used = 0;
+    for (int w = L; w >= 2 && used < cache_spans; --w)
+        for (Unit& u : by_w[w]) {
+            if (used + u.cnt > cache_spans) continue;       // a later, smaller unit may still fit
+            u.coff = used;
+            used += u.cnt;
+        }
 }
 
 template <class... KArgs, class... Args>
@@ -1554,9 +1586,9 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     rc = make_tmap_2d(&tmRC1, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, rows1);
     if (rc) return rc;
     CUtensorMap tmY, tmYtail;
-    rc = make_tmap_2d(&tmY, c.y(u.slot), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
+    rc = make_tmap_2d(&tmY, c.y_of(u), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmYtail, c.y(u.slot), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
+    rc = make_tmap_2d(&tmYtail, c.y_of(u), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
     if (rc) return rc;
     const int NS = N > 256 ? 256 : N;
     int halves = (NS + 127) / 128;
@@ -1584,7 +1616,7 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     if (half_sm && grid > sms) grid = sms;
     { ProfScope ps(KC_SPLITSUM, st);
       RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, kK1Threads, smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
-                                         c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y(u.slot), c.item_e(u.slot), nslots)); }
+                                         c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y_of(u), c.e_of(u), nslots)); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
 }
@@ -1609,11 +1641,11 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
     const int w = u.w, m0 = u.m0, cnt = u.cnt;
     size_t NN = (size_t)c.N * c.N;
     CUtensorMap tmA, tmB;
-    int rc = make_tmap_2d(&tmA, c.y(u.slot), NN, (uint64_t)cnt, NN * 2, 128);
+    int rc = make_tmap_2d(&tmA, c.y_of(u), NN, (uint64_t)cnt, NN * 2, 128);
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, c.wt, NN, (uint64_t)c.N, NN * 2, BN);
     if (rc) return rc;
-    EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.cv, c.ce, c.lc, c.rc, c.acc(u.slot), BN};
+    EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.e_of(u), c.cv, c.ce, c.lc, c.rc, c.acc(u.slot), BN};
     const int n_tiles = c.N / BN;                  // 1, or 2 when N = 512
     if (n_tiles > 1 && !use_pairs()) {
         set_error("N = %d needs the CTA-pair kernels (unset RBN_TC_1CTA)", c.N);
@@ -1633,7 +1665,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         rc = launch_tc_gemm2<false, false, BN, 3, 0, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule,half>", KC_RULE);
         if (rc) return rc;
         { ProfScope ps(KC_RULE_FIN, st);
-          k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+          k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
         RBN_LAUNCH_CHECK("k_rule_finalize");
         return RBN_OK;
     }
@@ -1654,7 +1686,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
-              k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+              k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
@@ -1666,7 +1698,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
-              k_rule_finalize<<<cnt - t_begin, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.item_e(u.slot), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+              k_rule_finalize<<<cnt - t_begin, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
@@ -1745,7 +1777,7 @@ static int launch_k4_bn(TcCtx& c, const Unit& u, float* gW, cudaStream_t st, int
     const int cnt = u.cnt;
     size_t NN = (size_t)c.N * c.N;
     CUtensorMap tmA, tmB;
-    int rc = make_tmap_2d(&tmA, c.y(u.slot), NN, (uint64_t)cnt, NN * 2, 64);            // MN-major A: [K=items][M=(b,c)]
+    int rc = make_tmap_2d(&tmA, c.y_of(u), NN, (uint64_t)cnt, NN * 2, 64);            // MN-major A: [K=items][M=(b,c)]
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, c.gabs(u.slot), (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 64);   // MN-major B: [K=items][N=a]
     if (rc) return rc;
@@ -1811,7 +1843,7 @@ static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     int grid = cnt < sms ? cnt : sms;
     { ProfScope ps(KC_CHILD, st);
       RBN_CUDA_CHECK(launch_maybe_paired(k_tc_childgrad, paired, grid, 384, smem, st, tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt,
-                                         c.lengths, tmAL, tmAR, tmALt, tmARt, (const int*)c.ce, (const int*)c.item_e(u.slot),
+                                         c.lengths, tmAL, tmAR, tmALt, tmARt, (const int*)c.ce, (const int*)c.e_of(u),
                                          (const int*)c.gexp(u.slot))); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;
@@ -1829,7 +1861,7 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
     const TcTune& tune = tc_tune();
     int rc = prep_weights(c, W, st);
     if (rc) return rc;
-    RBN_CUDA_CHECK(cudaMemsetAsync(c.y(0), 0, (size_t)ws.nslot * c.chunk * N * N * sizeof(__half), st));
+    // (the split-sum buffers need no clearing: K1 writes every span of a unit, zeros for spans beyond their sequence)
     // TMA slabs over-read rows of cells that are never written (start >= end, beyond a sequence's length): keep them 0
     RBN_CUDA_CHECK(cudaMemsetAsync(c.lc, 0, (size_t)B * L * c.Lp * N * sizeof(__half), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(c.rc, 0, (size_t)B * (L + 1) * c.Lp * N * sizeof(__half), st));
@@ -1848,10 +1880,12 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
     std::vector<cudaEvent_t> evK2;
     std::vector<int> last_prev(groups, -1), last_cur(groups, -1);
     int counter = 0;
+    // sorted ragged batch: only the first active[w] sequences reach width w (not combined with sequence groups)
+    std::vector<std::vector<Unit>> plan;
+    plan_units(plan, L, B, overlap ? nullptr : active, groups, c.chunk, wave, overlap ? 0 : ws.cache_spans);
     for (int w = 2; w <= L && !rc; ++w) {
         const size_t first = units.size();
-        // sorted ragged batch: only the first active[w] sequences reach width w (not combined with sequence groups)
-        diag_units(units, w, L, (active && !overlap) ? active[w] : B, groups, c.chunk, wave, ws.nslot, counter);
+        for (Unit u : plan[w]) { u.slot = counter++ % ws.nslot; units.push_back(u); }
         evK2.resize(units.size(), nullptr);
         for (size_t ui = first; ui < units.size() && !rc; ++ui) {
             const Unit& u = units[ui];
@@ -1889,7 +1923,6 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     RBN_CUDA_CHECK(cudaMemsetAsync(gW, 0, (size_t)N * N * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
-    RBN_CUDA_CHECK(cudaMemsetAsync(c.y(0), 0, (size_t)ws.nslot * c.chunk * N * N * sizeof(__half), st));
     { ProfScope ps(KC_OTHER, st); k_tc_outside_seed<<<B, 128, 0, st>>>(N, L, c.Lp, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior); }
     RBN_LAUNCH_CHECK("k_tc_outside_seed");
 
@@ -1906,19 +1939,22 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     std::vector<cudaEvent_t> evK5;
     std::vector<int> last_prev(groups, -1), last_cur(groups, -1);
     int counter = 0;
+    std::vector<std::vector<Unit>> plan;
+    plan_units(plan, L, B, overlap ? nullptr : active, groups, c.chunk, wave, overlap ? 0 : ws.cache_spans);
     for (int w = L; w >= 2 && !rc; --w) {
         const size_t first = units.size();
-        diag_units(units, w, L, (active && !overlap) ? active[w] : B, groups, c.chunk, wave, ws.nslot, counter);
+        for (Unit u : plan[w]) { u.slot = counter++ % ws.nslot; units.push_back(u); }
         evK5.resize(units.size(), nullptr);
         for (size_t ui = first; ui < units.size() && !rc; ++ui) {
             const Unit& u = units[ui];
             const int cnt = u.cnt;
             if ((int)ui - ws.nslot >= 0) S.wait(0, evK5[ui - ws.nslot]);         // every reader of the slot's buffers is done
-            if ((rc = launch_k1(c, u, S.st[0], S.sms[0], S.pair_launch))) break;
+            // split-sum: read back from the cache when the inside pass kept it, recomputed otherwise
+            if (u.coff < 0 && (rc = launch_k1(c, u, S.st[0], S.sms[0], S.pair_launch))) break;
             if (last_prev[u.g] >= 0) S.wait(0, evK5[last_prev[u.g]]);            // alpha of this diagonal is complete
             int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
             { ProfScope ps(KC_PREP, S.st[0]);
-              k_prep_g<<<(pg + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, pg, lengths, c.ce, c.item_e(u.slot), c.wexp, c.alpha,
+              k_prep_g<<<(pg + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, pg, lengths, c.ce, c.e_of(u), c.wexp, c.alpha,
                                              c.ghat(u.slot), c.gabs(u.slot), c.gexp(u.slot)); }
             RBN_LAUNCH_CHECK("k_prep_g");
             S.wait(1, S.record(0));

@@ -36,7 +36,7 @@ class LengthBucketedBatches:
     `max_work` (and whose size stays below `batch_size`), so a batch never mixes very short and very long sequences;
     the batch ORDER is shuffled per epoch when `shuffle=True` (content of a batch is fixed, like bucketed samplers).
     `rank` / `world` deal the batches round-robin to the ranks of a data-parallel job (equal counts per rank: the tail
-    that does not divide is dropped, or kept and repeated on the last ranks with `drop_last=False`)."""
+    that does not divide is dropped, or kept and the list wrapped around to a multiple of `world` with `drop_last=False`)."""
 
     def __init__(self, token_lists, batch_size=512, max_work=None, shuffle=False, seed=0, rank=0, world=1,
                  drop_last=True, pin_memory=True):
@@ -70,8 +70,7 @@ class LengthBucketedBatches:
         if self.drop_last or len(ids) % self.world == 0:
             ids = ids[:per * self.world]
         else:
-            pad = (per + 1) * self.world - len(ids)
-            ids = np.concatenate([ids, ids[-pad:]])
+            ids = np.resize(ids, (per + 1) * self.world)      # wraps around: also right when there are fewer batches than ranks
         return ids[self.rank::self.world]
 
     def __len__(self):

@@ -49,18 +49,64 @@ def shard_batch(tokens, lengths, rank=None, world=None, balance=True):
 
 
 def allreduce_counts(tensors, group=None):
-    """Sum the expected-count / gradient tensors over ranks, in ONE flat all-reduce (C5: 537 MB over NVLink)."""
+    """Sum the expected-count / gradient tensors over ranks IN PLACE: one all-reduce per tensor, issued together on the
+    process group's own stream (NCCL), no staging copy -- the big one (gW, 67 MB at N = 256, 537 MB at N = 512) moves at
+    NVLink rate, the small ones cost a launch each."""
     tensors = [t for t in tensors if t is not None]
     if not tensors or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return tensors
-    flat = torch.cat([t.reshape(-1) for t in tensors])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 0
-    for t in tensors:
-        n = t.numel()
-        t.copy_(flat[off:off + n].view_as(t))
-        off += n
+    works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in tensors]
+    for w in works:
+        w.wait()
     return tensors
+
+
+class CountReducer:
+    """Accumulates the count tensors of successive micro-batches; with several ranks every micro-batch's tensors are
+    all-reduced asynchronously (in place, on the process group's stream) WHILE the next micro-batch's chart pass runs,
+    and folded into the running sum one micro-batch later.  Summing per micro-batch moves a few times more bytes over
+    NVLink than one all-reduce at the end (C5: 2 x 537 MB per step against seconds of compute) and removes the
+    collective from the critical path.
+
+        red = CountReducer()
+        for micro-batch: red.add(torch.autograd.grad(logZ.sum(), (W, T, prior)))
+        gW, gT, gPrior = red.result()
+    """
+
+    def __init__(self, group=None):
+        self.group = group
+        self.acc = None
+        self.pending = None          # (tensors, works) of the micro-batch whose all-reduce is in flight
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def _fold(self, tensors):
+        if self.acc is None:
+            self.acc = [t if t.is_contiguous() else t.contiguous() for t in tensors]
+        else:
+            for a, t in zip(self.acc, tensors):
+                a.add_(t)
+
+    def _drain(self):
+        if self.pending is not None:
+            tensors, works = self.pending
+            for w in works:
+                w.wait()
+            self.pending = None
+            self._fold(tensors)
+
+    def add(self, tensors):
+        tensors = [t.detach() for t in tensors]
+        if not self.distributed:
+            self._fold(tensors)
+            return
+        self._drain()
+        tensors = [t if t.is_contiguous() else t.contiguous() for t in tensors]
+        works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for t in tensors]
+        self.pending = (tensors, works)
+
+    def result(self):
+        self._drain()
+        return self.acc
 
 
 def gather_logZ(logZ, idx, total, group=None):

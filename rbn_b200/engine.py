@@ -13,6 +13,7 @@ The inside pass and the outside pass (expected rule counts) run in librbn_b200.s
 torch.autograd.Function that joins them.  No arithmetic of the path happens on the host.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -31,22 +32,40 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-class _Pass:
-    """One forward pass on the device: inputs, workspace (holds the chart) and outputs."""
+def _cache_budget(dev, base_bytes):
+    """Bytes of device memory the split-sum cache of one pass may take (RbnDesc.cache_bytes): what is free on the device
+    plus what torch's allocator holds unused, minus the rest of the workspace and a safety margin.  RBN_Y_CACHE_GB
+    overrides it (0 switches the cache off).  The library clamps the figure to what the batch can use."""
+    env = os.environ.get("RBN_Y_CACHE_GB")
+    if env is not None:
+        return max(0, int(float(env) * 1e9))
+    free, total = torch.cuda.mem_get_info(dev)
+    reusable = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    return max(0, int(free + reusable - base_bytes - 4e9 - 0.03 * total))
 
-    def __init__(self, W, T, prior, tokens, lengths, path=_lib.PATH_AUTO, chunk_items=0):
+
+class _Pass:
+    """One forward pass on the device: inputs, workspace (holds the chart) and outputs.  `keep_split_sums`: let the
+    inside pass keep as many per-span split-sums as device memory allows, for the outside pass to read back."""
+
+    def __init__(self, W, T, prior, tokens, lengths, path=_lib.PATH_AUTO, chunk_items=0, keep_split_sums=False,
+                 len_host=None):
         lib = _lib.load()
         dev = W.device
         B, L, nt = tokens.shape
         self.desc = _lib.RbnDesc(N=W.shape[0], V=T.shape[0], B=B, L=L, n_tvars=nt, path=path,
-                                 chunk_items=chunk_items, flags=0)
+                                 chunk_items=chunk_items, flags=0, cache_bytes=0)
         nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
         if nbytes == 0:
             _lib.check(-1, "rbn_workspace_bytes")
+        if keep_split_sums and lib.rbn_resolve_path(ctypes.byref(self.desc)) == _lib.PATH_TCGEN05:
+            self.desc.cache_bytes = _cache_budget(dev, nbytes)
+            nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
         # ragged batch: sort by length (longest first) so that diagonal w only visits the sequences that reach it
         # (rbn_inside_forward_sorted); `order[k]` = original index of the k-th sorted sequence, `pos[b]` its inverse
         self.order = self.pos = self.active = None
-        len_host = lengths.detach().cpu().numpy().astype(np.int64)
+        if len_host is None:              # callers that validated the batch hand their host copy down (no second sync)
+            len_host = lengths.detach().cpu().numpy().astype(np.int64)
         if B > 1 and int(len_host.min()) != int(len_host.max()):
             order = np.argsort(-len_host, kind="stable")
             self.order = torch.as_tensor(order, device=dev)
@@ -57,6 +76,8 @@ class _Pass:
             self.active = (ctypes.c_int32 * (L + 1))(*[int((srt >= w).sum()) for w in range(L + 1)])
         self.W, self.T, self.prior, self.tokens, self.lengths = W, T, prior, tokens, lengths
         self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        if os.environ.get("RBN_DEBUG_POISON") == "1":     # tests: whatever the kernels read without having written shows as NaN
+            self.workspace.fill_(0xFF)
         self.ws_off = (-self.workspace.data_ptr()) % 1024
         self.ws_bytes = nbytes
         self.logZ = torch.empty(B, dtype=torch.float32, device=dev)
@@ -117,12 +138,13 @@ class _InsideFn(torch.autograd.Function):
     """(W, T, prior) -> log Z [B] or Z [B]; backward = the CUDA outside pass (expected rule counts)."""
 
     @staticmethod
-    def forward(ctx, W, T, prior, tokens, lengths, linear, holder, path, chunk_items):
+    def forward(ctx, W, T, prior, tokens, lengths, linear, holder, path, chunk_items, len_host=None):
         dev = _cuda_device() if not W.is_cuda else W.device
         f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
         p = _Pass(f32(W), f32(T), f32(prior),
-                  tokens.to(device=dev, dtype=torch.int32).contiguous(),
-                  lengths.to(device=dev, dtype=torch.int32).contiguous(), path, chunk_items)
+                  tokens.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous(),
+                  lengths.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous(), path, chunk_items,
+                  keep_split_sums=any(ctx.needs_input_grad[:3]), len_host=len_host)
         p.forward()
         holder.append(p)
         ctx.p = p
@@ -139,25 +161,42 @@ class _InsideFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         z64, e64 = ctx.saved_tensors
-        g = grad_out.to(device=z64.device, dtype=torch.float64)
+        g = torch.nan_to_num(grad_out.to(device=z64.device, dtype=torch.float64), nan=0.0, posinf=0.0, neginf=0.0)
         pos = z64 > 0
+        post = None
         if ctx.linear:
-            # dZ/dtheta = 2^R * (what the kernel accumulates); R = rootexp + log2(zroot) for Z > 0, rootexp otherwise
-            scale = torch.where(pos, torch.ldexp(z64, e64.to(torch.int32)), torch.ldexp(torch.ones_like(z64), e64.to(torch.int32)))
-            coef = g * scale
+            # dZ/dtheta = 2^R * (what the kernel accumulates); R = rootexp + log2(zroot) for Z > 0, rootexp otherwise.
+            # 2^R leaves fp32 after ~30 tokens, so the device pass runs in the log-Z normalisation: it gets
+            # coef_b = g_b 2^(R_b - S) with S = max_b (log2|g_b| + R_b) (|coef| <= 1), and the fp32 sums it returns are
+            # multiplied by 2^S in fp64 here -- exact down to what fp64 itself can hold, like the reference's autograd.
+            R = e64 + torch.where(pos, torch.log2(torch.where(pos, z64, torch.ones_like(z64))), torch.zeros_like(z64))
+            mag = torch.where(g != 0, torch.log2(g.abs().clamp_min(1e-300)) + R, torch.full_like(R, -float("inf")))
+            S = mag.max()
+            if bool(torch.isfinite(S)):
+                S = torch.round(S)
+                coef = torch.sign(g) * torch.exp2(mag - S)
+                post = S
+            else:
+                coef = torch.zeros_like(g)
         else:
             coef = torch.where(pos, g, torch.zeros_like(g))     # log Z = -inf has no gradient
-        coef = torch.nan_to_num(coef, nan=0.0, posinf=0.0, neginf=0.0)
         gW, gT, gP = ctx.p.backward(coef)
-        outs = [t.to(device=dv, dtype=dt) for t, (dt, dv) in zip((gW, gT, gP), ctx.in_meta)]
-        return outs[0], outs[1], outs[2], None, None, None, None, None, None
+        outs = []
+        for t, (dt, dv) in zip((gW, gT, gP), ctx.in_meta):
+            if post is not None:
+                t = torch.ldexp(t.double(), post.to(torch.int32))
+            outs.append(t.to(device=dv, dtype=dt))
+        return outs[0], outs[1], outs[2], None, None, None, None, None, None, None
 
 
-def _padded_cardinality(N, batch_spans):
+TC_MAX_L = 129        # tensor-core path: at most 128 splits per span (csrc/api.cu kTcMaxL)
+
+
+def _padded_cardinality(N, batch_spans, L=2):
     """Nonterminal count the tensor-core kernels take (64, 128, 192, 256, 512) when padding N up to it pays: the pad
     symbols get probability zero everywhere, so every result is unchanged.  Small problems stay on the CUDA-core path
-    (they are latency-bound, padding would only add work)."""
-    if N % 64 == 0 or N > 512 or N < 24 or batch_spans < 4096:
+    (they are latency-bound, padding would only add work), and so do sequences longer than the tensor-core kernels take."""
+    if N % 64 == 0 or N > 512 or N < 24 or batch_spans < 4096 or L > TC_MAX_L:
         return N
     if N > 256:
         return 512 if N >= 400 else N          # 257..399 would waste > 2.2x of the contraction: stay on the CUDA-core path
@@ -172,6 +211,35 @@ def _pad_grammar(W, T, prior, Np):
     return Wp, torch.nn.functional.pad(T, (0, Np - N)), torch.nn.functional.pad(prior, (0, Np - N))
 
 
+def _host_view(tokens, lengths):
+    """(lengths as int64 numpy, largest token) for validation, length sorting and the ragged schedule, with at most ONE
+    device -> host copy: inputs that already live on the host (the usual case: a data loader's pinned batch) cost none,
+    so a pass then never synchronises the device."""
+    B, L = int(tokens.shape[0]), int(tokens.shape[1])
+    dev_parts, where = [], []
+    if lengths is not None and lengths.is_cuda:
+        dev_parts.append(lengths.reshape(-1).to(torch.int64))
+        where.append("len")
+    if tokens.is_cuda and tokens.numel():
+        dev_parts.append(tokens.max().reshape(1).to(torch.int64))
+        where.append("tok")
+    host = None
+    if dev_parts:
+        same = all(p.device == dev_parts[0].device for p in dev_parts)
+        host = torch.cat(dev_parts).cpu().numpy() if same else np.concatenate([p.cpu().numpy() for p in dev_parts])
+    if lengths is None:
+        len_host = np.full((B,), L, dtype=np.int64)
+    elif "len" in where:
+        len_host = host[:B].astype(np.int64)
+    else:
+        len_host = lengths.detach().reshape(-1).numpy().astype(np.int64)
+    if "tok" in where:
+        tok_max = int(host[-1])
+    else:
+        tok_max = int(tokens.max()) if tokens.numel() else -1
+    return len_host, tok_max
+
+
 def inside_logZ(W, T, prior, tokens, lengths=None, linear=False, path=_lib.PATH_AUTO, chunk_items=0, holder=None):
     """Functional entry: flat grammar tensors (any float dtype / device) + integer tokens -> log Z [B] (or Z).
     With `path=AUTO`, a nonterminal count that is not one the tensor-core kernels take is zero-padded up to the next one
@@ -179,16 +247,22 @@ def inside_logZ(W, T, prior, tokens, lengths=None, linear=False, path=_lib.PATH_
     tokens = torch.as_tensor(tokens)
     if tokens.dim() == 2:
         tokens = tokens[:, :, None]
+    if lengths is not None:
+        lengths = torch.as_tensor(lengths)
+    len_host, tok_max = _host_view(tokens, lengths)
     if lengths is None:
-        lengths = torch.full((tokens.shape[0],), tokens.shape[1], dtype=torch.int32)
-    lengths = torch.as_tensor(lengths)
-    if int(lengths.min()) < 1 or int(lengths.max()) > tokens.shape[1]:
+        lengths = torch.from_numpy(len_host.astype(np.int32))
+    if int(len_host.min()) < 1 or int(len_host.max()) > tokens.shape[1]:
         raise ValueError("lengths must satisfy 1 <= lengths[b] <= tokens.shape[1]")
+    if tok_max >= int(T.shape[0]):
+        # the kernels index T[token] unchecked (pcfg.py:351 would raise the same IndexError from torch indexing)
+        raise IndexError(f"token {tok_max} out of range for a terminal alphabet of {int(T.shape[0])} rows")
     if path == _lib.PATH_AUTO:
         L = int(tokens.shape[1])
-        Np = _padded_cardinality(int(W.shape[0]), int(tokens.shape[0]) * L * (L - 1) // 2)
+        Np = _padded_cardinality(int(W.shape[0]), int(tokens.shape[0]) * L * (L - 1) // 2, L)
         W, T, prior = _pad_grammar(W, T, prior, Np)
-    return _InsideFn.apply(W, T, prior, tokens, lengths, linear, holder if holder is not None else [], path, chunk_items)
+    return _InsideFn.apply(W, T, prior, tokens, lengths, linear, holder if holder is not None else [], path, chunk_items,
+                           len_host)
 
 
 def viterbi(W, T, prior, tokens, lengths=None):
@@ -365,14 +439,25 @@ class InsideEngine:
         tokens = torch.as_tensor(tokens)
         if tokens.dim() == 2:
             tokens = tokens[:, :, None]
-        shift = torch.as_tensor(toff[:-1], dtype=tokens.dtype, device=tokens.device)
-        tokens = torch.where(tokens >= 0, tokens + shift[None, None, :], tokens)
-        if lengths is None:
-            lengths = torch.full((tokens.shape[0],), tokens.shape[1], dtype=torch.int32)
-        return tokens, torch.as_tensor(lengths)
+        nt = len(toff) - 1
+        if tokens.shape[2] != nt:
+            raise ValueError(f"tokens carry {tokens.shape[2]} terminal variables per position, the model has {nt}")
+        if nt > 1:
+            # several terminal variables: variable t owns rows toff[t] .. toff[t+1] of the flat T; a value beyond its own
+            # alphabet would silently read another variable's rows, so check per variable before shifting
+            size = torch.as_tensor(np.diff(toff), dtype=tokens.dtype, device=tokens.device)
+            if bool((tokens >= size[None, None, :]).any()):
+                raise IndexError("terminal value out of range for its terminal variable")
+            shift = torch.as_tensor(toff[:-1], dtype=tokens.dtype, device=tokens.device)
+            tokens = torch.where(tokens >= 0, tokens + shift[None, None, :], tokens)
+        # (one terminal variable: the flat alphabet is its own, inside_logZ checks the range)
+        return tokens, (None if lengths is None else torch.as_tensor(lengths))
 
     # ---- entry points --------------------------------------------------------------------------------------------------
-    def log_inside(self, tokens, lengths=None, prepacked=True):
+    def log_inside(self, tokens, lengths=None, prepacked=False):
+        """`tokens[B, L(, n_tvars)]` hold PER-VARIABLE terminal values (-1 = None / padding), as the reference's sequences
+        do; they are shifted into the flat alphabet here.  `prepacked=True`: they already index the rows of the flat T
+        (what `pack_sequences` returns).  Values are range-checked either way."""
         if not prepacked:
             tokens, lengths = self.pack_tokens(tokens, lengths)
         W, T, prior = self.flatten()

@@ -6,10 +6,17 @@ but when every brick is one of the discrete bricks of `rbn_b200.pcfg` the width-
 sequential.py:23-26, the split enumeration of sequential.py:51-71 and the chart writes of sequential.py:35-36 all
 happen inside the span-diagonal CUDA kernels.  Additive, batched entry points: `log_inside_batch`, `inside_batch`.
 """
+import warnings
+
 import torch
 
 from .base import RBN, Transition
 from .util import ConstrainedModuleList
+
+
+class HostTemplateWarning(UserWarning):
+    """Raised (as a warning) when a model falls outside the fused CUDA path and the Python template loop runs instead."""
+
 
 
 class SequentialRBN(RBN, torch.nn.Module):
@@ -72,6 +79,12 @@ class SequentialRBN(RBN, torch.nn.Module):
     def inside(self, *args, **kwargs):
         """Marginal likelihood of one sequence (base.py:93-121), linear probability space, float64, differentiable."""
         if not self._fused():
+            # Bricks that are not the discrete ones of rbn_b200.pcfg are arbitrary Python callables: only the template
+            # loop of base.py:93-121 can evaluate them, on the host, through their own hooks.  That is NOT the CUDA path;
+            # say so loudly instead of degrading silently (the discrete bricks themselves never evaluate on the host).
+            warnings.warn("SequentialRBN.inside: this model has bricks the fused CUDA path does not cover; running the "
+                          "host-side template loop over the bricks' own hooks (slow, not the B200 path)",
+                          HostTemplateWarning, stacklevel=2)
             return super().inside(*args, **kwargs)
         sequence = self._prepare_sequence(*args, **kwargs)
         self.n = len(sequence)
@@ -86,12 +99,16 @@ class SequentialRBN(RBN, torch.nn.Module):
 
     def log_inside_batch(self, sequences=None, tokens=None, lengths=None):
         """log Z for a batch (additive API).  Either `sequences` (iterable of reference-style sequences) or a padded
-        integer `tokens[B, L]` / `tokens[B, L, n_tvars]` (-1 = None / padding) plus optional `lengths[B]`.
+        integer `tokens[B, L]` / `tokens[B, L, n_tvars]` (-1 = None / padding) plus optional `lengths[B]`; the values are
+        PER TERMINAL VARIABLE (what a reference sequence holds at `sequence[i][t]`), range-checked like the reference's
+        indexing would (IndexError).  Host tensors (e.g. a loader's pinned batch) are copied to the device
+        asynchronously and the pass never synchronises; device tensors cost one small device -> host copy.
         Returns a float64 tensor [B] on the parameters' device, differentiable w.r.t. every brick parameter."""
         engine = self._get_engine()
         if tokens is None:
             tokens, lengths = engine.pack_sequences([self._prepare_sequence(s) for s in sequences])
-        return engine.log_inside(tokens, lengths)
+            return engine.log_inside(tokens, lengths, prepacked=True)
+        return engine.log_inside(tokens, lengths, prepacked=False)
 
     def inside_batch(self, sequences=None, tokens=None, lengths=None):
         """Z for a batch in linear space (may underflow for long sequences exactly as exp(log Z) does)."""

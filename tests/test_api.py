@@ -229,7 +229,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"librbn_b200.so does not export {name}"
     assert declared == set(_lib.exported_symbols())
-    assert lib.rbn_abi_version() == 1
+    assert lib.rbn_abi_version() == _lib.ABI_VERSION == 2
     # descriptor validation happens without touching a device
     bad = _lib.RbnDesc(N=0, V=1, B=1, L=1, n_tvars=1, path=0, chunk_items=0, flags=0)
     assert lib.rbn_workspace_bytes(ctypes.byref(bad)) == 0
@@ -266,3 +266,59 @@ def test_engine_flattens_unmodified_reference_objects():
     np.testing.assert_array_equal(pr.detach().numpy(), po.detach().numpy())
     tok, lengths = InsideEngine(g).pack_sequences([g.tokenise("aaab")])
     assert tok[0, :, 0].tolist() == [0, 0, 0, 1]
+
+
+def _two_terminal_variable_model():
+    """One nonterminal variable (3 values) emitting TWO terminal variables (alphabets of 2 and 4 symbols)."""
+    rng = np.random.default_rng(0)
+    cell = pcfg.DiscreteCell(variable=pcfg.DiscreteNonTermVar(3), weights=rng.random((3, 3)),
+                             transitions=[pcfg.DiscreteTerminalTransition(weights=rng.random((2, 3)), term_idx=0),
+                                          pcfg.DiscreteTerminalTransition(weights=rng.random((4, 3)), term_idx=1),
+                                          pcfg.DiscreteBinaryNonTerminalTransition(weights=rng.random((3, 3, 3)))])
+    prior = pcfg.DiscretePrior(struc_weights=np.ones(1), prior_weights=[rng.random(3)])
+    return sequential.SequentialRBN(cells=[cell], prior=prior)
+
+
+def test_batched_tokens_are_per_variable_values_and_range_checked():
+    """log_inside_batch(tokens=...) takes PER-VARIABLE terminal values: they are shifted into the flat alphabet
+    like pack_sequences does, and a value outside its own variable's alphabet raises IndexError instead of silently
+    reading another variable's rows of T."""
+    e = InsideEngine(_two_terminal_variable_model())
+    seqs = [[[1, 3], [0, None], [1, 0]], [[0, 2]]]
+    flat, lengths = e.pack_sequences(seqs)
+    raw = torch.tensor([[[1, 3], [0, -1], [1, 0]], [[0, 2], [-1, -1], [-1, -1]]])
+    packed, _ = e.pack_tokens(raw, lengths)
+    assert packed.tolist() == flat.tolist()                      # second variable's values moved up by the first's 2 rows
+    assert packed[0, 0].tolist() == [1, 2 + 3] and packed[0, 1].tolist() == [0, -1]
+    with pytest.raises(IndexError):
+        e.pack_tokens(torch.tensor([[[2, 0]]]))                  # variable 0 has only 2 symbols
+    with pytest.raises(ValueError):
+        e.pack_tokens(torch.tensor([[0, 1]]))                    # one value per position, the model has two variables
+    # the flat functional entry checks the range against the rows of T before anything touches a device
+    from rbn_b200 import inside_logZ
+    W, T, pr = torch.rand(4, 4, 4), torch.rand(5, 4), torch.rand(4)
+    with pytest.raises(IndexError):
+        inside_logZ(W, T, pr, torch.tensor([[0, 5, 1]]))
+    with pytest.raises(ValueError):
+        inside_logZ(W, T, pr, torch.tensor([[0, 1, 1]]), lengths=torch.tensor([4]))
+
+
+def test_long_sequences_are_not_padded_onto_the_tensor_core_path():
+    from rbn_b200 import engine
+    assert engine._padded_cardinality(40, 100000, L=128) == 64
+    assert engine._padded_cardinality(40, 100000, L=130) == 40   # tensor-core kernels take at most 128 splits per span
+    big = _lib.RbnDesc(N=64, V=4, B=2, L=130, n_tvars=1, path=_lib.PATH_TCGEN05, chunk_items=0, flags=0)
+    lib = _lib.load()
+    assert lib.rbn_resolve_path(ctypes.byref(big)) == -4         # RBN_E_UNSUPPORTED
+    big.path = _lib.PATH_AUTO
+    assert lib.rbn_resolve_path(ctypes.byref(big)) == _lib.PATH_SIMT
+    ok = _lib.RbnDesc(N=64, V=4, B=2, L=129, n_tvars=1, path=_lib.PATH_AUTO, chunk_items=0, flags=0)
+    assert lib.rbn_resolve_path(ctypes.byref(ok)) == _lib.PATH_TCGEN05
+    # the split-sum cache only adds whole spans, never more than the batch has
+    base = lib.rbn_workspace_bytes(ctypes.byref(ok))
+    ok.cache_bytes = 10 ** 15
+    full = lib.rbn_workspace_bytes(ctypes.byref(ok))
+    spans = 2 * 129 * 128 // 2
+    assert 0 < full - base - spans * (64 * 64 * 2 + 4) < 4096
+    ok.cache_bytes = -1
+    assert lib.rbn_workspace_bytes(ctypes.byref(ok)) == 0

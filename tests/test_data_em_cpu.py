@@ -77,3 +77,13 @@ def test_m_step_normalises_counts_over_the_constrained_dims():
     em.m_step(m, counts, pseudo_count=1.0)
     np.testing.assert_allclose(m.a.p.detach().numpy()[:, 1], [1 / 3] * 3)
     np.testing.assert_allclose(m.a.p.detach().numpy()[:, 0], [2 / 7, 2 / 7, 3 / 7])
+
+
+def test_fewer_batches_than_ranks_still_gives_every_rank_the_same_count():
+    """drop_last=False with 1 batch and 4 ranks: the batch list wraps around, every rank gets one batch."""
+    seqs = [np.array([1, 2, 3]), np.array([1])]
+    lens = [len(data.LengthBucketedBatches(seqs, batch_size=16, rank=r, world=4, drop_last=False, pin_memory=False)) for r in range(4)]
+    assert lens == [1, 1, 1, 1]
+    seqs = [np.arange(1 + (i % 7)) for i in range(80)]
+    lens = [len(data.LengthBucketedBatches(seqs, batch_size=16, rank=r, world=4, drop_last=False, pin_memory=False)) for r in range(4)]
+    assert len(set(lens)) == 1 and lens[0] == 2

@@ -35,6 +35,14 @@ def _worker(rank, world, port, W, T, pr, tok, lengths, q):
     lz, gW, gT, gP = O.flat_inside_with_grads(W, T, pr, t.numpy()[:, :, None], ln.numpy())
     D.allreduce_counts([gW, gT, gP])
     full = D.gather_logZ(lz, idx, tok.shape[0])
+    # the same counts through the micro-batched, overlapped reducer (two micro-batches per rank)
+    red = D.CountReducer()
+    half = t.shape[0] // 2
+    for sl in (slice(0, half), slice(half, None)):
+        _, *g = O.flat_inside_with_grads(W, T, pr, t.numpy()[sl][:, :, None], ln.numpy()[sl])
+        red.add(g)
+    for a, b in zip(red.result(), (gW, gT, gP)):
+        assert torch.allclose(a, b, rtol=1e-10, atol=1e-12)
     if rank == 0:
         q.put((full.numpy(), gW.numpy(), gT.numpy(), gP.numpy()))
     dist.barrier()
