@@ -87,6 +87,10 @@ struct TcTune {
     int bwd_sms0;       // RBN_TC_BWD_SMS0  SMs of the {split-sum, prep, gY} partition in the outside pass (even)
     int nslot;          // RBN_TC_SLOTS     per-chunk buffer copies
     int k3_stream;      // RBN_TC_K3_STREAM 0: gY GEMM beside the split-sum, 1: beside the child-gradient kernel
+    int hints;          // RBN_TC_HINTS     L2 eviction-priority hints on the bulk tensor copies (bit mask): 1 outside-chart
+                        //                  reduce-adds evict_last (the second contribution to a cell of a diagonal should find the
+                        //                  line in L2); 2 streamed stores (Y, gY) evict_first; 4 rule / count GEMM operand streams
+                        //                  (Y evict_first, W evict_last); 8 second read of gY in the child-gradient kernel evict_first
 };
 const TcTune& tc_tune();
 int device_sm_count();

@@ -23,6 +23,8 @@ struct GemmShape {
     // 2-CTA kernel only: every unit reports partial = true (N = 512: the max-shift epilogue needs both halves of a row,
     // so all tiles add into the fp32 buffer that k_rule_finalize turns into chart cells)
     int all_partial;
+    // L2 eviction priority of the two operand streams (ptx::kEvict*; 0 = no hint)
+    unsigned long long hint_a, hint_b;
 };
 
 struct GemmUnit {
@@ -314,19 +316,21 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     uint8_t* sA = smem + stage * S::STAGE_BYTES;
                     uint8_t* sB = sA + S::A_BYTES;
                     if (leader) ptx::mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
+                    const uint64_t ha = shape.hint_a ? shape.hint_a : ptx::kEvictNormal;
+                    const uint64_t hb = shape.hint_b ? shape.hint_b : ptx::kEvictNormal;
                     if (!A_MN) {
-                        ptx::tma_load_2d_pair(sA, &tmA, &full[stage], kb * kBK, row0);
+                        ptx::tma_load_2d_pair_hint(sA, &tmA, &full[stage], kb * kBK, row0, ha);
                     } else {
 #pragma unroll
                         for (int a = 0; a < kBM / 64; ++a)
-                            ptx::tma_load_2d_pair(sA + a * 8192, &tmA, &full[stage], row0 + a * 64, kb * kBK);
+                            ptx::tma_load_2d_pair_hint(sA + a * 8192, &tmA, &full[stage], row0 + a * 64, kb * kBK, ha);
                     }
                     if (!B_MN) {
-                        ptx::tma_load_2d_pair(sB, &tmB, &full[stage], kb * kBK, col0);
+                        ptx::tma_load_2d_pair_hint(sB, &tmB, &full[stage], kb * kBK, col0, hb);
                     } else {
 #pragma unroll
                         for (int a = 0; a < HALF_N / 64; ++a)
-                            ptx::tma_load_2d_pair(sB + a * 8192, &tmB, &full[stage], col0 + a * 64, kb * kBK);
+                            ptx::tma_load_2d_pair_hint(sB + a * 8192, &tmB, &full[stage], col0 + a * 64, kb * kBK, hb);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }

@@ -284,7 +284,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
               const __grid_constant__ CUtensorMap tmLC1, const __grid_constant__ CUtensorMap tmRC1,   // second K-slab (rows = Kpad - 64)
               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYtail,
               int N, int L, int Lp, int w, int m0, int cnt, int stages, const int* __restrict__ lengths,
-              const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e, int nslots) {
+              const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e, int nslots, uint64_t y_pol) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int Kpad = ((w - 1) + 15) & ~15;
@@ -506,7 +506,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                         ptx::tmem_ld32(taddr + c0, v);
                         ptx::tmem_ld32(taddr + c0 + 32, v + 32);
                         ptx::tmem_ld_wait();
-                        ptx::stage_store_tile(ybuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true);
+                        ptx::stage_store_tile(ybuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
                         ++nstore;
                     }
                     ptx::tc_fence_before();
@@ -538,7 +538,8 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                const __grid_constant__ CUtensorMap tmAR,    // the SAME chart as [b*L + start][end][N], box {128, 1, 32}: right children
                const __grid_constant__ CUtensorMap tmALt,   // same views, tail_rows instead of 32: last chunk of a span's splits
                const __grid_constant__ CUtensorMap tmARt,
-               const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp) {
+               const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp,
+               uint64_t red_pol, uint64_t gy2_pol) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* rbuf = smem + kK5Stages * kK5StageBytes;        // [2 groups][2] x 16 KB tiles [32 splits][128 nonterminals] fp32
@@ -600,8 +601,9 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                             ptx::tma_load_2d(sA, &tmGYk, &full[stage], kb * 64, t * N + h * 128);
                             ptx::tma_load_2d(sB, &tmRC, &full[stage], kb * 64, rc_row);
                         } else {
-                            ptx::tma_load_2d(sA, &tmGYm, &full[stage], h * 128, t * N + kb * 64);
-                            ptx::tma_load_2d(sA + 8192, &tmGYm, &full[stage], h * 128 + 64, t * N + kb * 64);
+                            // second (and last) read of this span's gY: nothing will want these lines again
+                            ptx::tma_load_2d_hint(sA, &tmGYm, &full[stage], h * 128, t * N + kb * 64, gy2_pol);
+                            ptx::tma_load_2d_hint(sA + 8192, &tmGYm, &full[stage], h * 128 + 64, t * N + kb * 64, gy2_pol);
                             ptx::tma_load_2d(sB, &tmLC, &full[stage], kb * 64, lc_row);
                         }
                         if (++stage == kK5Stages) { stage = 0; phase ^= 1; }
@@ -707,8 +709,8 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                         // left children (i, j): consecutive rows of start i.  Right children (j, k): row `end = k` of the
                         // consecutive starts j -- both land in ONE chart, so the two contributions a cell receives per
                         // diagonal meet in L2 (they are issued within a few microseconds of each other)
-                        if (kind == 0) ptx::tma_reduce_add_2d(last ? &tmALt : &tmAL, tile, h * 128, rowL + c0);
-                        else ptx::tma_reduce_add_3d(last ? &tmARt : &tmAR, tile, h * 128, k, b * L + (i + 1) + c0);
+                        if (kind == 0) ptx::tma_reduce_add_2d(last ? &tmALt : &tmAL, tile, h * 128, rowL + c0, red_pol);
+                        else ptx::tma_reduce_add_3d(last ? &tmARt : &tmAR, tile, h * 128, k, b * L + (i + 1) + c0, red_pol);
                         ptx::bulk_commit();
                     }
                     ++nred;
@@ -881,7 +883,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box {64, 128}
          const __grid_constant__ CUtensorMap tmW,     // Wk [N*N rows][N], box {64, 128}
          const __grid_constant__ CUtensorMap tmOut,   // gY [cnt rows][N*N], box {64, 128}
-         int N, int supertiles, int ranges) {
+         int N, int supertiles, int ranges, uint64_t out_pol, uint64_t w_pol) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int kblocks = N / 64;
@@ -941,7 +943,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
                     for (int kb = 0; kb < kblocks; ++kb) {
                         ptx::mbar_wait(&empty[stage], phase ^ 1);
                         if (leader) ptx::mbar_expect_tx(&full[stage], 2 * 16384);
-                        ptx::tma_load_2d_pair(sBring + stage * 16384, &tmW, &full[stage], kb * 64, nt * 256 + (int)rank * 128);
+                        ptx::tma_load_2d_pair_hint(sBring + stage * 16384, &tmW, &full[stage], kb * 64, nt * 256 + (int)rank * 128, w_pol);
                         if (++stage == STG) { stage = 0; phase ^= 1; }
                     }
             }
@@ -1002,7 +1004,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
                 ptx::mbar_arrive_leader(&tempty[buf]);           // the accumulator is in registers: release it early
 #pragma unroll
                 for (int c0 = 0; c0 < 128; c0 += 64) {
-                    ptx::stage_store_tile<NBUF>(mybuf, &tmOut, nt * 256 + grp * 128 + c0, st * 256 + (int)rank * 128, row, v + c0, nstore, 3 + grp, issuer, true);
+                    ptx::stage_store_tile<NBUF>(mybuf, &tmOut, nt * 256 + grp * 128 + c0, st * 256 + (int)rank * 128, row, v + c0, nstore, 3 + grp, issuer, true, out_pol);
                     ++nstore;
                 }
                 if (++buf == 2) { buf = 0; bphase ^= 1; }
@@ -1343,6 +1345,7 @@ k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, const int* __re
 // =======================================================================================================================
 // drivers
 // =======================================================================================================================
+static constexpr int kDefaultHints = 0;
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return (e && *e) ? atoi(e) : dflt;
@@ -1359,6 +1362,7 @@ const TcTune& tc_tune() {
         t.bwd_sms0 = env_int("RBN_TC_BWD_SMS0", 74) & ~1;
         t.nslot = env_int("RBN_TC_SLOTS", 3);
         t.k3_stream = env_int("RBN_TC_K3_STREAM", 0) != 0;
+        t.hints = env_int("RBN_TC_HINTS", kDefaultHints);
         if (t.groups < 1) t.groups = 1;
         if (t.nslot < 2) t.nslot = 2;
         if (t.nslot > 8) t.nslot = 8;
@@ -1616,7 +1620,8 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     if (half_sm && grid > sms) grid = sms;
     { ProfScope ps(KC_SPLITSUM, st);
       RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, kK1Threads, smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
-                                         c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y_of(u), c.e_of(u), nslots)); }
+                                         c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y_of(u), c.e_of(u), nslots,
+                                         (uint64_t)((tc_tune().hints & 2) ? ptx::kEvictFirst : ptx::kEvictNormal))); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
 }
@@ -1674,6 +1679,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         rc = make_tmap_2d(&tmB2, c.wt, NN, (uint64_t)c.N, NN * 2, BN / 2);
         if (rc) return rc;
         GemmShape shape2{(cnt + 255) / 256, n_tiles, (int)(NN / 64), 0, 1, 0};
+        if (tc_tune().hints & 4) { shape2.hint_a = ptx::kEvictFirst; shape2.hint_b = ptx::kEvictLast; }   // Y streams, W is reused
         // wave quantisation: the last, partial wave of tiles is split along K so that all CTA pairs stay busy
         const int pairs = sms / 2, T = shape2.m_tiles * n_tiles;
         const int full = (T / pairs) * pairs, r = T - full;
@@ -1756,7 +1762,9 @@ static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
         RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         int units2 = supertiles * ranges2;
         int np = units2 < pairs ? units2 : pairs;
-        { ProfScope ps(KC_GY, st); kern<<<2 * np, 384, smem2, st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges2); }
+        { ProfScope ps(KC_GY, st); kern<<<2 * np, 384, smem2, st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges2,
+                                                                     (uint64_t)((tc_tune().hints & 2) ? ptx::kEvictFirst : ptx::kEvictNormal),
+                                                                     (uint64_t)((tc_tune().hints & 4) ? ptx::kEvictLast : ptx::kEvictNormal)); }
         RBN_LAUNCH_CHECK("k_tc_gy2");
         return RBN_OK;
     }
@@ -1789,6 +1797,7 @@ static int launch_k4_bn(TcCtx& c, const Unit& u, float* gW, cudaStream_t st, int
     }
     if (use_pairs() && BN % 128 == 0) {
         GemmShape shape2{(int)(NN / 256), n_tiles, (cnt + 63) / 64, 0, 1, 0};
+        if (tc_tune().hints & 4) shape2.hint_a = ptx::kEvictFirst;                                       // last read of Y
         {   // K-split so that the work units fill whole waves of CTA pairs (256 tiles on 74 pairs = 3.46 waves otherwise)
             const int pairs = sms / 2, tiles = (int)(NN / 256) * n_tiles;
             int best = 1;
@@ -1844,7 +1853,9 @@ static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     { ProfScope ps(KC_CHILD, st);
       RBN_CUDA_CHECK(launch_maybe_paired(k_tc_childgrad, paired, grid, 384, smem, st, tmGYk, tmGYm, tmRC, tmLC, N, L, c.Lp, w, m0, cnt,
                                          c.lengths, tmAL, tmAR, tmALt, tmARt, (const int*)c.ce, (const int*)c.e_of(u),
-                                         (const int*)c.gexp(u.slot))); }
+                                         (const int*)c.gexp(u.slot),
+                                         (uint64_t)((tc_tune().hints & 1) ? ptx::kEvictLast : ptx::kEvictNormal),
+                                         (uint64_t)((tc_tune().hints & 8) ? ptx::kEvictFirst : ptx::kEvictNormal))); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;
 }

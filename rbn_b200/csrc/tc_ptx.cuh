@@ -51,19 +51,35 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
 
+// L2 eviction-priority policies for the .L2::cache_hint operand of bulk tensor copies (the fixed encodings
+// createpolicy.fractional.L2::evict_{normal,first,last} with fraction 1.0 produces)
+static constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;    // streamed once: do not displace what is reused
+static constexpr uint64_t kEvictLast = 0x14F0000000000000ull;     // reused soon: keep
+
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int x, int y, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(pol) : "memory");
+}
+
 // smem (128-byte swizzled tile) -> global, bulk-group completion
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
 }
-// smem tile (no swizzle) += into global (fp32 add performed at L2), bulk-group completion
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int x, int y) {
-    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* src, int x, int y, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(x), "r"(y), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int x, int y, int z) {
-    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z) : "memory");
+// smem tile (no swizzle) += into global (fp32 add performed at L2), bulk-group completion
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int x, int y, uint64_t pol) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(x), "r"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int x, int y, int z, uint64_t pol) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -75,7 +91,8 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // `nstore` counts the stores issued so far by this CTA (selects the ping-pong buffer).
 template <int NBUF = 2>
 __device__ __forceinline__ void stage_store_tile(uint8_t* bufs, const CUtensorMap* tm, int x, int y, int row,
-                                                 const float* v, uint32_t nstore, uint32_t bar_id, bool issuer, bool active) {
+                                                 const float* v, uint32_t nstore, uint32_t bar_id, bool issuer, bool active,
+                                                 uint64_t pol = kEvictNormal) {
     // One barrier per tile: buffer (nstore & 1) was declared free by the barrier of the previous call (before which
     // the issuer had waited for the store that last read it), so it can be written straight away.
     uint8_t* buf = bufs + (NBUF == 2 ? (nstore & 1) * 16384 : 0);
@@ -94,7 +111,7 @@ __device__ __forceinline__ void stage_store_tile(uint8_t* bufs, const CUtensorMa
     if (NBUF == 2 && issuer) bulk_wait_read<0>();    // the previous store (other buffer) has been read: free after the barrier
     named_bar_sync(bar_id, 128);
     if (issuer && active) {
-        tma_store_2d(tm, buf, x, y);
+        tma_store_2d_hint(tm, buf, x, y, pol);
         bulk_commit();
     }
 }
@@ -198,6 +215,11 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int x, int y, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void mma_f16_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
