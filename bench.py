@@ -369,6 +369,8 @@ def run_ours(args, wl, secondary=False):
         count_check = dict(binary_rules=float((grads[0].double() * Wd.detach().double()).sum()),
                            expected=float(world * (len_np - 1).sum()))
     del lz, grads
+    from rbn_b200 import release_workspaces
+    release_workspaces()
     gc.collect()
     torch.cuda.empty_cache()
 
@@ -406,6 +408,7 @@ def run_ours(args, wl, secondary=False):
     h2d = tok_pin.numel() * 4 + len_pin.numel() * 4
     d2h = 8
     del model, params
+    release_workspaces()
     gc.collect()
     torch.cuda.empty_cache()
 
@@ -425,7 +428,7 @@ def run_ours(args, wl, secondary=False):
     if N >= 64 and prof["split_sum"][1]:
         spans = B * (L * (L - 1) // 2)                         # spans of width >= 2 per pass
         splits = B * ((L ** 3 - L) // 6)
-        units = max(1, prof["rule_gemm"][1] - prof["rule_finalize"][1])      # (diagonal, chunk) units of the inside passes
+        units = max(1, prof["rule_gemm"][1])                   # (diagonal, chunk) units of the inside passes
         k1_passes = prof["split_sum"][1] / units               # 1 = every split-sum kept for the outside pass, 2 = all recomputed
         y_bytes = 2.0 * N * N * spans
         row_bytes = 2.0 * splits * 2 * N                       # fp16 child rows streamed once per diagonal

@@ -8,4 +8,4 @@ include/rbn_b200.h (librbn_b200.so); there is no CPU fallback.
 __version__ = "0.1.0"
 
 from . import base, sequential, pcfg, util, tmap, data, em  # noqa: F401
-from .engine import InsideEngine, inside_logZ  # noqa: F401
+from .engine import InsideEngine, inside_logZ, release_workspaces  # noqa: F401

@@ -140,13 +140,14 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->acc = take(ns * chunk * N * sizeof(float));
         // split-sum cache: whole spans only, never more than the batch has, off in the two-stream schedules (their
         // forward and backward passes cut the diagonals differently)
-        const size_t per_span = N * N * sizeof(__half) + sizeof(int);
+        const size_t per_span = N * N * sizeof(__half) + sizeof(int) + N * sizeof(__half);
         size_t cap = tune.overlap ? 0 : (size_t)d->cache_bytes / per_span;
         const size_t all_spans = B * (L * (L - 1) / 2);
         if (cap > all_spans) cap = all_spans;
         o->cache_spans = (long long)cap;
         o->ycache = take(cap * N * N * sizeof(__half));
         o->ycache_e = take(cap * sizeof(int));
+        o->gabs_all = take(cap * N * sizeof(__half));
     }
     o->total = off;
     return true;

@@ -68,6 +68,7 @@ struct WsLayout {
     // first) and the outside pass reads them back instead of recomputing them; E_m of the same spans beside it
     size_t ycache;      // half [cache_spans][N*N]
     size_t ycache_e;    // int32 [cache_spans]
+    size_t gabs_all;    // half [cache_spans][N]  upstream-gradient rows of the kept spans (the count GEMM over them runs once, last)
     long long cache_spans;
     size_t total;
     int Lp;

@@ -1296,12 +1296,14 @@ __global__ void k_tc_emission_bwd(int N, int L, int Lp, int nt, const int* __res
 // One WARP per span (8 spans per CTA), N / 32 values per lane: no block-level synchronisation, an eighth of the CTAs.
 static constexpr int kPrepWarps = 8;
 __global__ void __launch_bounds__(kPrepWarps * 32)
-k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, const int* __restrict__ lengths, const int* __restrict__ ce,
+k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, const int* __restrict__ lengths, const int* __restrict__ ce,
          const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
          __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);
     if (t >= rows) return;                          // rows = cnt rounded up to 64: the pad rows are written as zeros
+    // gabs_rows: rows of `gabs` this launch owns (= rows for a slot buffer; = cnt when the rows are packed behind the
+    // previous unit's in the deferred-count array, where the next unit's rows follow immediately)
     const int nI = L - w + 1;
     const int m = m0 + t;
     const int b = m / nI, i = m - b * nI;
@@ -1336,7 +1338,7 @@ k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, const int* __re
             const int a = q * 32 + lane;
             ghat[(size_t)t * N + a] = __float2half_rn(ldexpf(gs[q], -eg));
             const float ga = fminf(fmaxf(ldexpf(g[q], -kGabsShift), -65504.f), 65504.f);
-            gabs[(size_t)t * N + a] = __float2half_rn(ga);
+            if (t < gabs_rows) gabs[(size_t)t * N + a] = __float2half_rn(ga);     // (cached spans: packed rows, no pad rows)
         }
     }
     if (lane == 0) gexp[t] = eg;
@@ -1398,6 +1400,9 @@ struct TcCtx {
     int* gexp(int s) const { return (int*)(base + ws->gexp) + (size_t)s * chunk; }
     // split-sum and span exponents E_m of a unit: in the cache when the unit has a place there, else in its slot
     __half* y_of(const Unit& u) const { return u.coff >= 0 ? (__half*)(base + ws->ycache) + (size_t)u.coff * N * N : y(u.slot); }
+    // absolutely scaled upstream gradient rows of a unit: cached units keep them (packed like their Y) until the ONE count
+    // GEMM over all cached spans at the end of the outside pass
+    __half* gabs_of(const Unit& u) const { return u.coff >= 0 ? (__half*)(base + ws->gabs_all) + (size_t)u.coff * N : gabs(u.slot); }
     int* e_of(const Unit& u) const { return u.coff >= 0 ? (int*)(base + ws->ycache_e) + (size_t)u.coff : item_e(u.slot); }
 };
 
@@ -1526,8 +1531,8 @@ static void diag_units(std::vector<Unit>& out, int w, int L, int B, int groups, 
 // Every unit of a pass, per diagonal.  The inside and the outside pass of one workspace build the SAME plan (same
 // descriptor, same `active`), so a unit's place in the split-sum cache is known to both without any device state.
 // The cache goes to the widest diagonals first: their recompute is the most expensive one (most splits per span).
-static void plan_units(std::vector<std::vector<Unit>>& by_w, int L, int B, const int* active, int groups, int chunk, int wave,
-                       long long cache_spans) {
+static long long plan_units(std::vector<std::vector<Unit>>& by_w, int L, int B, const int* active, int groups, int chunk, int wave,
+                            long long cache_spans) {
     by_w.assign((size_t)L + 1, std::vector<Unit>());
     int counter = 0;
     for (int w = 2; w <= L; ++w) diag_units(by_w[w], w, L, active ? active[w] : B, groups, chunk, wave, 1, counter);
@@ -1538,6 +1543,7 @@ static void plan_units(std::vector<std::vector<Unit>>& by_w, int L, int B, const
             u.coff = used;
             used += u.cnt;
         }
+    return used;           // spans kept: they are rows [0, used) of the cache, in the order the outside pass visits them
 }
 
 template <class... KArgs, class... Args>
@@ -1751,8 +1757,18 @@ static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
     }
     if (use_pairs()) {
         int ntiles2 = (int)(NN / 256), pairs = sms / 2;
+        // A unit = one 256-span supertile x one range of Wk tiles; it loads its gradient rows once (about one Wk tile's
+        // worth of bytes) and streams its tiles.  Pick the number of ranges that minimises rounds x (tiles + 1): enough units
+        // to fill the CTA pairs evenly when a diagonal has few supertiles, without reloading the rows needlessly.
         int ranges2 = 1;
-        while (ranges2 < 16 && supertiles * ranges2 < 2 * pairs && ntiles2 % (ranges2 * 2) == 0 && ntiles2 / (ranges2 * 2) >= 8) ranges2 *= 2;
+        {
+            double best = 1e30;
+            for (int r = 1; r <= 64 && ntiles2 % r == 0 && ntiles2 / r >= 4; r *= 2) {
+                const long long units = (long long)supertiles * r;
+                const double cost = (double)((units + pairs - 1) / pairs) * (ntiles2 / r + 1.0);
+                if (cost < best * 0.995) { best = cost; ranges2 = r; }
+            }
+        }
         static const int deep = env_int("RBN_TC_GY_STAGES", 6);       // N <= 256: 6 ring stages (4: the former setting)
         const bool big = c.N > 256;
         const int nbuf = big ? 1 : 2;
@@ -1787,7 +1803,7 @@ static int launch_k4_bn(TcCtx& c, const Unit& u, float* gW, cudaStream_t st, int
     CUtensorMap tmA, tmB;
     int rc = make_tmap_2d(&tmA, c.y_of(u), NN, (uint64_t)cnt, NN * 2, 64);            // MN-major A: [K=items][M=(b,c)]
     if (rc) return rc;
-    rc = make_tmap_2d(&tmB, c.gabs(u.slot), (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 64);   // MN-major B: [K=items][N=a]
+    rc = make_tmap_2d(&tmB, c.gabs_of(u), (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 64);   // MN-major B: [K=items][N=a]
     if (rc) return rc;
     EpiCounts epi{gW, c.N, BN};
     const int n_tiles = c.N / BN;
@@ -1951,7 +1967,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     std::vector<int> last_prev(groups, -1), last_cur(groups, -1);
     int counter = 0;
     std::vector<std::vector<Unit>> plan;
-    plan_units(plan, L, B, overlap ? nullptr : active, groups, c.chunk, wave, overlap ? 0 : ws.cache_spans);
+    const long long kept = plan_units(plan, L, B, overlap ? nullptr : active, groups, c.chunk, wave, overlap ? 0 : ws.cache_spans);
     for (int w = L; w >= 2 && !rc; --w) {
         const size_t first = units.size();
         for (Unit u : plan[w]) { u.slot = counter++ % ws.nslot; units.push_back(u); }
@@ -1965,18 +1981,20 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
             if (last_prev[u.g] >= 0) S.wait(0, evK5[last_prev[u.g]]);            // alpha of this diagonal is complete
             int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
             { ProfScope ps(KC_PREP, S.st[0]);
-              k_prep_g<<<(pg + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, pg, lengths, c.ce, c.e_of(u), c.wexp, c.alpha,
-                                             c.ghat(u.slot), c.gabs(u.slot), c.gexp(u.slot)); }
+              k_prep_g<<<(pg + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, pg, u.coff >= 0 ? cnt : pg, lengths, c.ce, c.e_of(u), c.wexp, c.alpha,
+                                             c.ghat(u.slot), c.gabs_of(u), c.gexp(u.slot)); }
             RBN_LAUNCH_CHECK("k_prep_g");
             S.wait(1, S.record(0));
+            // expected rule counts: spans whose Y sits in the cache wait for ONE count GEMM over all of them after the
+            // last diagonal (K = all kept spans instead of one diagonal's: whole waves of tiles, one pass over gW)
             if (s3 == 0) {
                 if ((rc = launch_k3(c, u, S.st[0], S.sms[0]))) break;
                 cudaEvent_t e3 = S.record(0);
-                if ((rc = launch_k4(c, u, gW, S.st[1], S.sms[1]))) break;
+                if (u.coff < 0 && (rc = launch_k4(c, u, gW, S.st[1], S.sms[1]))) break;
                 S.wait(1, e3);
             } else {
                 if ((rc = launch_k3(c, u, S.st[1], S.sms[1]))) break;
-                if ((rc = launch_k4(c, u, gW, S.st[1], S.sms[1]))) break;
+                if (u.coff < 0 && (rc = launch_k4(c, u, gW, S.st[1], S.sms[1]))) break;
             }
             if ((rc = launch_k5(c, u, S.st[1], S.sms[1], S.pair_launch))) break;
             evK5[ui] = S.record(1);
@@ -1987,6 +2005,12 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     int rc2 = S.end();
     if (rc) return rc;
     if (rc2) return rc2;
+    if (kept > 0) {
+        Unit all;
+        all.w = 0; all.g = 0; all.m0 = 0; all.slot = 0; all.coff = 0;
+        all.cnt = (int)kept;
+        if ((rc = launch_k4(c, all, gW, st, sm_count()))) return rc;
+    }
     { ProfScope ps(KC_EMISSION, st); k_tc_emission_bwd<<<B * L, 128, 0, st>>>(N, L, c.Lp, d->n_tvars, tokens, lengths, c.ce, c.alpha, gT); }
     RBN_LAUNCH_CHECK("k_emission_bwd");
     return RBN_OK;

@@ -44,6 +44,33 @@ def _cache_budget(dev, base_bytes):
     return max(0, int(free + reusable - base_bytes - 4e9 - 0.03 * total))
 
 
+# One retired workspace per device is kept for the next pass (the split-sum cache makes a workspace most of the device's
+# memory: handing that back to torch's allocator and asking for it again every micro-batch invites fragmentation -- a
+# 67 MB tensor carved out of the freed block forces a fresh 150 GB cudaMalloc).  Same-stream reuse, like the allocator's.
+_WS_POOL = {}
+
+
+def _pool_take(dev, at_least):
+    t = _WS_POOL.get(dev.index)
+    if t is not None and t.numel() >= at_least:
+        del _WS_POOL[dev.index]
+        return t
+    return None
+
+
+def _pool_give(t):
+    if t is None or not t.is_cuda:
+        return
+    cur = _WS_POOL.get(t.device.index)
+    if cur is None or cur.numel() < t.numel():
+        _WS_POOL[t.device.index] = t
+
+
+def release_workspaces():
+    """Give the retained workspaces back to torch's allocator (and, with torch.cuda.empty_cache(), to the device)."""
+    _WS_POOL.clear()
+
+
 class _Pass:
     """One forward pass on the device: inputs, workspace (holds the chart) and outputs.  `keep_split_sums`: let the
     inside pass keep as many per-span split-sums as device memory allows, for the outside pass to read back."""
@@ -58,8 +85,11 @@ class _Pass:
         nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
         if nbytes == 0:
             _lib.check(-1, "rbn_workspace_bytes")
+        self._owner = _pool_take(dev, nbytes + 1024)
         if keep_split_sums and lib.rbn_resolve_path(ctypes.byref(self.desc)) == _lib.PATH_TCGEN05:
-            self.desc.cache_bytes = _cache_budget(dev, nbytes)
+            # a retained workspace is used as it is (whatever cache fits in it); otherwise size one from the free memory
+            budget = (self._owner.numel() - nbytes - 16384) if self._owner is not None else _cache_budget(dev, nbytes)
+            self.desc.cache_bytes = max(0, budget)
             nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
         # ragged batch: sort by length (longest first) so that diagonal w only visits the sequences that reach it
         # (rbn_inside_forward_sorted); `order[k]` = original index of the k-th sorted sequence, `pos[b]` its inverse
@@ -75,7 +105,9 @@ class _Pass:
             srt = len_host[order]
             self.active = (ctypes.c_int32 * (L + 1))(*[int((srt >= w).sum()) for w in range(L + 1)])
         self.W, self.T, self.prior, self.tokens, self.lengths = W, T, prior, tokens, lengths
-        self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        if self._owner is None:
+            self._owner = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        self.workspace = self._owner[:nbytes + 1024]
         if os.environ.get("RBN_DEBUG_POISON") == "1":     # tests: whatever the kernels read without having written shows as NaN
             self.workspace.fill_(0xFF)
         self.ws_off = (-self.workspace.data_ptr()) % 1024
@@ -83,6 +115,22 @@ class _Pass:
         self.logZ = torch.empty(B, dtype=torch.float32, device=dev)
         self.zroot = torch.empty(B, dtype=torch.float32, device=dev)
         self.rootexp = torch.empty(B, dtype=torch.float32, device=dev)
+
+    def release(self):
+        """Hand the workspace on to the next pass (the chart and the kept split-sums are gone after this)."""
+        owner, self._owner, self.workspace = self._owner, None, None
+        _pool_give(owner)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:          # interpreter shutdown
+            pass
+
+    def _live(self):
+        if self.workspace is None:
+            raise _lib.RbnError("this pass has handed its workspace on (it does so after its backward pass unless a `holder` "
+                                "keeps it for chart export): run the inside pass again, or pass holder=[] to inside_logZ")
 
     def _ws(self):
         return ctypes.c_void_p(self.workspace.data_ptr() + self.ws_off)
@@ -103,6 +151,7 @@ class _Pass:
             self.logZ, self.zroot, self.rootexp = (t.index_select(0, self.pos) for t in (self.logZ, self.zroot, self.rootexp))
 
     def backward(self, coef):
+        self._live()
         lib = _lib.load()
         dev = self.W.device
         gW = torch.empty_like(self.W)
@@ -122,6 +171,7 @@ class _Pass:
 
     def export_chart(self, seq):
         """float64 [n(n+1)/2, N] linear-space chart of sequence `seq` in TMap row order (device tensor)."""
+        self._live()
         lib = _lib.load()
         if self.pos is not None:
             seq = int(self.pos[seq])          # position of the caller's sequence in the length-sorted batch
@@ -146,7 +196,9 @@ class _InsideFn(torch.autograd.Function):
                   lengths.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous(), path, chunk_items,
                   keep_split_sums=any(ctx.needs_input_grad[:3]), len_host=len_host)
         p.forward()
-        holder.append(p)
+        ctx.release = holder is None       # nobody can ask this pass for its chart: its workspace moves on after backward
+        if holder is not None:
+            holder.append(p)
         ctx.p = p
         ctx.linear = linear
         ctx.in_meta = [(t.dtype, t.device) for t in (W, T, prior)]
@@ -181,6 +233,8 @@ class _InsideFn(torch.autograd.Function):
         else:
             coef = torch.where(pos, g, torch.zeros_like(g))     # log Z = -inf has no gradient
         gW, gT, gP = ctx.p.backward(coef)
+        if ctx.release:
+            ctx.p.release()
         outs = []
         for t, (dt, dv) in zip((gW, gT, gP), ctx.in_meta):
             if post is not None:
@@ -261,8 +315,7 @@ def inside_logZ(W, T, prior, tokens, lengths=None, linear=False, path=_lib.PATH_
         L = int(tokens.shape[1])
         Np = _padded_cardinality(int(W.shape[0]), int(tokens.shape[0]) * L * (L - 1) // 2, L)
         W, T, prior = _pad_grammar(W, T, prior, Np)
-    return _InsideFn.apply(W, T, prior, tokens, lengths, linear, holder if holder is not None else [], path, chunk_items,
-                           len_host)
+    return _InsideFn.apply(W, T, prior, tokens, lengths, linear, holder, path, chunk_items, len_host)
 
 
 def viterbi(W, T, prior, tokens, lengths=None):
@@ -461,11 +514,8 @@ class InsideEngine:
         if not prepacked:
             tokens, lengths = self.pack_tokens(tokens, lengths)
         W, T, prior = self.flatten()
-        holder = []
-        out = inside_logZ(W, T, prior, tokens, lengths, linear=False, path=self.path, chunk_items=self.chunk_items,
-                          holder=holder)
-        self.last_pass = holder[0]
-        return out
+        self.last_pass = None
+        return inside_logZ(W, T, prior, tokens, lengths, linear=False, path=self.path, chunk_items=self.chunk_items)
 
     def viterbi(self, sequences):
         """Best derivation of reference-style sequences under the model: (logP [B], trees over (variable, value) symbols)."""

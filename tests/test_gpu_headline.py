@@ -100,8 +100,9 @@ def test_headline_shape_vs_oracle(name):
 @pytest.mark.parametrize("N,L,B,chunk", [(64, 24, 5, 128), (256, 12, 3, 0)])
 def test_split_sum_cache_does_not_change_results(monkeypatch, N, L, B, chunk):
     """RbnDesc.cache_bytes (the inside pass keeps Y for the outside pass) is a pure speed / space trade: whole, partial
-    (only the widest diagonals fit) and no cache give bit-identical gradients; workspace memory is poisoned with NaN
-    bytes first, so a span beyond its sequence whose Y was never written would show."""
+    (only the widest diagonals fit) and no cache give the same gradients (the kept spans' expected counts come from ONE
+    count GEMM at the end instead of one per diagonal, so sums are ordered differently); workspace memory is poisoned with
+    NaN bytes first, so a span beyond its sequence whose Y was never written would show."""
     from oracle import inside_oracle as O
     from rbn_b200 import inside_logZ, _lib
     W, T, pr = O.synthetic_grammar(N, 16, seed=3)
@@ -117,9 +118,10 @@ def test_split_sum_cache_does_not_change_results(monkeypatch, N, L, B, chunk):
         lz.sum().backward()
         res.append((lz.detach().cpu().numpy(), Wt.grad.cpu().numpy(), Tt.grad.cpu().numpy(), pt.grad.cpu().numpy()))
     assert np.isfinite(res[0][1]).all()
-    for r in res[1:]:
-        for a, b in zip(res[0], r):
-            np.testing.assert_array_equal(a, b)
+    for r in res[1:]:         # equal up to the order of the atomic adds of K-split partial sums (and of the deferred count GEMM)
+        np.testing.assert_allclose(r[0], res[0][0], rtol=1e-6)
+        for a, b in zip(res[0][1:], r[1:]):
+            assert metrics(b, a)["max_rel"] <= 2e-5 and metrics(b, a)["l2_rel"] <= 2e-5
     ref, gW, gT, gP = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths)
     assert np.abs(res[0][0] - ref.numpy()).max() <= LOGZ_RTOL * np.abs(ref.numpy()).max()
     assert metrics(res[0][1], gW.numpy())["max_rel"] <= GRAD_RTOL
