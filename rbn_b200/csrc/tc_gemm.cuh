@@ -25,6 +25,10 @@ struct GemmShape {
     int all_partial;
     // L2 eviction priority of the two operand streams (ptx::kEvict*; 0 = no hint)
     unsigned long long hint_a, hint_b;
+    // 2-CTA kernel with segmented accumulation only: every unit of the launch is at most one segment long, so a unit needs
+    // ONE accumulator and consecutive units alternate between the two -- the epilogue of a unit (partial sums -> red.add)
+    // runs behind the next unit's MMAs instead of in front of them
+    int short_units;
 };
 
 struct GemmUnit {
@@ -266,9 +270,9 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
     uint64_t* empty = full + STAGES;
-    uint64_t* tfull = empty + STAGES;
-    uint64_t* tempty = tfull + 1;
-    uint64_t* segfull = tempty + 1;
+    uint64_t* tfull = empty + STAGES;       // [2] (index 1: short-unit mode only)
+    uint64_t* tempty = tfull + 2;           // [2]
+    uint64_t* segfull = tempty + 2;
     uint64_t* segfree = segfull + 1;
     uint32_t* tmem_slot = (uint32_t*)(segfree + 1);
 
@@ -284,8 +288,10 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             ptx::mbar_init(&full[s], 1);
             ptx::mbar_init(&empty[s], 1);
         }
-        ptx::mbar_init(tfull, 1);
-        ptx::mbar_init(tempty, 256);
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tfull[a], 1);
+            ptx::mbar_init(&tempty[a], 256);
+        }
         ptx::mbar_init(segfull, 1);
         ptx::mbar_init(segfree, 256);
         ptx::fence_barrier_init();
@@ -301,6 +307,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int total_units = gemm_units(shape);                  // m_tiles counts 256-row tiles here
+    const bool short_mode = SEG > 0 && shape.short_units != 0;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -340,18 +347,20 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (lane == 0 && leader) {
             constexpr uint32_t idesc = ptx::make_idesc_f16(256, BLOCK_N, A_MN, B_MN, 0);
             int stage = 0;
-            uint32_t phase = 0, acc_phase = 0, flush_waits = 0;
+            uint32_t phase = 0, it = 0, flush_waits = 0;
             for (int unit = pair; unit < total_units; unit += npairs) {
                 const GemmUnit gu = gemm_unit(shape, unit);
                 if (gu.kb0 >= gu.kb1) continue;                              // empty K range (cannot happen for sane splits)
-                ptx::mbar_wait(tempty, acc_phase ^ 1);
+                const uint32_t acc = short_mode ? (it & 1) : 0;              // accumulator (and barrier pair) of this unit
+                const uint32_t acc_phase = short_mode ? ((it >> 1) & 1) : (it & 1);
+                ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
                 for (int kbg = gu.kb0; kbg < gu.kb1; ++kbg) {
                     const int kb = kbg - gu.kb0;
                     const int nkb = gu.kb1 - gu.kb0;
-                    uint32_t d_tmem = tmem_base;
+                    uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                     bool seg_start = (kb == 0);
-                    if (SEG > 0) {
+                    if (SEG > 0 && !short_mode) {
                         const int seg = kb / SEGD;
                         seg_start = (kb - seg * SEGD) == 0;
                         d_tmem = tmem_base + (seg == 0 ? 0 : BLOCK_N);
@@ -375,28 +384,30 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     }
                     ptx::mma_commit_pair(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    if (SEG > 0) {
+                    if (SEG > 0 && !short_mode) {
                         const int seg = kb / SEGD;
                         const bool seg_end = ((kb + 1) % SEGD == 0) && (kb + 1 < nkb);
                         if (seg_end && seg >= 1) ptx::mma_commit_pair(segfull);
                     }
                 }
-                ptx::mma_commit_pair(tfull);
-                acc_phase ^= 1;
+                ptx::mma_commit_pair(&tfull[acc]);
+                ++it;
             }
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
-        uint32_t acc_phase = 0, flushes = 0, nstore = 0;
+        uint32_t it = 0, flushes = 0, nstore = 0;
         uint8_t* epi_smem = smem + S::EPI_OFF;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         for (int unit = pair; unit < total_units; unit += npairs) {
             const GemmUnit gu = gemm_unit(shape, unit);
             if (gu.kb0 >= gu.kb1) continue;
             const int mt = gu.tile / shape.n_tiles, nt = gu.tile - mt * shape.n_tiles;
-            const uint32_t t0 = tmem_base + lane_off;
+            const uint32_t acc = short_mode ? (it & 1) : 0;
+            const uint32_t acc_phase = short_mode ? ((it >> 1) & 1) : (it & 1);
+            const uint32_t t0 = tmem_base + acc * BLOCK_N + lane_off;
             uint32_t t1 = 0;
-            if (SEG > 0) {
+            if (SEG > 0 && !short_mode) {
                 const int nseg = (gu.kb1 - gu.kb0 + SEGD - 1) / SEGD;
                 const uint32_t tA = tmem_base + BLOCK_N + lane_off;
                 for (int sg = 1; sg + 1 < nseg; ++sg) {
@@ -414,12 +425,12 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 }
                 if (nseg >= 2) t1 = tA;
             }
-            ptx::mbar_wait(tfull, acc_phase);
+            ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
             epi(mt * 2 + (int)rank, nt, q * 32 + lane, t0, t1, epi_smem, nstore, gu.partial);
             ptx::tc_fence_before();
-            ptx::mbar_arrive_leader(tempty);
-            acc_phase ^= 1;
+            ptx::mbar_arrive_leader(&tempty[acc]);
+            ++it;
         }
         if (Epi::kSmem > 0 && threadIdx.x == 128) ptx::bulk_wait_all();
     }

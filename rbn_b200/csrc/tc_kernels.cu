@@ -888,7 +888,9 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int kblocks = N / 64;
     const int ntiles_total = N * N / 256;
-    const int ntiles_per_range = ntiles_total / ranges;
+    // range r of a supertile covers Wk tiles [r * ntiles / ranges, (r + 1) * ntiles / ranges): any number of ranges,
+    // sizes differ by at most one tile
+    auto range_lo = [&](int r) { return (int)(((long long)r * ntiles_total) / ranges); };
     uint8_t* sAres = smem;                                        // [kblocks] x 16 KB (this CTA's 128 rows)
     uint8_t* sBring = sAres + (size_t)kblocks * 16384;            // [stages] x 16 KB (this CTA's half of a Wk tile)
     uint8_t* ebuf = sBring + STG * 16384;                   // [2 groups][NBUF] x 16 KB staging tiles
@@ -939,7 +941,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
                 for (int kb = 0; kb < kblocks; ++kb)
                     ptx::tma_load_2d_pair(sAres + (size_t)kb * 16384, &tmG, a_full, kb * 64, st * 256 + (int)rank * 128);
                 aphase ^= 1;
-                for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt)
+                for (int nt = range_lo(r); nt < range_lo(r + 1); ++nt)
                     for (int kb = 0; kb < kblocks; ++kb) {
                         ptx::mbar_wait(&empty[stage], phase ^ 1);
                         if (leader) ptx::mbar_expect_tx(&full[stage], 2 * 16384);
@@ -960,7 +962,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
                 aphase ^= 1;
                 ptx::tc_fence_after();
                 const uint32_t aA = ptx::smem_u32(sAres);
-                for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt) {
+                for (int nt = range_lo(r); nt < range_lo(r + 1); ++nt) {
                     ptx::mbar_wait(&tempty[buf], bphase ^ 1);
                     ptx::tc_fence_after();
                     for (int kb = 0; kb < kblocks; ++kb) {
@@ -992,7 +994,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
         uint32_t bphase = 0, nstore = 0;
         for (int unit = pair; unit < units; unit += npairs) {
             const int st = unit / ranges, r = unit - st * ranges;
-            for (int nt = r * ntiles_per_range; nt < (r + 1) * ntiles_per_range; ++nt) {
+            for (int nt = range_lo(r); nt < range_lo(r + 1); ++nt) {
                 ptx::mbar_wait(&tfull[buf], bphase);
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem_base + buf * 256 + grp * 128 + ((uint32_t)(q * 32) << 16);
@@ -1635,13 +1637,20 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
 // K-split factor of the partial last wave of a 2-CTA GEMM: r tiles left for `pairs` CTA pairs.  Splitting each into s
 // K-ranges gives ceil(r s / pairs) rounds of 1/s of a tile each; pick the s with the shortest tail (ties: fewer
 // partial sums to add).
-static int tail_splits_for(int r, int pairs, int k_blocks) {
+// `all_tail`: the launch has no whole tiles at all (fewer tiles than CTA pairs).  Cost in k-block times: rounds x (k-blocks
+// per unit + epilogue).  The partial-sum epilogue (TMEM -> red.add) takes about 15 k-block times when it is exposed; when
+// every unit fits ONE accumulation segment (`all_tail` and <= kSegBlocks k-blocks) the two accumulators alternate and it
+// hides behind the next unit's MMAs (GemmShape.short_units).
+static int tail_splits_for(int r, int pairs, int k_blocks, bool all_tail = false) {
     if (r <= 0) return 1;
     int best = 1;
-    double best_t = 1.0;
-    for (int s2 = 2; s2 <= 16 && k_blocks / s2 >= 16; ++s2) {
+    double best_t = (double)((r + pairs - 1) / pairs) * (k_blocks + 6.0);
+    const int smax = all_tail ? 32 : 16;
+    for (int s2 = 2; s2 <= smax && k_blocks / s2 >= 16; ++s2) {
         const int rounds = (r * s2 + pairs - 1) / pairs;
-        const double t = (double)rounds / s2 + 0.01 * s2;
+        const int per = (k_blocks + s2 - 1) / s2;
+        const double epi = (all_tail && per <= kSegBlocks) ? 2.0 : 15.0;
+        const double t = (double)rounds * (per + epi) + 0.01 * k_blocks * s2 / 16.0;
         if (t < best_t - 1e-9) { best_t = t; best = s2; }
     }
     return best;
@@ -1689,7 +1698,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         // wave quantisation: the last, partial wave of tiles is split along K so that all CTA pairs stay busy
         const int pairs = sms / 2, T = shape2.m_tiles * n_tiles;
         const int full = (T / pairs) * pairs, r = T - full;
-        const int splits = tail_splits_for(r, pairs, shape2.k_blocks);
+        const int splits = tail_splits_for(r, pairs, shape2.k_blocks, full == 0 && n_tiles == 1);
         if (n_tiles > 1) {
             // both halves of a row are needed for its max shift: every tile adds into acc, k_rule_finalize does the rest
             shape2.all_partial = 1;
@@ -1705,6 +1714,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         if (splits > 1) {
             shape2.full_tiles = full;
             shape2.tail_splits = splits;
+            shape2.short_units = (full == 0 && (shape2.k_blocks + splits - 1) / splits <= kSegBlocks) ? 1 : 0;
             const int t_begin = full * 256;
             RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot) + (size_t)t_begin * c.N, 0, (size_t)(cnt - t_begin) * c.N * sizeof(float), st));
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
@@ -1763,9 +1773,9 @@ static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
         int ranges2 = 1;
         {
             double best = 1e30;
-            for (int r = 1; r <= 64 && ntiles2 % r == 0 && ntiles2 / r >= 4; r *= 2) {
+            for (int r = 1; r <= 64 && ntiles2 / r >= 4; ++r) {
                 const long long units = (long long)supertiles * r;
-                const double cost = (double)((units + pairs - 1) / pairs) * (ntiles2 / r + 1.0);
+                const double cost = (double)((units + pairs - 1) / pairs) * ((ntiles2 + r - 1) / r + 1.0);
                 if (cost < best * 0.995) { best = cost; ranges2 = r; }
             }
         }

@@ -121,7 +121,7 @@ def test_split_sum_cache_does_not_change_results(monkeypatch, N, L, B, chunk):
     for r in res[1:]:         # equal up to the order of the atomic adds of K-split partial sums (and of the deferred count GEMM)
         np.testing.assert_allclose(r[0], res[0][0], rtol=1e-6)
         for a, b in zip(res[0][1:], r[1:]):
-            assert metrics(b, a)["max_rel"] <= 2e-5 and metrics(b, a)["l2_rel"] <= 2e-5
+            assert metrics(b, a)["max_rel"] <= 2e-4 and metrics(b, a)["l2_rel"] <= 2e-4
     ref, gW, gT, gP = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths)
     assert np.abs(res[0][0] - ref.numpy()).max() <= LOGZ_RTOL * np.abs(ref.numpy()).max()
     assert metrics(res[0][1], gW.numpy())["max_rel"] <= GRAD_RTOL
