@@ -336,12 +336,18 @@ def run_ours(args, wl, secondary=False):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, nsteps):
+    def timed(fn, nsteps, profile_last=False):
+        """nsteps calls of fn between two CUDA events (barrier + synchronize on both sides), max over ranks.  With
+        `profile_last` the LAST of the timed steps also brackets every kernel launch of the library with CUDA events on
+        the launching stream (rbn_profile_*): the per-kernel times come from inside the timed region, and the event
+        records (two per launch, ~3600 launches per step) tax one step instead of all of them."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = None
-        for _ in range(nsteps):
+        for k in range(nsteps):
+            if profile_last and k == nsteps - 1:
+                _lib.profile_enable(True)
             out = fn()
         e1.record()
         barrier()
@@ -354,11 +360,13 @@ def run_ours(args, wl, secondary=False):
     for _ in range(warmup):
         device_step()
     _lib.profile_read(reset=True)
-    _lib.profile_enable(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_step, (lz, grads) = timed(device_step, steps)
+    prof_steps = steps if args.profile_all else 1
+    if args.profile_all:
+        _lib.profile_enable(True)
+    ms_step, (lz, grads) = timed(device_step, steps, profile_last=not args.profile_all)
     clocks = sampler.stop() if rank == 0 else None
     prof = _lib.profile_read(reset=True)
     _lib.profile_enable(False)
@@ -417,7 +425,7 @@ def run_ours(args, wl, secondary=False):
 
     f_step, f_rule_step, f_rule_fwd = (x * B for x in flops_per_sequence(N, L, wl["outside"]))
     peaks = load_peaks()
-    kms = {k: v[0] / steps for k, v in prof.items() if v[1]}
+    kms = {k: v[0] / prof_steps for k, v in prof.items() if v[1]}     # event times: summed over the profiled step(s)
     kms["rule_gemm"] = kms.get("rule_gemm", 0.0) + kms.pop("rule_finalize", 0.0)   # the max-shift epilogue of K-split tiles
     roofline = dict(step_tflops=f_step / (ms_step * 1e-3) / 1e12, step_frac=f_step / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
                     step_peak=f"{peaks['source']} bf16_tflops_sustained {peaks['tflops']} TFLOP/s (kernels timed inside a long step)",
@@ -448,7 +456,7 @@ def run_ours(args, wl, secondary=False):
             ms = kms.get(cls, 0.0)
             if ms <= 0:
                 return
-            launches = prof[cls][1] / steps
+            launches = prof[cls][1] / steps                    # (launches are counted on every step)
             ach = amount / (ms * 1e-3) / (1e12 if unit == "TFLOP/s" else 1e9)
             tr = traffic.get(cls, {}).get("dram_bytes_per_span")
             per[cls] = dict(bound=bound, kernel=names[cls], ms_per_step=round(ms, 3), achieved=round(ach, 1), peak=peak, unit=unit,
@@ -640,6 +648,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="spans per launch group (0 = library default)")
     ap.add_argument("--micro", type=int, default=0, help="sequences per micro-batch (default: the workload's)")
     ap.add_argument("--no-secondary", action="store_true", help="N > 1: skip the C5 line under `secondary`")
+    ap.add_argument("--profile-all", action="store_true", help="bracket the kernels of EVERY timed step with events (default: the last one)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the end-to-end arm")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the CPU baseline")
     args = ap.parse_args()

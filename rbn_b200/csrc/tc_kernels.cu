@@ -1637,20 +1637,22 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
 // K-split factor of the partial last wave of a 2-CTA GEMM: r tiles left for `pairs` CTA pairs.  Splitting each into s
 // K-ranges gives ceil(r s / pairs) rounds of 1/s of a tile each; pick the s with the shortest tail (ties: fewer
 // partial sums to add).
-// `all_tail`: the launch has no whole tiles at all (fewer tiles than CTA pairs).  Cost in k-block times: rounds x (k-blocks
-// per unit + epilogue).  The partial-sum epilogue (TMEM -> red.add) takes about 15 k-block times when it is exposed; when
-// every unit fits ONE accumulation segment (`all_tail` and <= kSegBlocks k-blocks) the two accumulators alternate and it
-// hides behind the next unit's MMAs (GemmShape.short_units).
+// Cost model in microseconds (constants measured on B200, C3 shapes, round 2): a CTA pair spends ~0.34 us per k-block of a
+// 256 x 256 tile; the partial sums of a K-split unit are red.global.add-ed into the fp32 buffer, and the chip's L2 sustains
+// only ~2 TB/s of those (256 KB per unit -> 0.122 us each, chip-wide, not hidden by anything); a split launch also needs
+// the buffer cleared and the finalize kernel (~8 us).  So: split as little as evens out the rounds.  (First version of this
+// model ignored the L2 reduction rate and split T = 64 tiles eight ways: 20 ms per C3 step slower than not splitting.)
+// `tiles_total`: all tiles of the launch whose units are partial (for the red traffic), r of them form the tail.
 static int tail_splits_for(int r, int pairs, int k_blocks, bool all_tail = false) {
     if (r <= 0) return 1;
+    const double t_kb = 0.34, t_red = 0.122, t_fixed = 8.0;
     int best = 1;
-    double best_t = (double)((r + pairs - 1) / pairs) * (k_blocks + 6.0);
-    const int smax = all_tail ? 32 : 16;
-    for (int s2 = 2; s2 <= smax && k_blocks / s2 >= 16; ++s2) {
+    double best_t = (double)((r + pairs - 1) / pairs) * k_blocks * t_kb;
+    for (int s2 = 2; s2 <= 16 && k_blocks / s2 >= 16; ++s2) {
         const int rounds = (r * s2 + pairs - 1) / pairs;
         const int per = (k_blocks + s2 - 1) / s2;
-        const double epi = (all_tail && per <= kSegBlocks) ? 2.0 : 15.0;
-        const double t = (double)rounds * (per + epi) + 0.01 * k_blocks * s2 / 16.0;
+        const double epi = (all_tail && per <= kSegBlocks) ? 0.0 : 4.0;       // exposed TMEM -> red issue time per unit
+        const double t = (double)rounds * (per * t_kb + epi) + (double)r * s2 * t_red + t_fixed;
         if (t < best_t - 1e-9) { best_t = t; best = s2; }
     }
     return best;

