@@ -29,6 +29,10 @@ struct GemmShape {
     // ONE accumulator and consecutive units alternate between the two -- the epilogue of a unit (partial sums -> red.add)
     // runs behind the next unit's MMAs instead of in front of them
     int short_units;
+    // 2-CTA kernel only, stream-K: > 0 = the launch's (tile, k-block) space, tile-major, is one linear range cut into equal
+    // pieces of sk_per k-blocks, one per CTA pair; a piece that crosses a tile boundary becomes two units.  Every unit is
+    // partial.  Evens out launches with fewer tiles than CTA pairs at the price of at most (pairs + tiles) partial sums.
+    int sk_per;
 };
 
 struct GemmUnit {
@@ -54,6 +58,36 @@ __device__ __forceinline__ GemmUnit gemm_unit(const GemmShape& s, int u) {
     }
     return r;
 }
+
+// The units of one CTA pair, in order; all three warp roles of the 2-CTA kernel walk the same sequence.
+struct PairUnits {
+    const GemmShape& s;
+    int unit, npairs, total;
+    long long lin, lin_end;
+    __device__ PairUnits(const GemmShape& shape, int pair, int np) : s(shape), unit(pair), npairs(np), total(gemm_units(shape)) {
+        const long long all = (long long)shape.m_tiles * shape.n_tiles * shape.k_blocks;
+        lin = (long long)pair * shape.sk_per;
+        lin_end = lin + shape.sk_per < all ? lin + shape.sk_per : all;
+    }
+    __device__ bool next(GemmUnit& gu) {
+        if (s.sk_per > 0) {
+            if (lin >= lin_end) return false;
+            gu.tile = (int)(lin / s.k_blocks);
+            gu.kb0 = (int)(lin - (long long)gu.tile * s.k_blocks);
+            const long long left = lin_end - lin;
+            gu.kb1 = (gu.kb0 + left < s.k_blocks) ? (int)(gu.kb0 + left) : s.k_blocks;
+            gu.partial = true;
+            lin += gu.kb1 - gu.kb0;
+            return true;
+        }
+        while (unit < total) {
+            gu = gemm_unit(s, unit);
+            unit += npairs;
+            if (gu.kb0 < gu.kb1) return true;       // (an empty K range cannot happen for sane splits)
+        }
+        return false;
+    }
+};
 
 template <int BLOCK_N, int STAGES, int EPI_SMEM>
 struct GemmSmem {
@@ -305,16 +339,16 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int total_units = gemm_units(shape);                  // m_tiles counts 256-row tiles here
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;     // (m_tiles counts 256-row tiles here)
     const bool short_mode = SEG > 0 && shape.short_units != 0;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = pair; unit < total_units; unit += npairs) {
-                const GemmUnit gu = gemm_unit(shape, unit);
+            PairUnits units(shape, pair, npairs);
+            GemmUnit gu;
+            while (units.next(gu)) {
                 const int mt = gu.tile / shape.n_tiles, nt = gu.tile - mt * shape.n_tiles;   // n fastest: the pairs that
                 const int row0 = mt * 256 + (int)rank * kBM;                 // share an A tile run side by side (L2 hit)
                 const int col0 = nt * BLOCK_N + (int)rank * HALF_N;          // this CTA's half of B
@@ -348,9 +382,9 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             constexpr uint32_t idesc = ptx::make_idesc_f16(256, BLOCK_N, A_MN, B_MN, 0);
             int stage = 0;
             uint32_t phase = 0, it = 0, flush_waits = 0;
-            for (int unit = pair; unit < total_units; unit += npairs) {
-                const GemmUnit gu = gemm_unit(shape, unit);
-                if (gu.kb0 >= gu.kb1) continue;                              // empty K range (cannot happen for sane splits)
+            PairUnits units(shape, pair, npairs);
+            GemmUnit gu;
+            while (units.next(gu)) {
                 const uint32_t acc = short_mode ? (it & 1) : 0;              // accumulator (and barrier pair) of this unit
                 const uint32_t acc_phase = short_mode ? ((it >> 1) & 1) : (it & 1);
                 ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -399,9 +433,9 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         uint32_t it = 0, flushes = 0, nstore = 0;
         uint8_t* epi_smem = smem + S::EPI_OFF;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        for (int unit = pair; unit < total_units; unit += npairs) {
-            const GemmUnit gu = gemm_unit(shape, unit);
-            if (gu.kb0 >= gu.kb1) continue;
+        PairUnits units(shape, pair, npairs);
+        GemmUnit gu;
+        while (units.next(gu)) {
             const int mt = gu.tile / shape.n_tiles, nt = gu.tile - mt * shape.n_tiles;
             const uint32_t acc = short_mode ? (it & 1) : 0;
             const uint32_t acc_phase = short_mode ? ((it >> 1) & 1) : (it & 1);
@@ -449,6 +483,10 @@ int launch_tc_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape sh
     int tiles = shape.m_tiles * shape.n_tiles;
     if (shape.tail_splits > 1) tiles = shape.full_tiles + (tiles - shape.full_tiles) * shape.tail_splits;
     int pairs = num_sms / 2;
+    if (shape.sk_per > 0) {
+        const long long all = (long long)shape.m_tiles * shape.n_tiles * shape.k_blocks;
+        tiles = (int)((all + shape.sk_per - 1) / shape.sk_per);       // pieces; the caller sized sk_per for `pairs` of them
+    }
     if (tiles < pairs) pairs = tiles;
     if (pairs < 1) return RBN_OK;
     { ProfScope ps(kclass, st); kern<<<2 * pairs, 256, S::TOTAL, st>>>(tmA, tmB, shape, epi); }

@@ -525,8 +525,11 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
 // =======================================================================================================================
 // K5: child gradients, one span per CTA iteration, TMA-fed
 // =======================================================================================================================
-static constexpr int kK5Stages = 4;
-static constexpr int kK5StageBytes = 32768;   // A 16 KB + B 16 KB
+// Operand ring: a stage is a 16 KB gY tile + the Npad x 64 child-row tile (Npad * 128 B, at most 16 KB).  The ring takes
+// whatever shared memory is left beside the reduce staging tiles: 5 stages at 128 splits, 8 (the cap) from 33 splits down.
+// A span is 16 stage loads; with 4 stages of 32 KB narrow diagonals were bound by the bytes in flight per SM (5.8 us per
+// span at w = 2 against 3 us of HBM time), which is where most spans are.
+static constexpr int kK5MaxStages = 8;
 
 __global__ void __launch_bounds__(384, 1)
 k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)][c], box {64,128}: A of the left-child GEMM
@@ -539,13 +542,14 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                const __grid_constant__ CUtensorMap tmALt,   // same views, tail_rows instead of 32: last chunk of a span's splits
                const __grid_constant__ CUtensorMap tmARt,
                const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp,
-               uint64_t red_pol, uint64_t gy2_pol) {
+               uint64_t red_pol, uint64_t gy2_pol, int stages) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* rbuf = smem + kK5Stages * kK5StageBytes;        // [2 groups][2] x 16 KB tiles [32 splits][128 nonterminals] fp32
+    const int stage_bytes = 16384 + ((((w - 1) + 15) & ~15) * 128);
+    uint8_t* rbuf = smem + stages * stage_bytes;        // [2 groups][2] x 16 KB tiles [32 splits][128 nonterminals] fp32
     uint64_t* full = (uint64_t*)(rbuf + 65536);
-    uint64_t* empty = full + kK5Stages;
-    uint64_t* afull = empty + kK5Stages;     // [4]
+    uint64_t* empty = full + kK5MaxStages;
+    uint64_t* afull = empty + kK5MaxStages;  // [4]
     uint64_t* aempty = afull + 4;            // [4]
     uint32_t* tmem_slot = (uint32_t*)(aempty + 4);
     float* fac = (float*)(tmem_slot + 2);    // [2 groups][2][128] split factors c_j * 2^eG of the current / next span
@@ -559,7 +563,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
     const size_t C = cells_per_seq(L);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kK5Stages; ++s) {
+        for (int s = 0; s < stages; ++s) {
             ptx::mbar_init(&full[s], 1);
             ptx::mbar_init(&empty[s], 1);
         }
@@ -594,7 +598,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                     const int kind = u / halves, h = u - kind * halves;
                     for (int kb = 0; kb < kblocks; ++kb) {
                         ptx::mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* sA = smem + stage * kK5StageBytes;
+                        uint8_t* sA = smem + stage * stage_bytes;
                         uint8_t* sB = sA + 16384;
                         ptx::mbar_expect_tx(&full[stage], 16384 + b_bytes);
                         if (kind == 0) {
@@ -606,7 +610,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                             ptx::tma_load_2d_hint(sA + 8192, &tmGYm, &full[stage], h * 128 + 64, t * N + kb * 64, gy2_pol);
                             ptx::tma_load_2d(sB, &tmLC, &full[stage], kb * 64, lc_row);
                         }
-                        if (++stage == kK5Stages) { stage = 0; phase ^= 1; }
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -631,7 +635,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                     for (int kb = 0; kb < kblocks; ++kb) {
                         ptx::mbar_wait(&full[stage], phase);
                         ptx::tc_fence_after();
-                        const uint32_t sA = ptx::smem_u32(smem + stage * kK5StageBytes);
+                        const uint32_t sA = ptx::smem_u32(smem + stage * stage_bytes);
                         const uint32_t sB = sA + 16384;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
@@ -641,7 +645,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                             ptx::mma_f16_ss(d_tmem, ad, bd, kind ? idesc_m : idesc_k, (uint32_t)((kb | kk) != 0));
                         }
                         ptx::mma_commit(&empty[stage]);
-                        if (++stage == kK5Stages) { stage = 0; phase ^= 1; }
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
                     }
                     ptx::mma_commit(&afull[slot]);
                 }
@@ -1643,7 +1647,8 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
 // the buffer cleared and the finalize kernel (~8 us).  So: split as little as evens out the rounds.  (First version of this
 // model ignored the L2 reduction rate and split T = 64 tiles eight ways: 20 ms per C3 step slower than not splitting.)
 // `tiles_total`: all tiles of the launch whose units are partial (for the red traffic), r of them form the tail.
-static int tail_splits_for(int r, int pairs, int k_blocks, bool all_tail = false) {
+static int tail_splits_for(int r, int pairs, int k_blocks, bool all_tail = false, double* t_best = nullptr) {
+    if (t_best) *t_best = 0;
     if (r <= 0) return 1;
     const double t_kb = 0.34, t_red = 0.122, t_fixed = 8.0;
     int best = 1;
@@ -1655,6 +1660,7 @@ static int tail_splits_for(int r, int pairs, int k_blocks, bool all_tail = false
         const double t = (double)rounds * (per * t_kb + epi) + (double)r * s2 * t_red + t_fixed;
         if (t < best_t - 1e-9) { best_t = t; best = s2; }
     }
+    if (t_best) *t_best = best_t;
     return best;
 }
 
@@ -1700,7 +1706,25 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         // wave quantisation: the last, partial wave of tiles is split along K so that all CTA pairs stay busy
         const int pairs = sms / 2, T = shape2.m_tiles * n_tiles;
         const int full = (T / pairs) * pairs, r = T - full;
-        const int splits = tail_splits_for(r, pairs, shape2.k_blocks, full == 0 && n_tiles == 1);
+        double t_split = 0;
+        const int splits = tail_splits_for(r, pairs, shape2.k_blocks, full == 0 && n_tiles == 1, &t_split);
+        if (full == 0 && n_tiles == 1 && T >= 1) {
+            // fewer tiles than CTA pairs: stream-K (every pair gets the same number of k-blocks) when it beats the best
+            // uniform split -- same constants as tail_splits_for; a pair then owns ~2 units with exposed epilogues
+            const int per = (int)(((long long)T * shape2.k_blocks + pairs - 1) / pairs);
+            const double t_sk = per * 0.34 + (double)(pairs + T) * 0.122 + 8.0 + 2 * 4.0;
+            if (per >= 8 && t_sk < t_split) {
+                shape2.sk_per = per;
+                shape2.short_units = per <= kSegBlocks ? 1 : 0;
+                RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot), 0, (size_t)cnt * c.N * sizeof(float), st));
+                rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
+                if (rc) return rc;
+                { ProfScope ps(KC_RULE_FIN, st);
+                  k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+                RBN_LAUNCH_CHECK("k_rule_finalize");
+                return RBN_OK;
+            }
+        }
         if (n_tiles > 1) {
             // both halves of a row are needed for its max shift: every tile adds into acc, k_rule_finalize does the rest
             shape2.all_partial = 1;
@@ -1875,7 +1899,11 @@ static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     if (rc) return rc;
     rc = make_tmap_3d_f32(&tmARt, c.alpha, (uint64_t)N, (uint64_t)c.Lp, (uint64_t)B * L, 128, tail_rows);
     if (rc) return rc;
-    size_t smem = (size_t)kK5Stages * kK5StageBytes + 65536 + 256 + 2048 + 1024;
+    const size_t stage_bytes = 16384 + (size_t)Npad * 128;
+    const size_t fixed = 65536 + 512 + 2048 + 1024;          // reduce staging, barriers, split factors, alignment
+    int stages = (int)((232448 - fixed) / stage_bytes);
+    if (stages > kK5MaxStages) stages = kK5MaxStages;
+    size_t smem = (size_t)stages * stage_bytes + fixed;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < sms ? cnt : sms;
     { ProfScope ps(KC_CHILD, st);
@@ -1883,7 +1911,7 @@ static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
                                          c.lengths, tmAL, tmAR, tmALt, tmARt, (const int*)c.ce, (const int*)c.e_of(u),
                                          (const int*)c.gexp(u.slot),
                                          (uint64_t)((tc_tune().hints & 1) ? ptx::kEvictLast : ptx::kEvictNormal),
-                                         (uint64_t)((tc_tune().hints & 8) ? ptx::kEvictFirst : ptx::kEvictNormal))); }
+                                         (uint64_t)((tc_tune().hints & 8) ? ptx::kEvictFirst : ptx::kEvictNormal), stages)); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;
 }
