@@ -371,6 +371,14 @@ def run_ours(args, wl, secondary=False):
     prof = _lib.profile_read(reset=True)
     _lib.profile_enable(False)
     lz_host = lz.detach().double().cpu().numpy()
+    # sequence 0 of the benched batch is sequence 0 of the headline fixture (tests/golden/headline_c3.npz, written by the
+    # fp64 oracle): its log Z inside the full batch, checked on every run without the 30 s oracle
+    fixture_check = None
+    fpath = os.path.join(ROOT, "tests", "golden", "headline_c3.npz")
+    if (N, V, L) == (256, 32, 128) and rank == 0 and os.path.exists(fpath):
+        ref0 = float(np.load(fpath)["logZ"][0])
+        fixture_check = dict(logZ0=float(lz_host[0]), logZ0_oracle=ref0, abs_err=float(lz_host[0] - ref0),
+                             rel_err=float(abs(lz_host[0] - ref0) / abs(ref0)))
     count_check = None
     if grads is not None:
         # expected-count identity over the whole job: sum_{bca} gW * W = number of binary rule applications = sum (len - 1)
@@ -506,7 +514,7 @@ def run_ours(args, wl, secondary=False):
                 e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="seq/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h),
                 gpu_launches=launches, roofline=roofline, clocks=clocks,
-                logZ_mean=float(np.mean(lz_host)), count_check=count_check)
+                logZ_mean=float(np.mean(lz_host)), count_check=count_check, fixture_check=fixture_check)
     if cpu_v is not None:
         line["cpu_baseline"] = dict(value=cpu_v, unit="seq/s", cores=cores, kind="port", sample=cpu_samp)
     if parity is not None:

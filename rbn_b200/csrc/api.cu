@@ -129,8 +129,9 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->wt = take(N * N * N * sizeof(__half));
         o->wk = take(N * N * N * sizeof(__half));
         o->wexp = take(N * sizeof(int));
-        o->wscale = take(N * sizeof(float));
-        o->wbits = take(N * sizeof(int));
+        o->wscale = take(2 * N * sizeof(float));
+        o->wdens = take(N * sizeof(float));
+        o->wbits = take(2 * N * sizeof(int));
         o->y = take(ns * chunk * N * N * sizeof(__half));
         o->gy = take(ns * chunk * N * N * sizeof(__half));
         o->item_e = take(ns * chunk * sizeof(int));

@@ -53,8 +53,9 @@ struct WsLayout {
     size_t wt;          // half [N][N*N]         Wt[a][b*N+c] = W[b][c][a] * 2^-wexp[a]
     size_t wk;          // half [N*N][N]         Wk[b*N+c][a] = W[b][c][a] * 2^-wexp[a]
     size_t wexp;        // int32 [N]   W = W16 * 2^wexp[a]
-    size_t wscale;      // float [N]   2^wexp[a]
-    size_t wbits;       // int32 [N]   scratch: float bits of max_{b,c} W[b][c][a]
+    size_t wscale;      // float [2][N]  2^wexp[a]; the same times (1 + truncation compensation of a whole-tile chain)
+    size_t wdens;       // float [N]   fraction of nonzero rules of parent a
+    size_t wbits;       // int32 [2][N]  scratch: float bits of max_{b,c} W[b][c][a]; number of nonzero rules
     // per-chunk buffers: `nslot` copies each (slot s at offset + s * chunk * row bytes), so that chunks in flight on
     // the two launch streams of the overlapped schedule never share a buffer
     size_t y;           // half [nslot][chunk][N*N]
@@ -88,6 +89,7 @@ struct TcTune {
     int bwd_sms0;       // RBN_TC_BWD_SMS0  SMs of the {split-sum, prep, gY} partition in the outside pass (even)
     int nslot;          // RBN_TC_SLOTS     per-chunk buffer copies
     int k3_stream;      // RBN_TC_K3_STREAM 0: gY GEMM beside the split-sum, 1: beside the child-gradient kernel
+    float kappa;        // RBN_TC_KAPPA     tcgen05 accumulator-truncation bias per k-block of a chain (compensated in the rule GEMM)
     int hints;          // RBN_TC_HINTS     L2 eviction-priority hints on the bulk tensor copies (bit mask): 1 outside-chart
                         //                  reduce-adds evict_last (the second contribution to a cell of a diagonal should find the
                         //                  line in L2); 2 streamed stores (Y, gY) evict_first; 4 rule / count GEMM operand streams

@@ -1184,23 +1184,44 @@ k_tc_gy3(const __grid_constant__ CUtensorMap tmW,     // Wk [N*N rows][N], box {
 // element-wise helpers of the tensor-core path
 // =======================================================================================================================
 // per-parent exponent of max_{b,c} W[b][c][a]
+// (and, in wmax_bits[N + a], the number of nonzero rules of parent a)
 __global__ void k_w_colmax(int N, const float* __restrict__ W, int* __restrict__ wmax_bits) {
     // grid over (b,c) rows in slabs; thread a
     size_t rows = (size_t)N * N;
     for (int a = threadIdx.x; a < N; a += blockDim.x) {
         float mx = 0.f;
-        for (size_t r = blockIdx.x; r < rows; r += gridDim.x) mx = fmaxf(mx, W[r * N + a]);
+        int nnz = 0;
+        for (size_t r = blockIdx.x; r < rows; r += gridDim.x) {
+            const float x = W[r * N + a];
+            mx = fmaxf(mx, x);
+            nnz += (x != 0.f);
+        }
         atomicMax(&wmax_bits[a], __float_as_int(mx));     // non-negative floats order like ints
+        atomicAdd(&wmax_bits[N + a], nnz);
     }
 }
-__global__ void k_w_exp(int N, const int* __restrict__ wmax_bits, int* __restrict__ wexp, float* __restrict__ wscale) {
+// tcgen05.mma adds into its fp32 accumulator with TRUNCATION: a chain of non-negative products comes out low by
+// kTruncPerKBlock per k-block of 64 (measured: K = 1024 / 4096 / 8192 / 65536 -> 5.5e-6 / 2.4e-5 / 4.8e-5 / 3.9e-4,
+// tools/experiments/exp_bias.py; linear in the chain length, independent of the data's scale).  The inside pass feeds one
+// such GEMM into the next 127 times.  log Z only moves by ~3e-3, but posteriors of a node at depth d of a derivation
+// come out HIGH by d times the per-level bias (the outside recursion has K = 256 chains and no such bias to cancel
+// it): +4e-4 on the expected counts at L = 128, i.e. half of the 1e-3 budget, as a systematic error.  The rule GEMM's
+// epilogue therefore multiplies parent a by 1 + kTruncPerKBlock * (k-blocks per accumulation chain) * density[a], where
+// density[a] = fraction of nonzero rules of parent a (adding an exact zero does not truncate).  RBN_TC_KAPPA overrides
+// the constant (0 switches the compensation off).
+static constexpr float kTruncPerKBlock = 3.7e-7f;
+__global__ void k_w_exp(int N, const int* __restrict__ wmax_bits, int* __restrict__ wexp, float* __restrict__ wscale,
+                        float* __restrict__ wdens, float kc_full) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= N) return;
     float mx = __int_as_float(wmax_bits[a]);
     int e = 0;
     if (mx > 0.f) frexpf(mx, &e);
     wexp[a] = e;
+    const float dens = (float)wmax_bits[N + a] / ((float)N * (float)N);
+    wdens[a] = dens;
     wscale[a] = ldexpf(1.0f, e);
+    wscale[N + a] = ldexpf(1.0f, e) * (1.0f + kc_full * dens);     // whole tiles: chains of kSegBlocks k-blocks
 }
 // Wk[(b,c)][a] = W * 2^-wexp[a]  and its transpose Wt[a][(b,c)]  (32x32 tiles through shared memory)
 __global__ void k_w_copies(int N, const float* __restrict__ W, const int* __restrict__ wexp, __half* __restrict__ wk,
@@ -1237,7 +1258,7 @@ __global__ void k_copy_width1(int N, int L, int Lp, const int* __restrict__ leng
 __global__ void k_rule_finalize(int N, int L, int Lp, int w, int m0, int t_begin, int cnt, const int* __restrict__ lengths,
                                 const float* __restrict__ wscale, const int* __restrict__ item_e,
                                 const float* __restrict__ acc, float* __restrict__ cv, int* __restrict__ ce,
-                                __half* __restrict__ lc, __half* __restrict__ rc) {
+                                __half* __restrict__ lc, __half* __restrict__ rc, const float* __restrict__ wdens, float kc) {
     __shared__ float red[32];
     const int t = t_begin + blockIdx.x;
     if (t >= cnt) return;
@@ -1246,7 +1267,7 @@ __global__ void k_rule_finalize(int N, int L, int Lp, int w, int m0, int t_begin
     const int b = m / nI, i = m - b * nI, k = i + w;
     if (k > lengths[b]) return;
     const int a = threadIdx.x;                       // blockDim.x == N
-    const float x = acc[(size_t)t * N + a] * wscale[a];
+    const float x = acc[(size_t)t * N + a] * wscale[a] * (1.0f + kc * wdens[a]);   // kc: truncation compensation of this launch's chains
     float mx = x;
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((a & 31) == 0) red[a >> 5] = mx;
@@ -1371,6 +1392,8 @@ const TcTune& tc_tune() {
         t.nslot = env_int("RBN_TC_SLOTS", 3);
         t.k3_stream = env_int("RBN_TC_K3_STREAM", 0) != 0;
         t.hints = env_int("RBN_TC_HINTS", kDefaultHints);
+        const char* ek = getenv("RBN_TC_KAPPA");
+        t.kappa = (ek && *ek) ? (float)atof(ek) : kTruncPerKBlock;
         if (t.groups < 1) t.groups = 1;
         if (t.nslot < 2) t.nslot = 2;
         if (t.nslot > 8) t.nslot = 8;
@@ -1394,7 +1417,9 @@ struct TcCtx {
     float* alpha;    // start-major outside chart: root seed + left- and right-child contributions
     __half *lc, *rc, *wt, *wk;
     int *wexp, *wbits;
-    float* wscale;
+    float* wscale;     // [2][N]: 2^wexp[a], and the same times the truncation compensation of whole tiles
+    float* wdens;      // [N] fraction of nonzero rules per parent
+    float kappa;       // truncation bias per k-block of an accumulation chain (kTruncPerKBlock or RBN_TC_KAPPA)
     const int* lengths;
     // per-chunk buffers, `nslot` copies
     __half* y(int s) const { return (__half*)(base + ws->y) + (size_t)s * chunk * N * N; }
@@ -1418,6 +1443,8 @@ static void fill_ctx(TcCtx& c, const RbnDesc* d, const WsLayout& ws, char* base,
     c.lc = (__half*)(base + ws.lc); c.rc = (__half*)(base + ws.rc); c.wt = (__half*)(base + ws.wt);
     c.wk = (__half*)(base + ws.wk);
     c.wexp = (int*)(base + ws.wexp); c.wbits = (int*)(base + ws.wbits); c.wscale = (float*)(base + ws.wscale);
+    c.wdens = (float*)(base + ws.wdens);
+    c.kappa = tc_tune().kappa;
     c.lengths = lengths;
 }
 
@@ -1576,10 +1603,10 @@ static cudaError_t launch_maybe_paired(void (*kern)(KArgs...), bool paired, int 
 static int prep_weights(TcCtx& c, const float* W, cudaStream_t st) {
     int N = c.N;
     int* bits = c.wbits;
-    RBN_CUDA_CHECK(cudaMemsetAsync(bits, 0, (size_t)N * sizeof(int), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(bits, 0, (size_t)2 * N * sizeof(int), st));
     { ProfScope ps(KC_OTHER, st); k_w_colmax<<<256, 256, 0, st>>>(N, W, bits); }
     RBN_LAUNCH_CHECK("k_w_colmax");
-    { ProfScope ps(KC_OTHER, st); k_w_exp<<<(N + 127) / 128, 128, 0, st>>>(N, bits, c.wexp, c.wscale); }
+    { ProfScope ps(KC_OTHER, st); k_w_exp<<<(N + 127) / 128, 128, 0, st>>>(N, bits, c.wexp, c.wscale, c.wdens, c.kappa * kSegBlocks); }
     RBN_LAUNCH_CHECK("k_w_exp");
     dim3 grid((unsigned)((size_t)N * N / 32), (unsigned)(N / 32));
     { ProfScope ps(KC_OTHER, st); k_w_copies<<<grid, dim3(32, 8), 0, st>>>(N, W, c.wexp, c.wk, c.wt); }
@@ -1673,7 +1700,9 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, c.wt, NN, (uint64_t)c.N, NN * 2, BN);
     if (rc) return rc;
-    EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale, c.e_of(u), c.cv, c.ce, c.lc, c.rc, c.acc(u.slot), BN};
+    // (the direct epilogue only ever sees whole tiles: chains of kSegBlocks k-blocks -> the compensated scale row)
+    EpiRule epi{c.N, c.L, c.Lp, w, m0, cnt, c.lengths, c.wscale + c.N, c.e_of(u), c.cv, c.ce, c.lc, c.rc, c.acc(u.slot), BN};
+    auto chain_kc = [&](int per) { return c.kappa * (float)(per < kSegBlocks ? per : kSegBlocks); };
     const int n_tiles = c.N / BN;                  // 1, or 2 when N = 512
     if (n_tiles > 1 && !use_pairs()) {
         set_error("N = %d needs the CTA-pair kernels (unset RBN_TC_1CTA)", c.N);
@@ -1693,7 +1722,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         rc = launch_tc_gemm2<false, false, BN, 3, 0, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule,half>", KC_RULE);
         if (rc) return rc;
         { ProfScope ps(KC_RULE_FIN, st);
-          k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+          k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
         RBN_LAUNCH_CHECK("k_rule_finalize");
         return RBN_OK;
     }
@@ -1720,7 +1749,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
                 rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
                 if (rc) return rc;
                 { ProfScope ps(KC_RULE_FIN, st);
-                  k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+                  k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(per)); }
                 RBN_LAUNCH_CHECK("k_rule_finalize");
                 return RBN_OK;
             }
@@ -1733,7 +1762,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
-              k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+              k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
@@ -1746,7 +1775,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
-              k_rule_finalize<<<cnt - t_begin, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc); }
+              k_rule_finalize<<<cnt - t_begin, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc((shape2.k_blocks + splits - 1) / splits)); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }

@@ -128,7 +128,9 @@ def test_full_size_shape_properties_n256_l128():
     perm = np.array([3, 0, 5, 2, 1, 4])
     lz2 = inside_logZ(torch.tensor(W, device="cuda"), torch.tensor(T, device="cuda"), torch.tensor(pr, device="cuda"),
                       torch.tensor(tok[perm]), torch.tensor(lengths[perm]), path=_lib.PATH_TCGEN05, chunk_items=256)
-    np.testing.assert_allclose(lz2.cpu().numpy(), lz.detach().cpu().numpy()[perm], rtol=2e-6)
+    # (the chunking changes how the rule GEMM's K range is cut over the CTA pairs, i.e. the length of the tcgen05
+    # accumulation chains and the order of the partial sums: results agree to the accumulation error, not bit for bit)
+    np.testing.assert_allclose(lz2.cpu().numpy(), lz.detach().cpu().numpy()[perm], rtol=1e-5)
 
 
 def test_n256_vs_oracle_medium_length():
@@ -164,7 +166,7 @@ def test_n512_count_identities_and_chunk_invariance():
     assert abs((gP.astype(np.float64) * pr).sum() - 3) <= 1e-3 * 3
     lz2 = inside_logZ(torch.tensor(W, device="cuda"), torch.tensor(T, device="cuda"), torch.tensor(pr, device="cuda"),
                       torch.tensor(tok), torch.tensor(lengths), path=_lib.PATH_TCGEN05, chunk_items=128)
-    np.testing.assert_allclose(lz2.cpu().numpy(), lz.detach().cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(lz2.cpu().numpy(), lz.detach().cpu().numpy(), rtol=1e-5)
 
 
 @pytest.mark.parametrize("mode,shape", [("1", (128, 8, 14, 9)), ("2", (128, 8, 14, 9)), ("2", (256, 8, 8, 5)), ("3", (128, 8, 14, 9))])
@@ -213,4 +215,4 @@ def test_full_size_config2_shape_inside_only():
     np.testing.assert_allclose(lz_t, lz_s, rtol=LOGZ_RTOL)
     perm = np.random.default_rng(5).permutation(B)
     lz_p = inside_logZ(*dev, torch.tensor(tok[perm]), torch.tensor(lengths[perm]), path=_lib.PATH_TCGEN05, chunk_items=512).cpu().numpy()
-    np.testing.assert_allclose(lz_p, lz_t[perm], rtol=2e-6)
+    np.testing.assert_allclose(lz_p, lz_t[perm], rtol=1e-5)
