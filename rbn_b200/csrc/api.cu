@@ -137,11 +137,13 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->item_e = take(ns * chunk * sizeof(int));
         o->ghat = take(ns * chunk * N * sizeof(__half));
         o->gabs = take(ns * chunk * N * sizeof(__half));
+        o->g32 = take(ns * chunk * N * sizeof(float));
+        o->gmax = take(32 * sizeof(int));
         o->gexp = take(ns * chunk * sizeof(int));
         o->acc = take(ns * chunk * N * sizeof(float));
         // split-sum cache: whole spans only, never more than the batch has, off in the two-stream schedules (their
         // forward and backward passes cut the diagonals differently)
-        const size_t per_span = N * N * sizeof(__half) + sizeof(int) + N * sizeof(__half);
+        const size_t per_span = N * N * sizeof(__half) + sizeof(int) + N * sizeof(__half) + N * sizeof(float);
         size_t cap = tune.overlap ? 0 : (size_t)d->cache_bytes / per_span;
         const size_t all_spans = B * (L * (L - 1) / 2);
         if (cap > all_spans) cap = all_spans;
@@ -149,6 +151,7 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->ycache = take(cap * N * N * sizeof(__half));
         o->ycache_e = take(cap * sizeof(int));
         o->gabs_all = take(cap * N * sizeof(__half));
+        o->g32_all = take(cap * N * sizeof(float));
     }
     o->total = off;
     return true;

@@ -62,7 +62,9 @@ struct WsLayout {
     size_t gy;          // half [nslot][chunk][N*N]
     size_t item_e;      // int32 [nslot][chunk]         E_m = max_j (e_ij + e_jk)
     size_t ghat;        // half [nslot][chunk][N]       item-normalised upstream gradient
-    size_t gabs;        // half [nslot][chunk][N]       absolutely scaled upstream gradient (for the count GEMM)
+    size_t gabs;        // half [nslot][chunk][N]       upstream gradient under one scale per launch (operand of the count GEMM)
+    size_t g32;         // float [nslot][chunk][N]      upstream gradient G, fp32 (k_prep_g -> k_gabs_convert)
+    size_t gmax;        // int32 [16] running max |G| (float bits) per scale group + float [16] the groups' inverse scales
     size_t gexp;        // int32 [nslot][chunk]
     size_t acc;         // float [nslot][chunk][N]  K-split partial sums of the rule GEMM's tail tiles
     // split-sum cache (RbnDesc.cache_bytes): the inside pass writes the Y of `cache_spans` spans here (widest diagonals
@@ -70,6 +72,7 @@ struct WsLayout {
     size_t ycache;      // half [cache_spans][N*N]
     size_t ycache_e;    // int32 [cache_spans]
     size_t gabs_all;    // half [cache_spans][N]  upstream-gradient rows of the kept spans (the count GEMM over them runs once, last)
+    size_t g32_all;     // float [cache_spans][N] the same rows in fp32, before their common scale is known
     long long cache_spans;
     size_t total;
     int Lp;

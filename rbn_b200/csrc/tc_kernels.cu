@@ -233,8 +233,7 @@ struct EpiGY {
     }
 };
 
-// K4: gW[(b,c)][a] += D * 2^kGabsShift
-static constexpr int kGabsShift = 8;
+// K4: gW[(b,c)][a] += D * scale, scale = 2^-shift of this launch's gradient rows (k_gabs_convert)
 static constexpr int kK2Stages = 7;      // TMA ring of the CTA-pair rule / count GEMMs: 7 x 32 KB is what fits (more bytes in flight)
 static constexpr int kSegBlocks = 64;   // k-blocks (of 64) per accumulation segment: K chain of 4096 -> bias ~2e-5
 struct EpiCounts {
@@ -242,13 +241,14 @@ struct EpiCounts {
     float* gW;
     int N;
     int bn;              // parents per tile (N, or 256 when N = 512)
+    const float* scale;  // device scalar written by k_gabs_convert
     __device__ void operator()(int mt, int nt, int row, uint32_t t0, uint32_t t1, uint8_t* es, uint32_t& nstore, bool partial) const {
         (void)es; (void)nstore; (void)partial;
         float* dst = gW + ((size_t)mt * kBM + row) * N + nt * bn;
         for (int c0 = 0; c0 < bn; c0 += 32) {
             float v[32];
             ptx::tmem_ld32_sum(t0, t1, c0, v);
-            const float sc = (float)(1 << kGabsShift);
+            const float sc = __ldg(scale);
             if (partial) {        // several K-split units add into the same tile
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -1319,13 +1319,14 @@ __global__ void k_tc_emission_bwd(int N, int L, int Lp, int nt, const int* __res
         }
     }
 }
-// upstream gradient of one chunk:  G = alpha * 2^-e_new ;  Ghat = G * 2^wexp[a] normalised per item ; Gabs = G * 2^-8
+// upstream gradient of one chunk:  G = alpha * 2^-e_new ;  Ghat = G * 2^wexp[a] normalised per item (fp16, operand of the
+// gY GEMM) ; G itself in fp32 plus the running max |G| of the launch group (k_gabs_convert makes the count GEMM's operand)
 // One WARP per span (8 spans per CTA), N / 32 values per lane: no block-level synchronisation, an eighth of the CTAs.
 static constexpr int kPrepWarps = 8;
 __global__ void __launch_bounds__(kPrepWarps * 32)
 k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, const int* __restrict__ lengths, const int* __restrict__ ce,
          const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
-         __half* __restrict__ ghat, __half* __restrict__ gabs, int* __restrict__ gexp) {
+         __half* __restrict__ ghat, float* __restrict__ g32, int* __restrict__ gmax_bits, int* __restrict__ gexp) {
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);
     if (t >= rows) return;                          // rows = cnt rounded up to 64: the pad rows are written as zeros
@@ -1337,7 +1338,7 @@ k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, 
     const bool valid = (t < cnt) && (i + w <= lengths[t < cnt ? b : 0]);
     constexpr int kMaxPerLane = 16;                 // N <= 512
     float g[kMaxPerLane], gs[kMaxPerLane];
-    float mx = 0.f;
+    float mx = 0.f, mxg = 0.f;
     const int per = N >> 5;
     if (valid) {
         const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
@@ -1350,25 +1351,52 @@ k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, 
                 g[q] = ldexpf(row[a], -e_new);
                 gs[q] = ldexpf(g[q], wexp[a]);
                 mx = fmaxf(mx, fabsf(gs[q]));
+                mxg = fmaxf(mxg, fabsf(g[q]));
             }
         }
     } else {
 #pragma unroll
         for (int q = 0; q < kMaxPerLane; ++q) g[q] = gs[q] = 0.f;
     }
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mxg = fmaxf(mxg, __shfl_xor_sync(0xffffffffu, mxg, o));
+    }
     int eg = 0;
     if (mx > 0.f) frexpf(mx, &eg);
+    if (lane == 0 && mxg > 0.f && mxg <= 3.0e38f) atomicMax(gmax_bits, __float_as_int(mxg));   // non-negative floats order like ints
 #pragma unroll
     for (int q = 0; q < kMaxPerLane; ++q) {
         if (q < per) {
             const int a = q * 32 + lane;
             ghat[(size_t)t * N + a] = __float2half_rn(ldexpf(gs[q], -eg));
-            const float ga = fminf(fmaxf(ldexpf(g[q], -kGabsShift), -65504.f), 65504.f);
-            if (t < gabs_rows) gabs[(size_t)t * N + a] = __float2half_rn(ga);     // (cached spans: packed rows, no pad rows)
+            if (t < gabs_rows) g32[(size_t)t * N + a] = g[q];     // (cached spans: packed rows, no pad rows)
         }
     }
     if (lane == 0) gexp[t] = eg;
+}
+
+// Operand of the count GEMM: G rows in fp16 under ONE power-of-two scale for the whole launch (the GEMM sums over spans,
+// so a per-span scale cannot be factored out).  The scale puts the largest |G| of the launch at 2^14: every entry down
+// to 2^-28 of it stays a NORMAL fp16 number.  (Round 1 used a fixed 2^-8, which left the bulk of the posterior mass --
+// entries of 1e-5 .. 1e-2 -- in the subnormal range, which the tensor core does not honour: -6e-4 on the counts at
+// N = 512.)  `scale` receives the inverse factor for the GEMM's epilogue.
+__global__ void k_gabs_convert(long long n, const float* __restrict__ g32, __half* __restrict__ g16, const int* __restrict__ gmax_bits,
+                               float* __restrict__ scale) {
+    const float mx = __int_as_float(*gmax_bits);
+    int e = 0;
+    if (mx > 0.f) frexpf(mx, &e);
+    const int shift = 14 - e;                       // max * 2^shift in [2^13, 2^14)
+    if (blockIdx.x == 0 && threadIdx.x == 0) *scale = ldexpf(1.0f, -shift);
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(g32 + i);
+        __half2 lo = __floats2half2_rn(ldexpf(v.x, shift), ldexpf(v.y, shift));
+        __half2 hi = __floats2half2_rn(ldexpf(v.z, shift), ldexpf(v.w, shift));
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(g16 + i) = o;
+    }
 }
 
 // =======================================================================================================================
@@ -1434,6 +1462,12 @@ struct TcCtx {
     // absolutely scaled upstream gradient rows of a unit: cached units keep them (packed like their Y) until the ONE count
     // GEMM over all cached spans at the end of the outside pass
     __half* gabs_of(const Unit& u) const { return u.coff >= 0 ? (__half*)(base + ws->gabs_all) + (size_t)u.coff * N : gabs(u.slot); }
+    float* g32_of(const Unit& u) const {
+        return u.coff >= 0 ? (float*)(base + ws->g32_all) + (size_t)u.coff * N : (float*)(base + ws->g32) + (size_t)u.slot * chunk * N;
+    }
+    // [0]: max |G| (float bits) of the kept spans, [1 + slot]: of the unit in that slot; gscale likewise (written by k_gabs_convert)
+    int* gmax(int i) const { return (int*)(base + ws->gmax) + i; }
+    float* gscale(int i) const { return (float*)(base + ws->gmax) + 16 + i; }
     int* e_of(const Unit& u) const { return u.coff >= 0 ? (int*)(base + ws->ycache_e) + (size_t)u.coff : item_e(u.slot); }
 };
 
@@ -1742,7 +1776,8 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             // uniform split -- same constants as tail_splits_for; a pair then owns ~2 units with exposed epilogues
             const int per = (int)(((long long)T * shape2.k_blocks + pairs - 1) / pairs);
             const double t_sk = per * 0.34 + (double)(pairs + T) * 0.122 + 8.0 + 2 * 4.0;
-            if (per >= 8 && t_sk < t_split) {
+            static const int streamk = env_int("RBN_TC_STREAMK", 1);
+            if (streamk && per >= 8 && t_sk < t_split) {
                 shape2.sk_per = per;
                 shape2.short_units = per <= kSegBlocks ? 1 : 0;
                 RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot), 0, (size_t)cnt * c.N * sizeof(float), st));
@@ -1870,7 +1905,16 @@ static int launch_k4_bn(TcCtx& c, const Unit& u, float* gW, cudaStream_t st, int
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, c.gabs_of(u), (uint64_t)c.N, (uint64_t)cnt, (uint64_t)c.N * 2, 64);   // MN-major B: [K=items][N=a]
     if (rc) return rc;
-    EpiCounts epi{gW, c.N, BN};
+    const int gi = u.coff >= 0 ? 0 : 1 + u.slot;      // scale group: all kept spans, or this unit alone
+    {
+        const long long n = (long long)cnt * c.N;
+        int blocks = (int)((n / 4 + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        ProfScope ps(KC_PREP, st);
+        k_gabs_convert<<<blocks, 256, 0, st>>>(n, c.g32_of(u), c.gabs_of(u), c.gmax(gi), c.gscale(gi));
+    }
+    RBN_LAUNCH_CHECK("k_gabs_convert");
+    EpiCounts epi{gW, c.N, BN, c.gscale(gi)};
     const int n_tiles = c.N / BN;
     if (n_tiles > 1 && !use_pairs()) {
         set_error("N = %d needs the CTA-pair kernels (unset RBN_TC_1CTA)", c.N);
@@ -1931,7 +1975,9 @@ static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     const size_t stage_bytes = 16384 + (size_t)Npad * 128;
     const size_t fixed = 65536 + 512 + 2048 + 1024;          // reduce staging, barriers, split factors, alignment
     int stages = (int)((232448 - fixed) / stage_bytes);
+    static const int stage_cap = env_int("RBN_TC_K5_STAGES", kK5MaxStages);
     if (stages > kK5MaxStages) stages = kK5MaxStages;
+    if (stages > stage_cap && stage_cap >= 2) stages = stage_cap;
     size_t smem = (size_t)stages * stage_bytes + fixed;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_childgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < sms ? cnt : sms;
@@ -2019,6 +2065,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     RBN_CUDA_CHECK(cudaMemsetAsync(gW, 0, (size_t)N * N * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gT, 0, (size_t)d->V * N * sizeof(float), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(gPrior, 0, (size_t)N * sizeof(float), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(c.gmax(0), 0, 32 * sizeof(int), st));
     { ProfScope ps(KC_OTHER, st); k_tc_outside_seed<<<B, 128, 0, st>>>(N, L, c.Lp, prior, lengths, c.cv, (const float*)(base + ws.zroot), coef, c.alpha, gPrior); }
     RBN_LAUNCH_CHECK("k_tc_outside_seed");
 
@@ -2048,10 +2095,11 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
             // split-sum: read back from the cache when the inside pass kept it, recomputed otherwise
             if (u.coff < 0 && (rc = launch_k1(c, u, S.st[0], S.sms[0], S.pair_launch))) break;
             if (last_prev[u.g] >= 0) S.wait(0, evK5[last_prev[u.g]]);            // alpha of this diagonal is complete
-            int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros (they are K rows of the count GEMM tail)
+            int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros
+            if (u.coff < 0) RBN_CUDA_CHECK(cudaMemsetAsync(c.gmax(1 + u.slot), 0, sizeof(int), S.st[0]));
             { ProfScope ps(KC_PREP, S.st[0]);
               k_prep_g<<<(pg + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, pg, u.coff >= 0 ? cnt : pg, lengths, c.ce, c.e_of(u), c.wexp, c.alpha,
-                                             c.ghat(u.slot), c.gabs_of(u), c.gexp(u.slot)); }
+                                             c.ghat(u.slot), c.g32_of(u), c.gmax(u.coff >= 0 ? 0 : 1 + u.slot), c.gexp(u.slot)); }
             RBN_LAUNCH_CHECK("k_prep_g");
             S.wait(1, S.record(0));
             // expected rule counts: spans whose Y sits in the cache wait for ONE count GEMM over all of them after the
