@@ -1254,35 +1254,63 @@ __global__ void k_copy_width1(int N, int L, int Lp, const int* __restrict__ leng
         r[a] = h;
     }
 }
-// max-shift epilogue of the K-split tail tiles of the rule GEMM: acc[t][a] (fp32 sums) -> chart, exponents, fp16 copies
-__global__ void k_rule_finalize(int N, int L, int Lp, int w, int m0, int t_begin, int cnt, const int* __restrict__ lengths,
-                                const float* __restrict__ wscale, const int* __restrict__ item_e,
-                                const float* __restrict__ acc, float* __restrict__ cv, int* __restrict__ ce,
-                                __half* __restrict__ lc, __half* __restrict__ rc, const float* __restrict__ wdens, float kc) {
-    __shared__ float red[32];
-    const int t = t_begin + blockIdx.x;
+// max-shift epilogue of the K-split tail tiles of the rule GEMM: acc[t][a] (fp32 sums) -> chart, exponents, fp16 copies.
+// One WARP per span (8 spans per CTA, N / 32 values per lane, float4 accesses): no block-level synchronisation and an
+// eighth of the CTAs of the former one-CTA-per-span version (20 -> ~8 us per diagonal of 16 k spans; 508 launches per step).
+static constexpr int kFinWarps = 8;
+__global__ void __launch_bounds__(kFinWarps * 32)
+k_rule_finalize(int N, int L, int Lp, int w, int m0, int t_begin, int cnt, const int* __restrict__ lengths,
+                const float* __restrict__ wscale, const int* __restrict__ item_e,
+                const float* __restrict__ acc, float* __restrict__ cv, int* __restrict__ ce,
+                __half* __restrict__ lc, __half* __restrict__ rc, const float* __restrict__ wdens, float kc) {
+    const int lane = threadIdx.x & 31;
+    const int t = t_begin + blockIdx.x * kFinWarps + (threadIdx.x >> 5);
     if (t >= cnt) return;
     const int nI = L - w + 1;
     const int m = m0 + t;
     const int b = m / nI, i = m - b * nI, k = i + w;
     if (k > lengths[b]) return;
-    const int a = threadIdx.x;                       // blockDim.x == N
-    const float x = acc[(size_t)t * N + a] * wscale[a] * (1.0f + kc * wdens[a]);   // kc: truncation compensation of this launch's chains
-    float mx = x;
+    constexpr int kMaxQuads = 4;                     // N <= 512: N / 128 float4 per lane
+    const int quads = N >> 7;                        // (N = 64, 192: the tail quad is handled by the lanes that own it)
+    float4 x[kMaxQuads];
+    float mx = 0.f;
+    const float* src = acc + (size_t)t * N;
+#pragma unroll
+    for (int q = 0; q < kMaxQuads; ++q) {
+        const int a = (q * 32 + lane) * 4;
+        x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q <= quads && a < N) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + a));      // written by red.global.add: read at L2
+            const float4 sc = *reinterpret_cast<const float4*>(wscale + a);
+            const float4 dn = *reinterpret_cast<const float4*>(wdens + a);
+            // kc: truncation compensation of this launch's accumulation chains
+            x[q] = make_float4(v.x * sc.x * (1.0f + kc * dn.x), v.y * sc.y * (1.0f + kc * dn.y),
+                               v.z * sc.z * (1.0f + kc * dn.z), v.w * sc.w * (1.0f + kc * dn.w));
+            mx = fmaxf(mx, fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w)));
+        }
+    }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((a & 31) == 0) red[a >> 5] = mx;
-    __syncthreads();
-    mx = red[0];
-    for (int q = 1; q < (blockDim.x >> 5); ++q) mx = fmaxf(mx, red[q]);
     int e_new = 0;
     if (mx > 0.f) frexpf(mx, &e_new);
-    const float v = ldexpf(x, -e_new);
     const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
-    cv[cell * N + a] = v;
-    const __half h = __float2half_rn(v);
-    lc[((size_t)((size_t)b * L + i) * Lp + k) * N + a] = h;
-    rc[((size_t)((size_t)b * (L + 1) + k) * Lp + i) * N + a] = h;
-    if (a == 0) ce[cell] = item_e[t] + e_new;
+    float* cvp = cv + cell * N;
+    __half* lcp = lc + ((size_t)((size_t)b * L + i) * Lp + k) * N;
+    __half* rcp = rc + ((size_t)((size_t)b * (L + 1) + k) * Lp + i) * N;
+#pragma unroll
+    for (int q = 0; q < kMaxQuads; ++q) {
+        const int a = (q * 32 + lane) * 4;
+        if (q <= quads && a < N) {
+            const float4 v = make_float4(ldexpf(x[q].x, -e_new), ldexpf(x[q].y, -e_new), ldexpf(x[q].z, -e_new), ldexpf(x[q].w, -e_new));
+            *reinterpret_cast<float4*>(cvp + a) = v;
+            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            uint2 hp;
+            hp.x = *reinterpret_cast<const uint32_t*>(&h0);
+            hp.y = *reinterpret_cast<const uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(lcp + a) = hp;
+            *reinterpret_cast<uint2*>(rcp + a) = hp;
+        }
+    }
+    if (lane == 0) ce[cell] = item_e[t] + e_new;
 }
 
 // root seed into the start-major outside chart (and the prior gradient)
@@ -1364,7 +1392,10 @@ k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, 
     }
     int eg = 0;
     if (mx > 0.f) frexpf(mx, &eg);
-    if (lane == 0 && mxg > 0.f && mxg <= 3.0e38f) atomicMax(gmax_bits, __float_as_int(mxg));   // non-negative floats order like ints
+    if (mxg > 0.f && mxg <= 3.0e38f) {                // non-negative floats order like ints; one atomic per warp, aggregated by
+        const int bits = __float_as_int(mxg);         // the hardware when several warps of an SM hit the address together
+        if (lane == 0 && bits > *(volatile int*)gmax_bits) atomicMax(gmax_bits, bits);
+    }
 #pragma unroll
     for (int q = 0; q < kMaxPerLane; ++q) {
         if (q < per) {
@@ -1756,7 +1787,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         rc = launch_tc_gemm2<false, false, BN, 3, 0, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule,half>", KC_RULE);
         if (rc) return rc;
         { ProfScope ps(KC_RULE_FIN, st);
-          k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
+          k_rule_finalize<<<(cnt + kFinWarps - 1) / kFinWarps, kFinWarps * 32, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
         RBN_LAUNCH_CHECK("k_rule_finalize");
         return RBN_OK;
     }
@@ -1784,7 +1815,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
                 rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
                 if (rc) return rc;
                 { ProfScope ps(KC_RULE_FIN, st);
-                  k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(per)); }
+                  k_rule_finalize<<<(cnt + kFinWarps - 1) / kFinWarps, kFinWarps * 32, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(per)); }
                 RBN_LAUNCH_CHECK("k_rule_finalize");
                 return RBN_OK;
             }
@@ -1797,7 +1828,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
-              k_rule_finalize<<<cnt, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
+              k_rule_finalize<<<(cnt + kFinWarps - 1) / kFinWarps, kFinWarps * 32, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
@@ -1810,7 +1841,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
-              k_rule_finalize<<<cnt - t_begin, c.N, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc((shape2.k_blocks + splits - 1) / splits)); }
+              k_rule_finalize<<<(cnt - t_begin + kFinWarps - 1) / kFinWarps, kFinWarps * 32, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc((shape2.k_blocks + splits - 1) / splits)); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
