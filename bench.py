@@ -242,12 +242,75 @@ def run_reference_gauss(args, wl):
                           e2e=dict(value=v, unit="seq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)), flush=True)
 
 
+def literal_reference_available(wl):
+    """The UNMODIFIED reference (rbnet's own Python loop nest + torch.autograd) can be timed where it is importable
+    (/root/reference, or the copy oracle/vendor_reference.py makes at build time) and where one pass finishes in seconds:
+    configs[0].  At C3 it needs ~4 h per sequence: there the vectorised port is the CPU arm."""
+    if wl.get("gauss") or wl["N"] > 16 or wl["L"] > 24:
+        return False
+    try:
+        from oracle.reference_loader import reference_available
+        return reference_available()
+    except Exception:
+        return False
+
+
+def literal_reference_sample(wl, reps, threads):
+    """seq/s of rbnet.SequentialRBN.inside() + backward() (tier T0) on sequence 0 of the workload, `threads` host threads."""
+    import numpy as np
+    import torch
+    from oracle.reference_loader import load_reference
+    from rbn_b200 import synth
+    ref = load_reference()
+    torch.set_num_threads(threads)
+    N, V, L = wl["N"], wl["V"], wl["L"]
+    rng = np.random.default_rng(0)          # the same weights build_model() gives this repo's model
+    rp = ref["pcfg"]
+    cell = rp.DiscreteCell(variable=rp.DiscreteNonTermVar(N), weights=rng.random((2, N)),
+                           transitions=[rp.DiscreteTerminalTransition(weights=rng.random((V, N))),
+                                        rp.DiscreteBinaryNonTerminalTransition(weights=rng.random((N, N, N)))])
+    prior = rp.DiscretePrior(struc_weights=np.ones(1), prior_weights=[rng.random(N)])
+    model = ref["sequential"].SequentialRBN(cells=[cell], prior=prior)
+    tok, _ = synth.synthetic_tokens(1, L, V, seed=1)
+    seq = [[int(y)] for y in tok[0]]
+    times, z = [], None
+    for _ in range(reps):
+        model.zero_grad()
+        t0 = time.perf_counter()
+        Z = model.inside(sequence=seq)
+        (-torch.log(Z)).backward()
+        times.append(time.perf_counter() - t0)
+        z = float(Z.detach())
+    return 1.0 / (sum(times) / len(times)), z
+
+
+def run_reference_literal(args, wl):
+    import torch
+    cores = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 1)):
+        literal_reference_sample(wl, 1, cores)
+    v_all, z = literal_reference_sample(wl, args.steps, cores)
+    v_one, _ = literal_reference_sample(wl, args.steps, 1)
+    sample = (f"rbnet (unmodified, {('/root/reference' if os.path.isdir('/root/reference/rbnet') else 'oracle/_ref copy')}) "
+              f"SequentialRBN.inside() + backward(), 1 sequence per step, N={wl['N']} L={wl['L']}; "
+              f"{v_all:.2f} seq/s on {cores} threads, {v_one:.2f} seq/s on 1 thread (the loop nest is Python-bound)")
+    line = dict(metric="inside+outside sequences/sec", value=v_all, unit="seq/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 / v_all, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=workload_config(wl, args.batch or wl["B"], int(os.environ.get("WORLD_SIZE", "1"))),
+                cpu_baseline=dict(value=v_all, unit="seq/s", cores=cores, kind="reference", sample=sample, value_1thread=v_one),
+                e2e=dict(value=v_all, unit="seq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0, Z=z)
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if wl.get("gauss"):
         return run_reference_gauss(args, wl)
+    if literal_reference_available(wl):
+        return run_reference_literal(args, wl)
     import torch
     torch.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: use the box's cores anyway
     vals = []
@@ -501,9 +564,18 @@ def run_ours(args, wl, secondary=False):
                                          "the step is bandwidth-bound, see DESIGN.md section 3.4")
     launches = int(sum(v[1] for v in prof.values()))
     cpu_v = parity = None
+    cpu_kind = "port"
     if world == 1 and not args.skip_cpu and not secondary:
         cpu_v, cpu_t, cpu_samp, cores = cpu_sample(wl)
         parity = parity_check(wl, batch_logz0=float(lz_host[0]))
+        if literal_reference_available(wl):      # configs[0]: the literal reference is runnable: it is the CPU baseline
+            port_v = cpu_v
+            cores = os.cpu_count() or 1
+            cpu_v, _ = literal_reference_sample(wl, 5, cores)
+            one, _ = literal_reference_sample(wl, 5, 1)
+            cpu_kind = "reference"
+            cpu_samp = (f"rbnet (unmodified) SequentialRBN.inside() + backward(), sequence 0, 5 repetitions: {cpu_v:.2f} seq/s on "
+                        f"{cores} threads, {one:.2f} on 1 thread; the vectorised fp64 port (oracle/) does {port_v:.1f} seq/s")
     line = dict(metric="inside+outside sequences/sec" if wl["outside"] else "inside sequences/sec",
                 value=world * B / (ms_step * 1e-3), unit="seq/s", n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
@@ -516,7 +588,7 @@ def run_ours(args, wl, secondary=False):
                 gpu_launches=launches, roofline=roofline, clocks=clocks,
                 logZ_mean=float(np.mean(lz_host)), count_check=count_check, fixture_check=fixture_check)
     if cpu_v is not None:
-        line["cpu_baseline"] = dict(value=cpu_v, unit="seq/s", cores=cores, kind="port", sample=cpu_samp)
+        line["cpu_baseline"] = dict(value=cpu_v, unit="seq/s", cores=cores, kind=cpu_kind, sample=cpu_samp)
     if parity is not None:
         line["parity_check"] = parity
     return line

@@ -11,8 +11,11 @@ import importlib
 import os
 import sys
 
-REFERENCE_ROOT = "/root/reference"
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference in the build container; on the GPU box the byte-for-byte copy oracle/vendor_reference.py made at build
+# time (oracle/_ref/, git-ignored build output)
+REFERENCE_ROOT = "/root/reference" if os.path.isdir("/root/reference/rbnet") else os.path.join(_HERE, "_ref")
+_SHIMS = os.path.join(_HERE, "ref_shims")
 
 
 def reference_available():
@@ -22,7 +25,7 @@ def reference_available():
 def load_reference():
     """Return the reference's modules as a dict {name: module}; raises if /root/reference is absent."""
     if not reference_available():
-        raise RuntimeError("/root/reference is not present (GPU box?) -- use the committed fixtures instead")
+        raise RuntimeError("neither /root/reference nor oracle/_ref is present -- use the committed fixtures instead")
     for p in (_SHIMS, REFERENCE_ROOT):          # appended, not prepended: /root/reference has a `tests` package of its
         if p not in sys.path:                   # own that must not shadow this repo's (spawned test workers import ours)
             sys.path.append(p)
