@@ -5,7 +5,7 @@ __graft_entry__.smoke() and by bench.py's cpu_baseline / `--impl reference` legs
 checker or as the timed CPU arm -- never as the product.
 
 Parity status: PINNED.  tests/test_oracle.py checks every function below against
-  (1) the golden vectors held by the reference's own tests (tests/golden/reference_tests.json restates
+  (1) the golden vectors held by the reference's own tests (restated in tests/test_oracle.py from
       /root/reference/tests/test_pcfg.py:14-35,37-81 and /root/reference/tests/test_base.py:47-295), and
   (2) outputs of the UNMODIFIED reference run in the build container (tests/golden/*.npz written by
       oracle/make_golden.py, which imports /root/reference through oracle/reference_loader.py).

@@ -111,7 +111,5 @@ def m_step(model, counts, pseudo_count=0.0):
 def em_step(model, tokens=None, lengths=None, sequences=None, micro_batch=512, pseudo_count=0.0):
     """One EM iteration; returns the mean log Z (over all ranks' finite sequences) BEFORE the update."""
     total, n_ok, counts = expected_counts(model, tokens, lengths, sequences, micro_batch)
-    m_step(model, counts, pseudo_count)
-    if hasattr(model, "_engine"):
-        pass                                                  # the engine re-flattens the grammar on every pass
+    m_step(model, counts, pseudo_count)        # (the engine re-flattens the grammar on every pass: nothing to invalidate)
     return float(total / torch.clamp(n_ok, min=1.0))

@@ -85,8 +85,23 @@ class GaussianRBN(torch.nn.Module):
         eye = np.eye(dim)
 
         def tril(c):
+            # a covariance may be given the three ways rbnet.multivariate_normal.MultivariateNormal takes its matrix
+            # argument (multivariate_normal.py:150): full [D, D], diagonal [D] (variances) or scalar (one variance), or
+            # as a MultivariateNormal whose covariance is taken.  The Parameter keeps the given parametrisation:
+            # lower-triangular factor, vector of standard deviations, or one standard deviation.
+            from .multivariate_normal import MultivariateNormal
+            if isinstance(c, MultivariateNormal):
+                c = c.covariance_matrix.detach().cpu().numpy()
             c = eye if c is None else np.asarray(c, dtype=np.float64)
-            return torch.nn.Parameter(torch.linalg.cholesky(torch.as_tensor(c, dtype=torch.float64)))
+            if c.ndim == 2:
+                if c.shape != (dim, dim):
+                    raise ValueError(f"covariance of shape {c.shape} does not match dim={dim}")
+                return torch.nn.Parameter(torch.linalg.cholesky(torch.as_tensor(c, dtype=torch.float64)))
+            if c.ndim == 1 and c.shape[0] != dim:
+                raise ValueError(f"Last dimension of tensor has size {c.shape[0]}, cannot expand to diagonal of size {dim}")
+            if c.ndim > 1 or (c < 0).any():
+                raise ValueError("a covariance is a non-negative scalar, a vector of variances or a [D, D] matrix")
+            return torch.nn.Parameter(torch.sqrt(torch.as_tensor(c, dtype=torch.float64)))
 
         self.term_scale_tril = tril(cov_term)
         self.left_scale_tril = tril(cov_left)
@@ -97,10 +112,12 @@ class GaussianRBN(torch.nn.Module):
         sw = torch.as_tensor(np.asarray(struct_weights, dtype=np.float64))
         self.struct_log_p = torch.nn.Parameter(torch.log(sw / sw.sum()))
 
-    @staticmethod
-    def _cov(tril):
-        low = torch.tril(tril)
-        return low @ low.T
+    def _cov(self, scale):
+        if scale.dim() == 2:                       # full: Sigma = L L^T
+            low = torch.tril(scale)
+            return low @ low.T
+        eye = torch.eye(self.dim, dtype=scale.dtype, device=scale.device)
+        return eye * (scale * scale)               # diagonal [D] or scalar []: Sigma = diag(s^2)
 
     def log_inside_batch(self, y, lengths=None):
         """log marginal likelihood [B] of observation sequences y [B, L, D] (float), differentiable."""

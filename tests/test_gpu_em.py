@@ -73,3 +73,44 @@ def test_em_on_the_tensor_core_path_and_fused_lognormalize():
     ref = x.double() - torch.logsumexp(x.double(), dim=(0, 1), keepdim=True)
     out = em._lognormalize_(x.clone(), (0, 1))
     np.testing.assert_allclose(out.cpu().numpy(), ref.float().cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_length_bucketed_batches_feed_the_tensor_core_em_step():
+    """SURVEY 8(f).2 end to end: a ragged corpus -> rbn_b200.data.LengthBucketedBatches (tokenise once, bucket by length,
+    pinned int32 batches) -> em.expected_counts on the tcgen05 path (N = 64), batch by batch -> the summed expected
+    counts equal the fp64 oracle's over the whole corpus.  The batches stay host tensors: the library copies them to the
+    device itself and a pass never synchronises."""
+    from oracle import inside_oracle as O
+    from rbn_b200 import data, em, engine
+    N, V = 64, 8
+    model = _model(N, V, seed=41)
+    rng = np.random.default_rng(42)
+    corpus = [rng.integers(0, V, int(n)).astype(np.int32) for n in rng.integers(3, 15, 37)]
+    loader = data.LengthBucketedBatches(corpus, batch_size=8, max_work=8 * 12.0 ** 3, shuffle=True, seed=1, drop_last=False)
+    cps = em.constrained_parameters(model)
+    sums = [torch.zeros_like(p, dtype=torch.float64) for _, p in cps]
+    seen, total = [], 0.0
+    for tok, lengths, idx in loader:
+        assert not tok.is_cuda and tok.dtype == torch.int32 and (not torch.cuda.is_available() or tok.is_pinned())
+        # the tensor-core path is what runs for these batches (N = 64, L <= 129)
+        assert engine._padded_cardinality(N, tok.shape[0] * tok.shape[1] * (tok.shape[1] - 1) // 2, tok.shape[1]) == 64
+        t, n_ok, counts = em.expected_counts(model, tok, lengths, reduce=False)
+        assert int(n_ok) == tok.shape[0]
+        total += float(t)
+        for s, c in zip(sums, counts):
+            s += c.double()
+        seen += idx.tolist()
+    assert sorted(seen) == list(range(len(corpus)))
+    W, T, pr = (x.detach().cpu().double().numpy() for x in model._get_engine().flatten())
+    L = max(len(s) for s in corpus)
+    tok_all = -np.ones((len(corpus), L), dtype=np.int64)
+    for b, s in enumerate(corpus):
+        tok_all[b, :len(s)] = s
+    lens = np.array([len(s) for s in corpus])
+    lz, gW, gT, gP = O.flat_inside_with_grads(W, T, pr, tok_all[:, :, None], lens)
+    assert abs(total - float(lz.sum())) <= 1e-4 * abs(float(lz.sum()))
+    by_shape = {tuple(c.shape): c.cpu().numpy() for c in sums}
+    for got, ref in ((by_shape[(N, N, N)], gW.numpy() * W), (by_shape[(V, N)], gT.numpy() * T), (by_shape[(N,)], gP.numpy() * pr)):
+        assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max()
+        assert np.linalg.norm(got - ref) <= 1e-3 * np.linalg.norm(ref)
+    assert abs(by_shape[(N, N, N)].sum() - (lens - 1).sum()) < 1e-3 * lens.sum()
