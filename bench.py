@@ -365,7 +365,10 @@ def run_ours(args, wl, secondary=False):
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
-    steps, warmup = (min(args.steps, 2), min(args.warmup, 1)) if secondary else (args.steps, args.warmup)
+    if secondary:       # bounded: a C5 step takes ~10 s; the small workloads take milliseconds (3 warm-ups, 5 steps)
+        steps, warmup = (min(args.steps, 2), min(args.warmup, 1)) if wl["N"] >= 512 else (5, 3)
+    else:
+        steps, warmup = args.steps, args.warmup
 
     N, V, L, B = wl["N"], wl["V"], wl["L"], (wl["B"] if secondary else (args.batch or wl["B"]))
     W, T, pr = synth.synthetic_grammar(N, V, seed=0)
@@ -594,12 +597,30 @@ def run_ours(args, wl, secondary=False):
     return line
 
 
+def _brief(line):
+    """The part of a workload's line that goes under `other_workloads`."""
+    r = line.get("roofline") or {}
+    return dict(workload=line["config"]["workload"], metric=line["metric"], value=line["value"], unit=line["unit"],
+                ms_per_step=line["ms_per_step"], steps=line["steps"], warmup=line["warmup"], e2e=line["e2e"]["value"],
+                roofline=dict(bound=r.get("bound"), kernel=r.get("kernel"), frac=r.get("frac"), step_frac=r.get("step_frac")),
+                kernels_ms_per_step=r.get("kernels_ms_per_step"), gpu_launches=line["gpu_launches"])
+
+
 def finish_ours(args, wl):
     """Print this arm's ONE JSON line.  With more than one GPU the line also carries, under `secondary`, the C5 step
-    (BASELINE configs[4]: N = 512, 1024 sequences per GPU, EM E-step + count all-reduce) measured in the same run."""
+    (BASELINE configs[4]: N = 512, 1024 sequences per GPU, EM E-step + count all-reduce) measured in the same run; on one
+    GPU, under `other_workloads`, short measurements of the other BASELINE configurations (configs[0], [1], [3])."""
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     line = run_ours(args, wl)
+    if world == 1 and args.workload == "c3" and not args.no_secondary and not args.batch and line is not None:
+        others = {}
+        for name in ("c1", "c2"):
+            others[name] = _brief(run_ours(args, WORKLOADS[name], secondary=True))
+        g = run_gauss(args, WORKLOADS["c4"], ret=True)
+        if g is not None:
+            others["c4"] = _brief(g)
+        line["other_workloads"] = others
     if world > 1 and args.workload == "c3" and not args.no_secondary:
         sec = run_ours(args, WORKLOADS["c5"], secondary=True)
         if line is not None and sec is not None:
@@ -610,7 +631,7 @@ def finish_ours(args, wl):
         dist.destroy_process_group()
 
 
-def run_gauss(args, wl):
+def run_gauss(args, wl, ret=False):
     """BASELINE configs[3]: fp64 Gaussian chart pass (csrc/gauss_kernels.cu).  HBM roofline per SURVEY.md 8(d): per cell
     4 (1 + D + D^2) bytes at the reference's fp32 = 292 B (this build stores fp64: 584 B); a pass re-reads two child
     cells per split, 2 (L^3 - L)/6 cells per sequence; inside + outside = forward reads + backward reads and adjoint
@@ -629,7 +650,8 @@ def run_gauss(args, wl):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
-    D, L, B = wl["D"], wl["L"], args.batch or wl["B"]
+    D, L, B = wl["D"], wl["L"], (wl["B"] if ret else (args.batch or wl["B"]))
+    steps_g, warm_g = (5, 3) if ret else (args.steps, args.warmup)
     syn = synth.synthetic_gauss(D, B, L, seed=10 + rank)
     y_np = syn["y"]
     model = GaussianRBN(D, cov_term=syn["cov_term"], cov_left=syn["cov_left"], cov_right=syn["cov_right"],
@@ -662,18 +684,18 @@ def run_gauss(args, wl):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, out
 
-    for _ in range(args.warmup):
+    for _ in range(warm_g):
         step(y_d)
     _lib.profile_read(reset=True)
     _lib.profile_enable(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_step, lz = timed(lambda: step(y_d), args.steps)
+    ms_step, lz = timed(lambda: step(y_d), steps_g)
     clocks = sampler.stop() if rank == 0 else None
     prof = _lib.profile_read(reset=True)
     _lib.profile_enable(False)
-    ms_e2e, _ = timed(lambda: float(step(y_pin.to(dev, non_blocking=True)).sum()), args.steps)
+    ms_e2e, _ = timed(lambda: float(step(y_pin.to(dev, non_blocking=True)).sum()), steps_g)
     if rank != 0:
         return
     peaks = load_peaks()
@@ -682,9 +704,9 @@ def run_gauss(args, wl):
     alg_bytes = 3.0 * B * 2 * splits * cell_bytes             # child-cell reads fwd + bwd + adjoint updates
     diag_ms = prof["simt_inside"][0] + prof["simt_outside"][0]      # k_gauss_diag + k_gauss_bwd_diag
     diag_launches = prof["simt_inside"][1] + prof["simt_outside"][1]
-    ach = alg_bytes * args.steps / (diag_ms * 1e-3) / 1e9 if diag_ms > 0 else None
+    ach = alg_bytes * steps_g / (diag_ms * 1e-3) / 1e9 if diag_ms > 0 else None
     cpu = None
-    if world == 1 and not args.skip_cpu:
+    if world == 1 and not args.skip_cpu and not ret:
         from oracle import gauss_oracle as GO      # cpu_baseline leg only
         t0 = time.perf_counter()
         n_cpu = 0
@@ -698,7 +720,7 @@ def run_gauss(args, wl):
         cpu = dict(value=n_cpu / dt, unit="seq/s", cores=torch.get_num_threads(), kind="port",
                    sample=f"{n_cpu} sequences of the same workload, fp64 torch restatement on rbnet.multivariate_normal's algebra, {dt:.1f}s")
     line = dict(metric="inside+gradient sequences/sec", value=world * B / (ms_step * 1e-3), unit="seq/s", n_gpus=world,
-                steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
+                steps=steps_g, warmup=warm_g, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
                 config=workload_config(wl, B, world),
                 impl_notes=dict(l2="chart (80 MB) fits L2: latency-bound launch train, no flush"),
@@ -710,10 +732,12 @@ def run_gauss(args, wl):
                               peak_source=f"{peaks['source']} hbm_gbs", launches=int(diag_launches),
                               avg_launch_ms=(diag_ms / diag_launches) if diag_launches else None,
                               algorithmic_bytes_per_step=alg_bytes,
-                              kernels_ms_per_step={k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]}),
+                              kernels_ms_per_step={k: round(v[0] / steps_g, 3) for k, v in prof.items() if v[1]}),
                 clocks=clocks, logZ_mean=float(lz.detach().double().mean()))
     if cpu:
         line["cpu_baseline"] = cpu
+    if ret:
+        return line
     print(json.dumps(line), flush=True)
 
 

@@ -1433,7 +1433,11 @@ __global__ void k_gabs_convert(long long n, const float* __restrict__ g32, __hal
 // =======================================================================================================================
 // drivers
 // =======================================================================================================================
-static constexpr int kDefaultHints = 0;
+// default: bit 4 (rule / count GEMM operand streams: Y evict_first, W evict_last).  Measured (round 2, ncu DRAM bytes per
+// launch): without it the 2 GB of Y streaming through L2 per launch keep evicting the 33 MB of W, which is then re-read
+// from HBM ~8 times per launch (164 KB read per span against 131 KB of Y); no change in kernel time (these GEMMs are
+// tensor-bound), less HBM traffic and power.  Bits 1, 2, 8 changed nothing measurable and stay off.
+static constexpr int kDefaultHints = 4;
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return (e && *e) ? atoi(e) : dflt;
@@ -1835,7 +1839,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         if (splits > 1) {
             shape2.full_tiles = full;
             shape2.tail_splits = splits;
-            shape2.short_units = (full == 0 && (shape2.k_blocks + splits - 1) / splits <= kSegBlocks) ? 1 : 0;
+            shape2.short_units = (shape2.k_blocks <= kSegBlocks || (full == 0 && (shape2.k_blocks + splits - 1) / splits <= kSegBlocks)) ? 1 : 0;
             const int t_begin = full * 256;
             RBN_CUDA_CHECK(cudaMemsetAsync(c.acc(u.slot) + (size_t)t_begin * c.N, 0, (size_t)(cnt - t_begin) * c.N * sizeof(float), st));
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
@@ -1845,6 +1849,9 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
+        // N = 64: a whole tile is ONE accumulation segment (64 k-blocks), so consecutive tiles alternate between the two
+        // accumulators and a tile's max-shift epilogue runs behind the next tile's MMAs
+        shape2.short_units = (shape2.k_blocks <= kSegBlocks) ? 1 : 0;
         return launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
     }
     GemmShape shape{(cnt + 127) / 128, 1, (int)(NN / 64), 0, 1, 0};

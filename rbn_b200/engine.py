@@ -88,9 +88,17 @@ class _Pass:
         self._owner = _pool_take(dev, nbytes + 1024)
         if keep_split_sums and lib.rbn_resolve_path(ctypes.byref(self.desc)) == _lib.PATH_TCGEN05:
             # a retained workspace is used as it is (whatever cache fits in it); otherwise size one from the free memory
-            budget = (self._owner.numel() - nbytes - 16384) if self._owner is not None else _cache_budget(dev, nbytes)
-            self.desc.cache_bytes = max(0, budget)
-            nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
+            base = nbytes
+            if self._owner is None:
+                self.desc.cache_bytes = _cache_budget(dev, base)
+                nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
+            else:
+                room = self._owner.numel() - 1024
+                self.desc.cache_bytes = 1 << 60                   # everything the batch can use (the library clamps)...
+                nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
+                if nbytes > room:                                 # ...or what fits beside the rest (alignment slack: 4 x 1 KB)
+                    self.desc.cache_bytes = max(0, room - base - 8192)
+                    nbytes = lib.rbn_workspace_bytes(ctypes.byref(self.desc))
         # ragged batch: sort by length (longest first) so that diagonal w only visits the sequences that reach it
         # (rbn_inside_forward_sorted); `order[k]` = original index of the k-th sorted sequence, `pos[b]` its inverse
         self.order = self.pos = self.active = None
