@@ -276,10 +276,15 @@ struct EpiCounts {
 // (64 k-rows x 128 B, 128-byte swizzle).  Four "fix-up" warps fold the per-split scale c_j = 2^(e_ij + e_jk - E)
 // into the left-child slab in shared memory (and zero the rows past the last split); one thread issues the MMAs.
 //   warps 0-3 epilogue (TMEM -> fp16 -> Y)   warps 4-7 fix-up   warp 8 TMA producer   warp 9 MMA issuer / TMEM owner
-static constexpr int kK1Threads = 320;
+//   warps 10-13 (one CTA per SM only): second epilogue group.  Draining a span is 8 tiles of [128 x 64] (TMEM load,
+//   fp16 pack, swizzled st.shared, barrier, TMA store) -- with one group that was the longest stage of the per-span
+//   pipeline and the kernel followed the SM clock (137 ms per C3 step on a 1.75 GHz box, 167 ms on a 1.5 GHz one) instead
+//   of the HBM write rate; with two groups each accumulator (= half of a span) has its own four warps.
+template <int MINB>
+static constexpr int k1_threads() { return MINB == 1 ? 448 : 320; }
 
 template <int MINB>       // co-resident CTAs per SM the register budget is cut for (2 for small N)
-__global__ void __launch_bounds__(kK1Threads, MINB)
+__global__ void __launch_bounds__(k1_threads<MINB>(), MINB)
 k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ CUtensorMap tmRC,
               const __grid_constant__ CUtensorMap tmLC1, const __grid_constant__ CUtensorMap tmRC1,   // second K-slab (rows = Kpad - 64)
               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYtail,
@@ -338,7 +343,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     // zero the A atoms that lie beyond N (N = 64 or 192) in every stage: TMA never writes them
     if (a_atoms > l_atoms)
         for (int sidx = 0; sidx < stages; ++sidx)
-            for (uint32_t off = (uint32_t)l_atoms * 8192 + threadIdx.x * 16; off < (uint32_t)a_atoms * 8192; off += kK1Threads * 16)
+            for (uint32_t off = (uint32_t)l_atoms * 8192 + threadIdx.x * 16; off < (uint32_t)a_atoms * 8192; off += blockDim.x * 16)
                 *reinterpret_cast<uint4*>(smem + (size_t)sidx * stage_bytes + off) = make_uint4(0, 0, 0, 0);
     if (warp == 9) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::fence_proxy_async_smem();
@@ -476,11 +481,20 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < 4 || warp >= 10) {
         // ---------------- epilogue: TMEM -> fp16 -> smem tile -> TMA store into Y[t][b][c] ----------------
+        // Two groups (warps 0-3 and, when present, 10-13): with two accumulators, group g drains accumulator g -- half g of
+        // every span when a span has two halves, every other sub-item otherwise -- through its own staging tile.
+        const int grp = warp >= 10 ? 1 : 0;
+        const bool two_groups = (blockDim.x > 320) && (nslots == 2);
+        if (grp == 1 && !two_groups) goto k1_done;
+        {
         uint32_t nacc = 0, nstore = 0;
-        const int row = warp * 32 + lane;
-        const bool issuer = (threadIdx.x == 0);
+        const int qd = warp & 3;                      // TMEM lane quarter this warp may touch
+        const int row = qd * 32 + lane;
+        const int gt = grp ? (int)threadIdx.x - 320 : (int)threadIdx.x;      // thread index within the group
+        const bool issuer = (gt == 0);
+        uint8_t* gbuf = two_groups ? ybuf + grp * 16384 : ybuf;
         for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI;
@@ -488,8 +502,10 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                 // span beyond its sequence (ragged batch): its Y rows are still read (as A rows of the rule GEMM whose
                 // output row is dropped, as K rows of the count GEMM against a zero gradient row), so they must be
                 // finite -- write zeros; nothing else ever clears these buffers
-                uint4* dst = reinterpret_cast<uint4*>(Y + (size_t)t * N * N);
-                for (int q = threadIdx.x; q < N * N / 8; q += 128) dst[q] = make_uint4(0, 0, 0, 0);
+                if (grp == 0) {
+                    uint4* dst = reinterpret_cast<uint4*>(Y + (size_t)t * N * N);
+                    for (int q = gt; q < N * N / 8; q += 128) dst[q] = make_uint4(0, 0, 0, 0);
+                }
                 continue;
             }
             for (int sub = 0; sub < nsub; ++sub) {
@@ -497,16 +513,20 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                 for (int h = 0; h < halves; ++h) {
                     const uint32_t na = nacc + h;
                     const uint32_t slot = nslots == 2 ? (na & 1) : 0, slot_phase = nslots == 2 ? ((na >> 1) & 1) : (na & 1);
+                    if (two_groups && (int)slot != grp) continue;        // the other group's accumulator
                     ptx::mbar_wait(&acc_full[slot], slot_phase);
                     ptx::tc_fence_after();
-                    const uint32_t taddr = tmem_base + slot * NS + ((uint32_t)(warp * 32) << 16);
+                    const uint32_t taddr = tmem_base + slot * NS + ((uint32_t)(qd * 32) << 16);
                     const bool tail_half = (h * 128 + 128 > NS);         // only 64 valid rows (N = 64 or 192)
                     for (int c0 = 0; c0 < NS; c0 += 64) {
                         float v[64];
                         ptx::tmem_ld32(taddr + c0, v);
                         ptx::tmem_ld32(taddr + c0 + 32, v + 32);
                         ptx::tmem_ld_wait();
-                        ptx::stage_store_tile(ybuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
+                        if (two_groups)          // one staging tile per group (the two groups' stores interleave)
+                            ptx::stage_store_tile<1>(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3 + grp, issuer, true, y_pol);
+                        else
+                            ptx::stage_store_tile(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
                         ++nstore;
                     }
                     ptx::tc_fence_before();
@@ -516,7 +536,9 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
             }
         }
         if (issuer) ptx::bulk_wait_all();
+        }
     }
+k1_done:
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 9) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -1727,7 +1749,8 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     int grid = cnt < sms * ctas ? cnt : sms * ctas;
     if (half_sm && grid > sms) grid = sms;
     { ProfScope ps(KC_SPLITSUM, st);
-      RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, kK1Threads, smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
+      static const int k1_groups = env_int("RBN_TC_K1_GROUPS", 2);       // 1: single epilogue group (A/B runs)
+      RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, (ctas > 1 || k1_groups < 2) ? k1_threads<2>() : k1_threads<1>(), smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
                                          c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y_of(u), c.e_of(u), nslots,
                                          (uint64_t)((tc_tune().hints & 2) ? ptx::kEvictFirst : ptx::kEvictNormal))); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
