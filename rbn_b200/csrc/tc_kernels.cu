@@ -276,10 +276,10 @@ struct EpiCounts {
 // (64 k-rows x 128 B, 128-byte swizzle).  Four "fix-up" warps fold the per-split scale c_j = 2^(e_ij + e_jk - E)
 // into the left-child slab in shared memory (and zero the rows past the last split); one thread issues the MMAs.
 //   warps 0-3 epilogue (TMEM -> fp16 -> Y)   warps 4-7 fix-up   warp 8 TMA producer   warp 9 MMA issuer / TMEM owner
-//   warps 10-13 (one CTA per SM only): second epilogue group.  Draining a span is 8 tiles of [128 x 64] (TMEM load,
-//   fp16 pack, swizzled st.shared, barrier, TMA store) -- with one group that was the longest stage of the per-span
-//   pipeline and the kernel followed the SM clock (137 ms per C3 step on a 1.75 GHz box, 167 ms on a 1.5 GHz one) instead
-//   of the HBM write rate; with two groups each accumulator (= half of a span) has its own four warps.
+//   warps 10-13 (RBN_TC_K1_GROUPS=2, one CTA per SM only): optional second epilogue group, one accumulator (= half of a
+//   span) per group.  The kernel follows the SM clock (137 ms per C3 step on a 1.75 GHz box, 167 ms on a 1.5 GHz one), so
+//   the epilogue (8 tiles of [128 x 64] per span: TMEM load, fp16 pack, swizzled st.shared, barrier, TMA store) looked like
+//   the longest stage of the per-span pipeline; measured, the second group does not help (see launch_k1) and is off.
 template <int MINB>
 static constexpr int k1_threads() { return MINB == 1 ? 448 : 320; }
 
@@ -1373,6 +1373,8 @@ __global__ void k_tc_emission_bwd(int N, int L, int Lp, int nt, const int* __res
 // gY GEMM) ; G itself in fp32 plus the running max |G| of the launch group (k_gabs_convert makes the count GEMM's operand)
 // One WARP per span (8 spans per CTA), N / 32 values per lane: no block-level synchronisation, an eighth of the CTAs.
 static constexpr int kPrepWarps = 8;
+// Lane `lane` owns the N / 32 CONSECUTIVE nonterminals [lane * per, (lane + 1) * per): its loads and stores are 8- / 16-byte
+// vectors (per is 2, 4, 6, 8 or 16), an eighth of the memory instructions of an interleaved mapping.
 __global__ void __launch_bounds__(kPrepWarps * 32)
 k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, const int* __restrict__ lengths, const int* __restrict__ ce,
          const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
@@ -1380,7 +1382,7 @@ k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, 
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);
     if (t >= rows) return;                          // rows = cnt rounded up to 64: the pad rows are written as zeros
-    // gabs_rows: rows of `gabs` this launch owns (= rows for a slot buffer; = cnt when the rows are packed behind the
+    // gabs_rows: rows of `g32` this launch owns (= rows for a slot buffer; = cnt when the rows are packed behind the
     // previous unit's in the deferred-count array, where the next unit's rows follow immediately)
     const int nI = L - w + 1;
     const int m = m0 + t;
@@ -1390,18 +1392,26 @@ k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, 
     float g[kMaxPerLane], gs[kMaxPerLane];
     float mx = 0.f, mxg = 0.f;
     const int per = N >> 5;
+    const int a0 = lane * per;
     if (valid) {
         const size_t cell = (size_t)b * cells_per_seq(L) + cell_off(w, L) + i;
-        const int e_new = ce[cell] - item_e[t];
-        const float* row = alpha + (((size_t)b * L + i) * Lp + (i + w)) * N;
+        const float2* row = reinterpret_cast<const float2*>(alpha + (((size_t)b * L + i) * Lp + (i + w)) * N + a0);
+        const int2* we = reinterpret_cast<const int2*>(wexp + a0);
+        float2 rv[kMaxPerLane / 2];
 #pragma unroll
-        for (int q = 0; q < kMaxPerLane; ++q) {
-            if (q < per) {
-                const int a = q * 32 + lane;
-                g[q] = ldexpf(row[a], -e_new);
-                gs[q] = ldexpf(g[q], wexp[a]);
-                mx = fmaxf(mx, fabsf(gs[q]));
-                mxg = fmaxf(mxg, fabsf(g[q]));
+        for (int q = 0; q < kMaxPerLane / 2; ++q)
+            if (2 * q < per) rv[q] = row[q];        // issued before the exponents arrive (independent loads)
+        const int e_new = ce[cell] - item_e[t];
+#pragma unroll
+        for (int q = 0; q < kMaxPerLane / 2; ++q) {
+            if (2 * q < per) {
+                const int2 ex = we[q];
+                g[2 * q] = ldexpf(rv[q].x, -e_new);
+                g[2 * q + 1] = ldexpf(rv[q].y, -e_new);
+                gs[2 * q] = ldexpf(g[2 * q], ex.x);
+                gs[2 * q + 1] = ldexpf(g[2 * q + 1], ex.y);
+                mx = fmaxf(mx, fmaxf(fabsf(gs[2 * q]), fabsf(gs[2 * q + 1])));
+                mxg = fmaxf(mxg, fmaxf(fabsf(g[2 * q]), fabsf(g[2 * q + 1])));
             }
         }
     } else {
@@ -1414,16 +1424,17 @@ k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, 
     }
     int eg = 0;
     if (mx > 0.f) frexpf(mx, &eg);
-    if (mxg > 0.f && mxg <= 3.0e38f) {                // non-negative floats order like ints; one atomic per warp, aggregated by
-        const int bits = __float_as_int(mxg);         // the hardware when several warps of an SM hit the address together
+    if (mxg > 0.f && mxg <= 3.0e38f) {                // non-negative floats order like ints
+        const int bits = __float_as_int(mxg);
         if (lane == 0 && bits > *(volatile int*)gmax_bits) atomicMax(gmax_bits, bits);
     }
+    __half2* hrow = reinterpret_cast<__half2*>(ghat + (size_t)t * N + a0);
+    float2* grow = reinterpret_cast<float2*>(g32 + (size_t)t * N + a0);
 #pragma unroll
-    for (int q = 0; q < kMaxPerLane; ++q) {
-        if (q < per) {
-            const int a = q * 32 + lane;
-            ghat[(size_t)t * N + a] = __float2half_rn(ldexpf(gs[q], -eg));
-            if (t < gabs_rows) g32[(size_t)t * N + a] = g[q];     // (cached spans: packed rows, no pad rows)
+    for (int q = 0; q < kMaxPerLane / 2; ++q) {
+        if (2 * q < per) {
+            hrow[q] = __floats2half2_rn(ldexpf(gs[2 * q], -eg), ldexpf(gs[2 * q + 1], -eg));
+            if (t < gabs_rows) grow[q] = make_float2(g[2 * q], g[2 * q + 1]);     // (cached spans: packed rows, no pad rows)
         }
     }
     if (lane == 0) gexp[t] = eg;
@@ -1749,7 +1760,9 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     int grid = cnt < sms * ctas ? cnt : sms * ctas;
     if (half_sm && grid > sms) grid = sms;
     { ProfScope ps(KC_SPLITSUM, st);
-      static const int k1_groups = env_int("RBN_TC_K1_GROUPS", 2);       // 1: single epilogue group (A/B runs)
+      // measured (round 2, same box, alternating runs): two groups 157 ms of split-sum per C3 step, one group 152 -- the
+      // single staging tile per group serialises on the TMA store's smem read; the second group stays selectable
+      static const int k1_groups = env_int("RBN_TC_K1_GROUPS", 1);
       RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, (ctas > 1 || k1_groups < 2) ? k1_threads<2>() : k1_threads<1>(), smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
                                          c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y_of(u), c.e_of(u), nslots,
                                          (uint64_t)((tc_tune().hints & 2) ? ptx::kEvictFirst : ptx::kEvictNormal))); }
