@@ -29,7 +29,7 @@ int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const floa
                 const int*, const float*, float*, float*, float*, const int*, cudaStream_t);
 int debug_gemm(int, int, int, const __half*, const __half*, float*, int, int, int, cudaStream_t);
 size_t gauss_workspace_bytes(int, int, int);
-int gauss_backward(int, int, int, const int*, const double*, const double*, const double*, const double*, const double*,
+int gauss_backward(int, int, int, const int*, const double*, const double*, const double*, const double*, const double*, const double*,
                    double*, const double*, double*, double*, double*, double*, double*, double*, double*, cudaStream_t);
 int gauss_forward(int, int, int, const double*, const int*, const double*, const double*, const double*, const double*,
                   const double*, const double*, double*, double*, cudaStream_t);
@@ -337,9 +337,9 @@ int rbn_gauss_inside_backward(const RbnGaussDesc* desc, const double* y, const i
                               const double* coef, double* g_y, double* g_cov_term, double* g_cov_left,
                               double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
                               void* stream) {
-    (void)y; (void)cov_term; (void)log_struct;
+    (void)y; (void)cov_term;
     if (!gdesc_ok(desc)) return RBN_E_BADARG;
-    if (!lengths || !cov_left || !cov_right || !prior_mean || !prior_cov || !workspace || !coef || !g_y || !g_cov_term ||
+    if (!lengths || !cov_left || !cov_right || !prior_mean || !prior_cov || !log_struct || !workspace || !coef || !g_y || !g_cov_term ||
         !g_cov_left || !g_cov_right || !g_prior_mean || !g_prior_cov || !g_log_struct) {
         set_error("rbn_gauss_inside_backward: NULL pointer argument");
         return RBN_E_BADARG;
@@ -350,7 +350,7 @@ int rbn_gauss_inside_backward(const RbnGaussDesc* desc, const double* y, const i
     }
     double* chart = (double*)workspace;
     double* adj = (double*)((char*)workspace + gauss_workspace_bytes(desc->D, desc->B, desc->L));
-    return gauss_backward(desc->D, desc->B, desc->L, lengths, cov_left, cov_right, prior_mean, prior_cov, chart, adj, coef,
+    return gauss_backward(desc->D, desc->B, desc->L, lengths, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, adj, coef,
                           g_y, g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct,
                           (cudaStream_t)stream);
 }

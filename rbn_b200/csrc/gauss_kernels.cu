@@ -11,6 +11,7 @@
 // then limited by summation order only.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace rbn {
 
@@ -18,6 +19,12 @@ template <int D>
 struct GCell {
     static constexpr int kStride = 1 + D + D * D;
 };
+
+// RBN_GAUSS_ROWS=0 selects the one-thread-per-split kernels for D = 8 too (A/B runs)
+static bool gauss_rows8() {
+    const char* e = getenv("RBN_GAUSS_ROWS");
+    return !(e && e[0] == '0');
+}
 
 // lower Cholesky factor of the symmetric matrix S (full storage), in place in the lower triangle; returns log det S
 template <int D>
@@ -212,6 +219,177 @@ k_gauss_diag(int L, int w, const int* __restrict__ lengths, const double* __rest
     }
 }
 
+
+// =====================================================================================================================
+// D = 8 (BASELINE config 4): eight lanes per split, lane r holds ROW r of every 8 x 8 matrix
+// =====================================================================================================================
+// The one-thread-per-split kernels above keep three to six 8 x 8 fp64 matrices per thread: 400-800 registers, i.e.
+// local-memory traffic for every entry (3.4 % of the HBM roofline in round 1).  Here a split is worked on by a group of 8
+// lanes; a matrix is 8 doubles per lane, rows move between lanes with warp shuffles (width 8), and a warp owns one span
+// (4 splits at a time).  Everything that is symmetric (A, S^-1, the moments) needs no transposes in this layout; the
+// products that involve a non-symmetric factor take the wanted COLUMN element out of a broadcast row (sel8).
+//   S = L L^T row-distributed Cholesky, Y = L^-1 A by forward substitution (no back substitution anywhere):
+//   quad = |L^-1 d|^2,  cov = A - Y^T Y,  mean = mu_l + Y^T (L^-1 d)      (PairwiseProduct, multivariate_normal.py:332-396)
+// The moment matching over the splits of a span (ApproximateMixture, :502-550) is accumulated ONLINE (running maximum of
+// the log weights with rescaling), so every split is visited once.
+namespace g8 {
+
+static constexpr int D8 = 8;
+static constexpr double kLog2Pi = 1.8378770664093454836;
+
+__device__ __forceinline__ double gshfl(unsigned mask, double v, int src) { return __shfl_sync(mask, v, src, 8); }
+__device__ __forceinline__ double gsum(unsigned mask, double v) {
+    v += __shfl_xor_sync(mask, v, 1, 8);
+    v += __shfl_xor_sync(mask, v, 2, 8);
+    v += __shfl_xor_sync(mask, v, 4, 8);
+    return v;
+}
+// element r (lane-dependent) of a register array
+__device__ __forceinline__ double sel8(const double (&v)[8], int r) {
+    double x = v[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) x = (r == k) ? v[k] : x;
+    return x;
+}
+
+// In place: row r of the symmetric S -> row r of its lower Cholesky factor (entries k <= r).  Returns L[r][r].
+__device__ __forceinline__ double chol_rows(unsigned mask, int r, double (&s)[8]) {
+    double mydiag = 1.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double t = s[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) t -= s[k] * s[k];
+        const double ljj = gshfl(mask, sqrt(t), j);            // lane j's value is the meaningful one
+        double acc = s[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) acc -= s[k] * gshfl(mask, s[k], j);
+        if (r > j) s[j] = acc / ljj;
+        else if (r == j) { s[j] = ljj; mydiag = ljj; }
+    }
+    return mydiag;
+}
+
+// Forward substitution L Y = X for 8 right-hand-side columns and one extra vector: lane r holds row r of X in x[] and
+// entry r of the vector in xv; on return row r of L^-1 X and entry r of L^-1 v.
+__device__ __forceinline__ void fwd_subst(unsigned mask, int r, const double (&s)[8], double mydiag, double (&x)[8], double& xv) {
+    const double inv = 1.0 / mydiag;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (r == k) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[c] *= inv;
+            xv *= inv;
+        }
+        const double lrk = s[k];                                // L[r][k] (meaningful for r > k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double yk = gshfl(mask, x[c], k);
+            if (r > k) x[c] -= lrk * yk;
+        }
+        const double yv = gshfl(mask, xv, k);
+        if (r > k) xv -= lrk * yv;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_gauss_diag8(int L, int w, int B, const int* __restrict__ lengths, const double* __restrict__ cov_left,
+              const double* __restrict__ cov_right, const double* __restrict__ log_struct, double* __restrict__ chart) {
+    constexpr int G = 1 + D8 + D8 * D8;
+    const int nI = L - w + 1;
+    const int span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= B * nI) return;
+    const int b = span / nI, i = span - b * nI;
+    if (i + w > lengths[b]) return;
+    const int lane = threadIdx.x & 31, g = lane >> 3, r = lane & 7;
+    const unsigned mask = 0xFFu << (lane & 24);
+    const double* seq = chart + (size_t)b * cells_per_seq(L) * G;
+    double cl[8], cr[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { cl[c] = cov_left[r * 8 + c]; cr[c] = cov_right[r * 8 + c]; }
+    // running moment-matching state of this group: max log weight, sum of weights, first moment (entry r), second moment (row r)
+    double mx = -INFINITY, se = 0.0, a1 = 0.0, a2[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a2[c] = 0.0;
+    for (int u = 1 + g; u < w; u += 4) {
+        const double* lc = seq + (size_t)(cell_off(u, L) + i) * G;
+        const double* rc = seq + (size_t)(cell_off(w - u, L) + i + u) * G;
+        double A[8], s[8], x[8];
+        const double mul = lc[1 + r];
+        double dv = rc[1 + r] - mul;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            A[c] = lc[1 + D8 + r * 8 + c] + cl[c];
+            s[c] = A[c] + rc[1 + D8 + r * 8 + c] + cr[c];
+            x[c] = A[c];
+        }
+        const double diag = chol_rows(mask, r, s);
+        fwd_subst(mask, r, s, diag, x, dv);                     // x = row r of Y = L^-1 A, dv = (L^-1 d)[r]
+        const double quad = gsum(mask, dv * dv);
+        const double logdet = 2.0 * gsum(mask, log(diag));
+        const double lw = lc[0] + rc[0] - 0.5 * (quad + logdet + D8 * kLog2Pi);
+        // cov = A - Y^T Y (row r), mean = mu_l + Y^T (L^-1 d) (entry r)
+        double C[8], m = mul;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) C[c] = A[c];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double yk[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) yk[c] = gshfl(mask, x[c], k);
+            const double ya = sel8(yk, r);                       // Y[k][r]
+            const double dk = gshfl(mask, dv, k);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) C[c] -= ya * yk[c];
+            m += ya * dk;
+        }
+        // online moment matching
+        const double nmx = fmax(mx, lw);
+        const double sc = (mx == -INFINITY) ? 0.0 : exp(mx - nmx);
+        const double wt = exp(lw - nmx);
+        se = se * sc + wt;
+        a1 = a1 * sc + wt * m;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double mc = gshfl(mask, m, c);
+            a2[c] = a2[c] * sc + wt * (C[c] + m * mc);
+        }
+        mx = nmx;
+    }
+    // combine the four groups of the warp (same rescaling), every lane ends with the span's totals
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const double ose = __shfl_xor_sync(0xffffffffu, se, o);
+        const double oa1 = __shfl_xor_sync(0xffffffffu, a1, o);
+        const double nmx = fmax(mx, omx);
+        const double s0 = (mx == -INFINITY) ? 0.0 : exp(mx - nmx), s1 = (omx == -INFINITY) ? 0.0 : exp(omx - nmx);
+        se = se * s0 + ose * s1;
+        a1 = a1 * s0 + oa1 * s1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double oa = __shfl_xor_sync(0xffffffffu, a2[c], o);
+            a2[c] = a2[c] * s0 + oa * s1;
+        }
+        mx = nmx;
+    }
+    const double log_norm = mx + log(se);
+    const double inv = 1.0 / se;
+    const double mean = a1 * inv;
+    double* out = chart + ((size_t)b * cells_per_seq(L) + cell_off(w, L) + i) * G;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double mc = __shfl_sync(0xffffffffu, mean, c, 8);
+        if (g == 0) out[1 + D8 + r * 8 + c] = a2[c] * inv - mean * mc;
+    }
+    if (g == 0) {
+        out[1 + r] = mean;
+        if (r == 0) out[0] = log_norm + log_struct[1];
+    }
+}
+
+}  // namespace g8
+
 template <int D>
 __global__ void k_gauss_root(int L, int B, const int* __restrict__ lengths, const double* __restrict__ prior_mean,
                              const double* __restrict__ prior_cov, const double* __restrict__ chart,
@@ -247,9 +425,13 @@ static int gauss_forward_t(int B, int L, const double* y, const int* lengths, co
     { ProfScope ps(KC_EMISSION, st); k_gauss_width1<D><<<B * L, 96, 0, st>>>(L, y, lengths, cov_term, log_struct, chart); }
     RBN_LAUNCH_CHECK("k_gauss_width1");
     size_t smem = ((size_t)L + D + 3 * D * D) * sizeof(double);
+    static const bool rows8 = gauss_rows8();
     for (int w = 2; w <= L; ++w) {
         { ProfScope ps(KC_SIMT_INSIDE, st);
-          k_gauss_diag<D><<<B * (L - w + 1), 64, smem, st>>>(L, w, lengths, cov_left, cov_right, log_struct, chart); }
+          if (D == 8 && rows8)
+              g8::k_gauss_diag8<<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
+          else
+              k_gauss_diag<D><<<B * (L - w + 1), 64, smem, st>>>(L, w, lengths, cov_left, cov_right, log_struct, chart); }
         RBN_LAUNCH_CHECK("k_gauss_diag");
     }
     { ProfScope ps(KC_OTHER, st); k_gauss_root<D><<<(B + 63) / 64, 64, 0, st>>>(L, B, lengths, prior_mean, prior_cov, chart, logZ); }
@@ -546,6 +728,184 @@ k_gauss_bwd_diag(int L, int w, const int* __restrict__ lengths, const double* __
     }
 }
 
+
+// Outside pass for D = 8 in the same layout (8 lanes per split, rows in registers).  The adjoint of a split needs the
+// softmax normaliser of its span and sum_u omega_u ob_u; both are known from the PARENT cell the inside pass wrote
+// (log c, and <g1, mu_p> + <M2_bar, Sigma_p + mu_p mu_p^T>), so every split is visited once.  With W = L^-1 (forward
+// substitution of the identity):  P = S^-1 = W^T W,  z = W^T (L^-1 d),  K = A P,  Q = M2_bar K,  <M2_bar, C> = <M2_bar - Q, A>.
+// Child adjoints and covariance gradients are accumulated UNsymmetrised (every reader of the adjoint chart symmetrises on
+// load; gauss_backward_t symmetrises the parameter gradients once at the end).
+namespace g8 {
+
+__global__ void __launch_bounds__(128)
+k_gauss_bwd_diag8(int L, int w, int B, const int* __restrict__ lengths, const double* __restrict__ cov_left,
+                  const double* __restrict__ cov_right, const double* __restrict__ log_struct,
+                  const double* __restrict__ chart, double* __restrict__ adj, double* __restrict__ g_cov_left,
+                  double* __restrict__ g_cov_right, double* __restrict__ g_log_struct) {
+    constexpr int G = 1 + D8 + D8 * D8;
+    const int nI = L - w + 1;
+    const int span = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (span >= B * nI) return;
+    const int b = span / nI, i = span - b * nI;
+    if (i + w > lengths[b]) return;
+    const int lane = threadIdx.x & 31, g = lane >> 3, r = lane & 7;
+    const unsigned mask = 0xFFu << (lane & 24);
+    const size_t seq_off = (size_t)b * cells_per_seq(L);
+    const double* seq = chart + seq_off * G;
+    double* aseq = adj + seq_off * G;
+    const size_t pcell = cell_off(w, L) + i;
+    const double* pa = aseq + pcell * G;
+    {   // skip spans that no gradient reaches
+        double any = 0.0;
+        for (int t = lane; t < G; t += 32) any += fabs(pa[t]);
+        for (int o = 16; o > 0; o >>= 1) any += __shfl_xor_sync(0xffffffffu, any, o);
+        if (any == 0.0) return;
+    }
+    const double abar = pa[0];
+    double M2b[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) M2b[c] = 0.5 * (pa[1 + D8 + r * 8 + c] + pa[1 + D8 + c * 8 + r]);
+    const double pm = seq[pcell * G + 1 + r];
+    double g1 = pa[1 + r], swo;
+    {
+        double t = 0.0, q = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double pmc = gshfl(mask, pm, c);
+            t += M2b[c] * pmc;                                                   // (M2_bar mu_p)[r]
+            q += M2b[c] * seq[pcell * G + 1 + D8 + r * 8 + c];                  // <M2_bar, Sigma_p>, row r
+        }
+        g1 -= 2.0 * t;                                                           // mu_bar_tot = mu_bar - 2 Sigma_bar mu_p
+        swo = gsum(mask, g1 * pm + q + pm * t);
+    }
+    const double log_norm = seq[pcell * G] - log_struct[1];
+    if (lane == 0) atomicAdd(&g_log_struct[1], abar);
+    double tL[8], tR[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) tL[c] = tR[c] = 0.0;
+
+    for (int u = 1 + g; u < w; u += 4) {
+        const size_t lcell = cell_off(u, L) + i, rcell = cell_off(w - u, L) + i + u;
+        const double* lc = seq + lcell * G;
+        const double* rc = seq + rcell * G;
+        double A[8], s[8], x[8];
+        const double mul = lc[1 + r];
+        double yd = rc[1 + r] - mul;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            A[c] = lc[1 + D8 + r * 8 + c] + cov_left[r * 8 + c];
+            s[c] = A[c] + rc[1 + D8 + r * 8 + c] + cov_right[r * 8 + c];
+            x[c] = (c == r) ? 1.0 : 0.0;
+        }
+        const double diag = chol_rows(mask, r, s);
+        fwd_subst(mask, r, s, diag, x, yd);                      // x = row r of W = L^-1, yd = (L^-1 d)[r]
+        const double quad = gsum(mask, yd * yd);
+        const double logdet = 2.0 * gsum(mask, log(diag));
+        const double lw = lc[0] + rc[0] - 0.5 * (quad + logdet + D8 * kLog2Pi);
+        const double om = exp(lw - log_norm);
+        // P = W^T W (row r), z = W^T (L^-1 d) (entry r)
+        double P[8], z = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) P[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double wk[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) wk[c] = gshfl(mask, x[c], k);
+            const double wa = sel8(wk, r);
+            const double ydk = gshfl(mask, yd, k);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) P[c] += wa * wk[c];
+            z += wa * ydk;
+        }
+        // K = A P (row r)
+        double K[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) K[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) K[c] += A[k] * gshfl(mask, P[c], k);
+        }
+        double zc[8], m = mul;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { zc[c] = gshfl(mask, z, c); m += A[c] * zc[c]; }    // m = mu_l + A z
+        // Q = M2_bar K (row r)
+        double Q[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Q[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) Q[c] += M2b[k] * gshfl(mask, K[c], k);
+        }
+        double t = 0.0, part = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            t += M2b[c] * gshfl(mask, m, c);                                     // (M2_bar m)[r]
+            part += (M2b[c] - Q[c]) * A[c];                                      // <M2_bar, C> = <M2_bar - Q, A>
+        }
+        const double ob = gsum(mask, g1 * m + part + m * t);
+        const double lwb = om * (ob - swo + abar);
+        const double mb = om * (g1 + 2.0 * t);
+        // K^T Q (row r) and row r of Q^T
+        double KtQ[8], QT[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) KtQ[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double kk[8], qk[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { kk[c] = gshfl(mask, K[c], k); qk[c] = gshfl(mask, Q[c], k); }
+            const double ka = sel8(kk, r);
+            QT[k] = sel8(qk, r);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) KtQ[c] += ka * qk[c];
+        }
+        double zb = 0.0, pz = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) zb += A[c] * gshfl(mask, mb, c);              // z_bar = A m_bar
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pz += P[c] * gshfl(mask, zb, c);              // P z_bar
+        const double db = -lwb * z + pz;
+        double* la = aseq + lcell * G;
+        double* ra = aseq + rcell * G;
+        if (r == 0) { atomicAdd(&la[0], lwb); atomicAdd(&ra[0], lwb); }
+        atomicAdd(&la[1 + r], mb - db);
+        atomicAdd(&ra[1 + r], db);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double sb = 0.5 * lwb * (z * zc[c] - P[c]) - pz * zc[c] + om * KtQ[c];
+            const double ab = mb * zc[c] + om * (M2b[c] - Q[c] - QT[c]) + sb;
+            atomicAdd(&la[1 + D8 + r * 8 + c], ab);
+            atomicAdd(&ra[1 + D8 + r * 8 + c], sb);
+            tL[c] += ab;
+            tR[c] += sb;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double vl = tL[c], vr = tR[c];
+        vl += __shfl_xor_sync(0xffffffffu, vl, 8);  vr += __shfl_xor_sync(0xffffffffu, vr, 8);
+        vl += __shfl_xor_sync(0xffffffffu, vl, 16); vr += __shfl_xor_sync(0xffffffffu, vr, 16);
+        if (g == 0) {
+            if (vl != 0.0) atomicAdd(&g_cov_left[r * 8 + c], vl);
+            if (vr != 0.0) atomicAdd(&g_cov_right[r * 8 + c], vr);
+        }
+    }
+}
+
+// g <- (g + g^T) / 2 for the two 8 x 8 covariance gradients
+__global__ void k_sym8(double* __restrict__ a, double* __restrict__ b) {
+    const int t = threadIdx.x, r = t >> 3, c = t & 7;
+    double* m = blockIdx.x ? b : a;
+    const double v = 0.5 * (m[r * 8 + c] + m[c * 8 + r]);
+    __syncthreads();
+    m[r * 8 + c] = v;
+}
+
+}  // namespace g8
+
 template <int D>
 __global__ void k_gauss_bwd_width1(int L, const int* __restrict__ lengths, const double* __restrict__ adj,
                                    double* __restrict__ g_y, double* __restrict__ g_cov_term,
@@ -568,7 +928,7 @@ __global__ void k_gauss_bwd_width1(int L, const int* __restrict__ lengths, const
 
 template <int D>
 static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_left, const double* cov_right,
-                            const double* prior_mean, const double* prior_cov, const double* chart, double* adj,
+                            const double* prior_mean, const double* prior_cov, const double* log_struct, const double* chart, double* adj,
                             const double* coef, double* g_y, double* g_cov_term, double* g_cov_left,
                             double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
                             cudaStream_t st) {
@@ -587,10 +947,19 @@ static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_
     RBN_LAUNCH_CHECK("k_gauss_bwd_root");
     size_t smem = ((size_t)2 * L + G + D + 4 * DD) * sizeof(double);
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_gauss_bwd_diag<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const bool rows8 = gauss_rows8();
     for (int w = L; w >= 2; --w) {
         { ProfScope ps(KC_SIMT_OUTSIDE, st);
-          k_gauss_bwd_diag<D><<<B * (L - w + 1), 32, smem, st>>>(L, w, lengths, cov_left, cov_right, chart, adj, g_cov_left, g_cov_right, g_log_struct); }
+          if (D == 8 && rows8)
+              g8::k_gauss_bwd_diag8<<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
+                                                                               g_cov_left, g_cov_right, g_log_struct);
+          else
+              k_gauss_bwd_diag<D><<<B * (L - w + 1), 32, smem, st>>>(L, w, lengths, cov_left, cov_right, chart, adj, g_cov_left, g_cov_right, g_log_struct); }
         RBN_LAUNCH_CHECK("k_gauss_bwd_diag");
+    }
+    if (D == 8 && rows8) {
+        { ProfScope ps(KC_OTHER, st); g8::k_sym8<<<2, 64, 0, st>>>(g_cov_left, g_cov_right); }
+        RBN_LAUNCH_CHECK("k_sym8");
     }
     { ProfScope ps(KC_EMISSION, st); k_gauss_bwd_width1<D><<<B * L, 96, 0, st>>>(L, lengths, adj, g_y, g_cov_term, g_log_struct); }
     RBN_LAUNCH_CHECK("k_gauss_bwd_width1");
@@ -598,10 +967,10 @@ static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_
 }
 
 int gauss_backward(int D, int B, int L, const int* lengths, const double* cov_left, const double* cov_right,
-                   const double* prior_mean, const double* prior_cov, const double* chart, double* adj,
+                   const double* prior_mean, const double* prior_cov, const double* log_struct, const double* chart, double* adj,
                    const double* coef, double* g_y, double* g_cov_term, double* g_cov_left, double* g_cov_right,
                    double* g_prior_mean, double* g_prior_cov, double* g_log_struct, cudaStream_t st) {
-#define RBN_G(DD_) case DD_: return gauss_backward_t<DD_>(B, L, lengths, cov_left, cov_right, prior_mean, prior_cov, chart, adj, coef, g_y, g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct, st)
+#define RBN_G(DD_) case DD_: return gauss_backward_t<DD_>(B, L, lengths, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, adj, coef, g_y, g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct, st)
     switch (D) {
         RBN_G(1); RBN_G(2); RBN_G(3); RBN_G(4); RBN_G(8);
         default:
