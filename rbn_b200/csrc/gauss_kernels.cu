@@ -20,6 +20,11 @@ struct GCell {
     static constexpr int kStride = 1 + D + D * D;
 };
 
+// RBN_GAUSS_OCC=1: the D = 8 row kernels compiled for 4 (inside) / 3 (outside) CTAs per SM (fewer registers, more warps)
+static int gauss_occ() {
+    const char* e = getenv("RBN_GAUSS_OCC");
+    return (e && e[0] == '1') ? 1 : 0;
+}
 // RBN_GAUSS_ROWS=0 selects the one-thread-per-split kernels for D = 8 too (A/B runs)
 static bool gauss_rows8() {
     const char* e = getenv("RBN_GAUSS_ROWS");
@@ -292,7 +297,8 @@ __device__ __forceinline__ void fwd_subst(unsigned mask, int r, const double (&s
     }
 }
 
-__global__ void __launch_bounds__(128)
+template <int MINB>      // CTAs per SM the register budget is cut for
+__global__ void __launch_bounds__(128, MINB)
 k_gauss_diag8(int L, int w, int B, const int* __restrict__ lengths, const double* __restrict__ cov_left,
               const double* __restrict__ cov_right, const double* __restrict__ log_struct, double* __restrict__ chart) {
     constexpr int G = 1 + D8 + D8 * D8;
@@ -428,8 +434,11 @@ static int gauss_forward_t(int B, int L, const double* y, const int* lengths, co
     static const bool rows8 = gauss_rows8();
     for (int w = 2; w <= L; ++w) {
         { ProfScope ps(KC_SIMT_INSIDE, st);
-          if (D == 8 && rows8)
-              g8::k_gauss_diag8<<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
+          if (D == 8 && rows8) {
+              static const int occ = gauss_occ();
+              if (occ) g8::k_gauss_diag8<4><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
+              else g8::k_gauss_diag8<1><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
+          }
           else
               k_gauss_diag<D><<<B * (L - w + 1), 64, smem, st>>>(L, w, lengths, cov_left, cov_right, log_struct, chart); }
         RBN_LAUNCH_CHECK("k_gauss_diag");
@@ -737,7 +746,8 @@ k_gauss_bwd_diag(int L, int w, const int* __restrict__ lengths, const double* __
 // load; gauss_backward_t symmetrises the parameter gradients once at the end).
 namespace g8 {
 
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_gauss_bwd_diag8(int L, int w, int B, const int* __restrict__ lengths, const double* __restrict__ cov_left,
                   const double* __restrict__ cov_right, const double* __restrict__ log_struct,
                   const double* __restrict__ chart, double* __restrict__ adj, double* __restrict__ g_cov_left,
@@ -950,9 +960,13 @@ static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_
     static const bool rows8 = gauss_rows8();
     for (int w = L; w >= 2; --w) {
         { ProfScope ps(KC_SIMT_OUTSIDE, st);
-          if (D == 8 && rows8)
-              g8::k_gauss_bwd_diag8<<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
-                                                                               g_cov_left, g_cov_right, g_log_struct);
+          if (D == 8 && rows8) {
+              static const int occ = gauss_occ();
+              if (occ) g8::k_gauss_bwd_diag8<3><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
+                                                                                      g_cov_left, g_cov_right, g_log_struct);
+              else g8::k_gauss_bwd_diag8<1><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
+                                                                                  g_cov_left, g_cov_right, g_log_struct);
+          }
           else
               k_gauss_bwd_diag<D><<<B * (L - w + 1), 32, smem, st>>>(L, w, lengths, cov_left, cov_right, chart, adj, g_cov_left, g_cov_right, g_log_struct); }
         RBN_LAUNCH_CHECK("k_gauss_bwd_diag");
