@@ -20,10 +20,12 @@ struct GCell {
     static constexpr int kStride = 1 + D + D * D;
 };
 
-// RBN_GAUSS_OCC=1: the D = 8 row kernels compiled for 4 (inside) / 3 (outside) CTAs per SM (fewer registers, more warps)
+// Register budget of the D = 8 row kernels.  Measured (C4, round 2): inside pass 21.3 ms at 252 registers (1-2 CTAs per
+// SM), 15.6 ms at 128 (4 CTAs per SM: the kernel is latency-bound, more warps help); outside pass 38.6 ms at 255 registers,
+// 39.1 ms at 168 (spills eat the gain).  Default: inside 128, outside 255.  RBN_GAUSS_OCC=0 / 2 select all-wide / all-narrow.
 static int gauss_occ() {
     const char* e = getenv("RBN_GAUSS_OCC");
-    return (e && e[0] == '1') ? 1 : 0;
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
 }
 // RBN_GAUSS_ROWS=0 selects the one-thread-per-split kernels for D = 8 too (A/B runs)
 static bool gauss_rows8() {
@@ -436,7 +438,7 @@ static int gauss_forward_t(int B, int L, const double* y, const int* lengths, co
         { ProfScope ps(KC_SIMT_INSIDE, st);
           if (D == 8 && rows8) {
               static const int occ = gauss_occ();
-              if (occ) g8::k_gauss_diag8<4><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
+              if (occ >= 1) g8::k_gauss_diag8<4><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
               else g8::k_gauss_diag8<1><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
           }
           else
@@ -962,7 +964,7 @@ static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_
         { ProfScope ps(KC_SIMT_OUTSIDE, st);
           if (D == 8 && rows8) {
               static const int occ = gauss_occ();
-              if (occ) g8::k_gauss_bwd_diag8<3><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
+              if (occ >= 2) g8::k_gauss_bwd_diag8<3><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
                                                                                       g_cov_left, g_cov_right, g_log_struct);
               else g8::k_gauss_bwd_diag8<1><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
                                                                                   g_cov_left, g_cov_right, g_log_struct);
