@@ -289,7 +289,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
               const __grid_constant__ CUtensorMap tmLC1, const __grid_constant__ CUtensorMap tmRC1,   // second K-slab (rows = Kpad - 64)
               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYtail,
               int N, int L, int Lp, int w, int m0, int cnt, int stages, const int* __restrict__ lengths,
-              const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e, int nslots, uint64_t y_pol) {
+              const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e, int nslots, uint64_t y_pol, int nbuf) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int Kpad = ((w - 1) + 15) & ~15;
@@ -308,8 +308,8 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     const int l_atoms = RB / 64;               // left-child atoms actually loaded
     const int b_atoms = NS / 64;
     const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * 8192;
-    uint8_t* ybuf = smem + (size_t)stages * stage_bytes;       // 2 x 16 KB staging tiles for the Y stores
-    uint8_t* tail = ybuf + 32768;
+    uint8_t* ybuf = smem + (size_t)stages * stage_bytes;       // nbuf x 16 KB staging tiles for the Y stores
+    uint8_t* tail = ybuf + (size_t)nbuf * 16384;
     uint64_t* tma_full = (uint64_t*)tail;         // [stages]
     uint64_t* fix_full = tma_full + stages;       // [stages]
     uint64_t* empty = fix_full + stages;          // [stages]
@@ -525,6 +525,10 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                         ptx::tmem_ld_wait();
                         if (two_groups)          // one staging tile per group (the two groups' stores interleave)
                             ptx::stage_store_tile<1>(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3 + grp, issuer, true, y_pol);
+                        else if (nbuf == 4)
+                            ptx::stage_store_tile<4>(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
+                        else if (nbuf == 3)
+                            ptx::stage_store_tile<3>(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
                         else
                             ptx::stage_store_tile(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
                         ++nstore;
@@ -1742,7 +1746,11 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     static const int k1_ctas_env = env_int("RBN_TC_K1_CTAS", 0);
     int ctas = k1_ctas_env > 0 ? (k1_ctas_env > 2 ? 2 : k1_ctas_env) : (N <= 128 ? 2 : 1);
     if (paired) ctas = 1;
-    int stages = (int)((232448 / ctas - 1024 * ctas - 2048 - 32768) / stage_bytes);
+    // staging tiles of the Y stores: 4 (three stores in flight) when the CTA has the SM to itself, else 2
+    static const int nbuf_env = env_int("RBN_TC_K1_NBUF", 0);
+    int nbuf = (nbuf_env >= 2 && nbuf_env <= 4) ? nbuf_env : (ctas == 1 && !half_sm ? 4 : 2);
+    if (ctas > 1 || half_sm) nbuf = 2;
+    int stages = (int)((232448 / ctas - 1024 * ctas - 2048 - nbuf * 16384) / stage_bytes);
     if (stages > 6) stages = 6;
     if (stages < 1) { stages = 1; ctas = 1; }
     int nslots = 2;
@@ -1754,7 +1762,7 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
         nslots = 1;
         ctas = 2;               // selects the register-capped instantiation; the grid stays one CTA per SM
     }
-    size_t smem = stages * stage_bytes + 32768 /*Y staging*/ + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
+    size_t smem = stages * stage_bytes + (size_t)nbuf * 16384 /*Y staging*/ + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
     auto kern = ctas > 1 ? k_tc_splitsum<2> : k_tc_splitsum<1>;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cnt < sms * ctas ? cnt : sms * ctas;
@@ -1765,7 +1773,7 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
       static const int k1_groups = env_int("RBN_TC_K1_GROUPS", 1);
       RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, (ctas > 1 || k1_groups < 2) ? k1_threads<2>() : k1_threads<1>(), smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
                                          c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y_of(u), c.e_of(u), nslots,
-                                         (uint64_t)((tc_tune().hints & 2) ? ptx::kEvictFirst : ptx::kEvictNormal))); }
+                                         (uint64_t)((tc_tune().hints & 2) ? ptx::kEvictFirst : ptx::kEvictNormal), nbuf)); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
 }
@@ -1945,10 +1953,12 @@ static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
         }
         static const int deep = env_int("RBN_TC_GY_STAGES", 6);       // N <= 256: 6 ring stages (4: the former setting)
         const bool big = c.N > 256;
-        const int nbuf = big ? 1 : 2;
-        const int stg = big ? 4 : (deep >= 6 ? 6 : 4);
+        static const int gy_nbuf = env_int("RBN_TC_GY_NBUF", 2);      // 3: two stores in flight per epilogue group, 4-stage Wk ring
+        const bool three = !big && gy_nbuf == 3;
+        const int nbuf = big ? 1 : (three ? 3 : 2);
+        const int stg = big ? 4 : (three ? 4 : (deep >= 6 ? 6 : 4));
         size_t smem2 = (size_t)(c.N / 64) * 16384 + (size_t)stg * 16384 + (size_t)2 * nbuf * 16384 + 256 + 1024;
-        auto kern = big ? k_tc_gy2<1, 4> : (stg == 6 ? k_tc_gy2<2, 6> : k_tc_gy2<2, 4>);
+        auto kern = big ? k_tc_gy2<1, 4> : (three ? k_tc_gy2<3, 4> : (stg == 6 ? k_tc_gy2<2, 6> : k_tc_gy2<2, 4>));
         RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         int units2 = supertiles * ranges2;
         int np = units2 < pairs ? units2 : pairs;

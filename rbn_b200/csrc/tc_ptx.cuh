@@ -93,9 +93,11 @@ template <int NBUF = 2>
 __device__ __forceinline__ void stage_store_tile(uint8_t* bufs, const CUtensorMap* tm, int x, int y, int row,
                                                  const float* v, uint32_t nstore, uint32_t bar_id, bool issuer, bool active,
                                                  uint64_t pol = kEvictNormal) {
-    // One barrier per tile: buffer (nstore & 1) was declared free by the barrier of the previous call (before which
-    // the issuer had waited for the store that last read it), so it can be written straight away.
-    uint8_t* buf = bufs + (NBUF == 2 ? (nstore & 1) * 16384 : 0);
+    // One barrier per tile: buffer (nstore % NBUF) was declared free by the barrier of the previous call (before which
+    // the issuer had waited for the store that last read it), so it can be written straight away.  With NBUF buffers up
+    // to NBUF - 1 stores are in flight: a 16 KB store takes ~0.4 us from issue to "source read", and with ONE in flight
+    // (NBUF = 2) that latency, not bandwidth, paced the split-sum kernel (8 tiles per span -> 3.5 us per span).
+    uint8_t* buf = bufs + (NBUF >= 2 ? (nstore % NBUF) * 16384 : 0);
     if (NBUF == 1) {
         if (issuer) bulk_wait_read<0>();
         named_bar_sync(bar_id, 128);
@@ -108,7 +110,7 @@ __device__ __forceinline__ void stage_store_tile(uint8_t* bufs, const CUtensorMa
     for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(buf + row * 128 + ((c ^ (row & 7)) << 4)) = pk[c];
     fence_proxy_async_smem();
-    if (NBUF == 2 && issuer) bulk_wait_read<0>();    // the previous store (other buffer) has been read: free after the barrier
+    if (NBUF >= 2 && issuer) bulk_wait_read<(NBUF >= 2 ? NBUF - 2 : 0)>();    // the store that read the NEXT buffer is done: free after the barrier
     named_bar_sync(bar_id, 128);
     if (issuer && active) {
         tma_store_2d_hint(tm, buf, x, y, pol);
