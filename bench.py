@@ -327,8 +327,9 @@ def run_reference(args, wl):
                 impl="reference", config=workload_config(wl, args.batch or wl["B"], int(os.environ.get("WORLD_SIZE", "1"))),
                 cpu_baseline=dict(value=v, unit="seq/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit="seq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
-                note="the reference (pure Python rbnet) cannot travel to the GPU box; this arm times oracle/ (its "
-                     "vectorised fp64 restatement) on the host cores, one sequence per step")
+                note="the literal reference (pure Python loop nest) needs hours per sequence at this size (BASELINE.md section 2; it "
+                     "IS the timed arm for --workload c1); this arm times oracle/, its vectorised fp64 restatement, on all host "
+                     "cores, one sequence per step")
     print(json.dumps(line), flush=True)
 
 

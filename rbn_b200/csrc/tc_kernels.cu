@@ -1844,7 +1844,8 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         rc = make_tmap_2d(&tmB2, c.wt, NN, (uint64_t)c.N, NN * 2, BN / 2);
         if (rc) return rc;
         GemmShape shape2{(cnt + 255) / 256, n_tiles, (int)(NN / 64), 0, 1, 0};
-        if (tc_tune().hints & 4) { shape2.hint_a = ptx::kEvictFirst; shape2.hint_b = ptx::kEvictLast; }   // Y streams, W is reused
+        // Y streams, W is reused.  (N = 512: a Y tile is read by the two parent-half tiles, the second time from L2 -- no hint)
+        if ((tc_tune().hints & 4) && n_tiles == 1) { shape2.hint_a = ptx::kEvictFirst; shape2.hint_b = ptx::kEvictLast; }
         // wave quantisation: the last, partial wave of tiles is split along K so that all CTA pairs stay busy
         const int pairs = sms / 2, T = shape2.m_tiles * n_tiles;
         const int full = (T / pairs) * pairs, r = T - full;
@@ -2006,7 +2007,7 @@ static int launch_k4_bn(TcCtx& c, const Unit& u, float* gW, cudaStream_t st, int
     }
     if (use_pairs() && BN % 128 == 0) {
         GemmShape shape2{(int)(NN / 256), n_tiles, (cnt + 63) / 64, 0, 1, 0};
-        if (tc_tune().hints & 4) shape2.hint_a = ptx::kEvictFirst;                                       // last read of Y
+        if ((tc_tune().hints & 4) && n_tiles == 1) shape2.hint_a = ptx::kEvictFirst;                     // last read of Y
         {   // K-split so that the work units fill whole waves of CTA pairs (256 tiles on 74 pairs = 3.46 waves otherwise)
             const int pairs = sms / 2, tiles = (int)(NN / 256) * n_tiles;
             int best = 1;
