@@ -41,7 +41,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ---- workspace layout -------------------------------------------------------------------------------------------
 struct WsLayout {
     // common (both paths)
-    size_t chart_val;   // float  [B][C][N]   mantissas, max 1 per cell (power-of-two scaled => exact)
+    size_t chart_val;   // float  [B][C][N]   mantissas, largest entry of a cell in [0.5, 1) (power-of-two scaled => exact)
     size_t chart_exp;   // int32  [B][C]      beta = mantissa * 2^exp
     size_t alpha;       // float  scaled outside values (backward only): CUDA-core path [B][C][N]; tensor-core path
                         //        start-major [B][L][Lp][N] (root seed + left- and right-child sums), cell (i,j) at row (b*L+i)*Lp + j

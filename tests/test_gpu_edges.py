@@ -156,3 +156,46 @@ def test_ragged_batch_is_sorted_internally_and_results_come_back_in_caller_order
     alone = []
     inside_logZ(Wt.detach(), Tt.detach(), pt.detach(), torch.tensor(tok[5:6, :lengths[5]]), torch.tensor(lengths[5:6]), path=p, holder=alone)
     np.testing.assert_allclose(holder[0].export_chart(5).cpu().numpy(), alone[0].export_chart(0).cpu().numpy(), rtol=1e-5, atol=1e-300)
+
+
+def test_batched_tokens_with_two_terminal_variables():
+    """`log_inside_batch(tokens=...)` takes per-variable terminal values (they used to be read as flat-alphabet
+    offsets, so variable 1 silently indexed variable 0's rows of T).  Same log Z and gradients as the `sequences=` path,
+    which packs through pack_sequences; an out-of-range value raises IndexError before anything is launched."""
+    from rbn_b200 import pcfg, sequential
+    rng = np.random.default_rng(60)
+    K, V0, V1 = 5, 3, 4
+
+    def model():
+        r = np.random.default_rng(61)
+        cell = pcfg.DiscreteCell(variable=pcfg.DiscreteNonTermVar(K), weights=r.random((3, K)),
+                                 transitions=[pcfg.DiscreteTerminalTransition(weights=r.random((V0, K)), term_idx=0),
+                                              pcfg.DiscreteTerminalTransition(weights=r.random((V1, K)), term_idx=1),
+                                              pcfg.DiscreteBinaryNonTerminalTransition(weights=r.random((K, K, K)))])
+        prior = pcfg.DiscretePrior(struc_weights=np.ones(1), prior_weights=[r.random(K)])
+        return sequential.SequentialRBN(cells=[cell], prior=prior).to("cuda")
+
+    B, L = 4, 7
+    lengths = np.array([7, 5, 7, 2])
+    raw = -np.ones((B, L, 2), dtype=np.int64)
+    seqs = []
+    for b in range(B):
+        seq = []
+        for i in range(lengths[b]):
+            y0, y1 = int(rng.integers(0, V0)), (int(rng.integers(0, V1)) if rng.random() > 0.3 else None)
+            raw[b, i] = [y0, -1 if y1 is None else y1]
+            seq.append([y0, y1])
+        seqs.append(seq)
+    m1, m2 = model(), model()
+    lz1 = m1.log_inside_batch(sequences=seqs)
+    lz2 = m2.log_inside_batch(tokens=torch.tensor(raw), lengths=torch.tensor(lengths))
+    np.testing.assert_allclose(lz2.detach().cpu().numpy(), lz1.detach().cpu().numpy(), rtol=1e-6)
+    lz1.sum().backward()
+    lz2.sum().backward()
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert n1 == n2
+        np.testing.assert_allclose(p2.grad.cpu().numpy(), p1.grad.cpu().numpy(), rtol=1e-5, atol=1e-8)
+    bad = raw.copy()
+    bad[0, 0, 0] = V0                              # valid for variable 1's alphabet, not for variable 0's
+    with pytest.raises(IndexError):
+        m2.log_inside_batch(tokens=torch.tensor(bad), lengths=torch.tensor(lengths))
