@@ -155,6 +155,8 @@ int rbn_export_chart(const RbnDesc* desc, const int32_t* lengths,
  * normalises over the LEADING dims, parent last).  Returns RBN_E_BADARG if a group's normaliser is -inf
  * is NOT detected on device; `bad` (device int32, may be NULL) is set to the number of such groups. */
 int rbn_lognormalize(float* log_p, int64_t group_size, int64_t groups, int32_t* bad, void* stream);
+/* The same for float64 parameters (the reference's Prob / LogProb are fp64 when built from numpy weights, util.py:128-135). */
+int rbn_lognormalize_f64(double* log_p, int64_t group_size, int64_t groups, int32_t* bad, void* stream);
 
 /* ---- continuous RBN with multivariate-normal transitions (BASELINE config 4) ------------------------------------
  * beta_{i:k}(x) = exp(logc) N(x; mu, Sigma).  Terminal p(y|x) = N(y; x, cov_term); binary transition

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "rbn_viterbi": (ctypes.c_int, [ctypes.POINTER(RbnDesc), _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P, _P, _P, _P]),
     "rbn_export_chart": (ctypes.c_int, [ctypes.POINTER(RbnDesc), _P, _P, ctypes.c_size_t, ctypes.c_int32, _P, _P]),
     "rbn_lognormalize": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, _P, _P]),
+    "rbn_lognormalize_f64": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, _P, _P]),
     "rbn_gauss_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(GaussDesc)]),
     "rbn_gauss_inside_forward": (ctypes.c_int, [ctypes.POINTER(GaussDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                                 ctypes.c_size_t, _P, _P]),

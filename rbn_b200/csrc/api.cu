@@ -22,7 +22,7 @@ int simt_backward(const RbnDesc*, const WsLayout&, char*, const float*, const fl
 int export_chart(const RbnDesc*, const WsLayout&, const char*, const int*, int, double*, cudaStream_t);
 int simt_viterbi(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*, const int*,
                  float*, int*, int*, cudaStream_t);
-int lognormalize(float*, long long, long long, int*, cudaStream_t);
+int lognormalize(void*, int, long long, long long, int*, cudaStream_t);
 int tc_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*, const int*,
                float*, float*, float*, const int*, cudaStream_t);
 int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
@@ -289,7 +289,15 @@ int rbn_lognormalize(float* log_p, int64_t group_size, int64_t groups, int32_t* 
         set_error("rbn_lognormalize: bad argument");
         return RBN_E_BADARG;
     }
-    return lognormalize(log_p, group_size, groups, bad, (cudaStream_t)stream);
+    return lognormalize(log_p, 0, group_size, groups, bad, (cudaStream_t)stream);
+}
+
+int rbn_lognormalize_f64(double* log_p, int64_t group_size, int64_t groups, int32_t* bad, void* stream) {
+    if (!log_p || group_size < 1 || groups < 1) {
+        set_error("rbn_lognormalize_f64: bad argument");
+        return RBN_E_BADARG;
+    }
+    return lognormalize(log_p, 1, group_size, groups, bad, (cudaStream_t)stream);
 }
 
 int rbn_debug_gemm(int32_t M, int32_t N, int32_t K, const void* A, const void* B, float* D, int32_t a_mn, int32_t b_mn,

@@ -476,19 +476,23 @@ __global__ void k_export_chart(int N, int L, const int* __restrict__ lengths, in
 }
 
 // ---- log-space renormalisation (LogProb.enforce_constraints, util.py:193-198) --------------------------------------
-__global__ void k_lognormalize(float* __restrict__ lp, long long gs, long long groups, int* __restrict__ bad) {
+template <class F>      // float (fast exp) or double (the reference's parameters are fp64)
+__global__ void k_lognormalize(F* __restrict__ lp, long long gs, long long groups, int* __restrict__ bad) {
     // one thread per group; element (g, k) at lp[k * groups + g] => coalesced across the warp
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= groups) return;
-    float mx = -INFINITY;
-    for (long long k = 0; k < gs; ++k) mx = fmaxf(mx, lp[k * groups + g]);
+    F mx = -INFINITY;
+    for (long long k = 0; k < gs; ++k) mx = lp[k * groups + g] > mx ? lp[k * groups + g] : mx;
     if (mx == -INFINITY) {
         if (bad) atomicAdd(bad, 1);
         return;
     }
-    float s = 0.f;
-    for (long long k = 0; k < gs; ++k) s += __expf(lp[k * groups + g] - mx);
-    float lse = mx + logf(s);
+    F s = 0;
+    for (long long k = 0; k < gs; ++k) {
+        if (sizeof(F) == 4) s += __expf((float)(lp[k * groups + g] - mx));
+        else s += exp((double)(lp[k * groups + g] - mx));
+    }
+    const F lse = mx + (sizeof(F) == 4 ? (F)logf((float)s) : (F)log((double)s));
     for (long long k = 0; k < gs; ++k) lp[k * groups + g] -= lse;
 }
 
@@ -629,11 +633,12 @@ int export_chart(const RbnDesc* d, const WsLayout& ws, const char* base, const i
     return RBN_OK;
 }
 
-int lognormalize(float* lp, long long gs, long long groups, int* bad, cudaStream_t st) {
+int lognormalize(void* lp, int is_f64, long long gs, long long groups, int* bad, cudaStream_t st) {
     if (bad) RBN_CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
     int threads = 128;
     long long blocks = (groups + threads - 1) / threads;
-    k_lognormalize<<<(unsigned)blocks, threads, 0, st>>>(lp, gs, groups, bad);
+    if (is_f64) k_lognormalize<double><<<(unsigned)blocks, threads, 0, st>>>((double*)lp, gs, groups, bad);
+    else k_lognormalize<float><<<(unsigned)blocks, threads, 0, st>>>((float*)lp, gs, groups, bad);
     RBN_LAUNCH_CHECK("k_lognormalize");
     return RBN_OK;
 }

@@ -5,7 +5,7 @@ E-step  expected rule counts = raw gradient of sum_b log Z_b w.r.t. the log-para
         over the ranks (`rbn_b200.distributed.allreduce_counts`).
 M-step  every constrained parameter becomes its normalised expected counts over the dims the reference normalises
         (`Prob.enforce_constraints` / `LogProb.enforce_constraints`, /root/reference/rbnet/util.py:158-167, 193-198);
-        float32 `LogProb` tensors on the GPU are normalised by the fused kernel behind `rbn_lognormalize`.
+        `LogProb` tensors on the GPU (float32 or the API's float64) are normalised by the fused kernel behind `rbn_lognormalize` / `rbn_lognormalize_f64`.
 
 The reference has no EM loop of its own; what it prescribes is the constraint set (which dims sum to one) and the
 gradient these counts are.  Groups that received no count keep their old distribution.
@@ -69,19 +69,20 @@ def expected_counts(model, tokens=None, lengths=None, sequences=None, micro_batc
 
 
 def _lognormalize_(log_p, dims):
-    """log_p -= logsumexp over `dims`, in place.  float32 CUDA tensors whose normalised dims are the LEADING ones go
+    """log_p -= logsumexp over `dims`, in place.  CUDA tensors (fp32 / fp64) whose normalised dims are the LEADING ones go
     through the fused kernel (rbn_lognormalize: element (g, k) at log_p[k * groups + g])."""
     nd = log_p.dim()
     lead = tuple(range(len(dims)))
-    if log_p.is_cuda and log_p.dtype == torch.float32 and log_p.is_contiguous() and tuple(sorted(dims)) == lead and nd >= len(dims):
+    if log_p.is_cuda and log_p.dtype in (torch.float32, torch.float64) and log_p.is_contiguous() and tuple(sorted(dims)) == lead and nd >= len(dims):
         group = 1
         for d in dims:
             group *= log_p.shape[d]
         groups = log_p.numel() // max(group, 1)
         lib = _lib.load()
         with torch.cuda.device(log_p.device):
-            rc = lib.rbn_lognormalize(ctypes.c_void_p(log_p.data_ptr()), group, groups, None,
-                                      ctypes.c_void_p(torch.cuda.current_stream(log_p.device).cuda_stream))
+            fn = lib.rbn_lognormalize if log_p.dtype == torch.float32 else lib.rbn_lognormalize_f64
+            rc = fn(ctypes.c_void_p(log_p.data_ptr()), group, groups, None,
+                    ctypes.c_void_p(torch.cuda.current_stream(log_p.device).cuda_stream))
         _lib.check(rc, "rbn_lognormalize")
         return log_p
     return log_p.sub_(torch.logsumexp(log_p, dim=dims, keepdim=True))

@@ -73,6 +73,15 @@ def test_em_on_the_tensor_core_path_and_fused_lognormalize():
     ref = x.double() - torch.logsumexp(x.double(), dim=(0, 1), keepdim=True)
     out = em._lognormalize_(x.clone(), (0, 1))
     np.testing.assert_allclose(out.cpu().numpy(), ref.float().cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # the API's parameters are float64 (built from numpy weights): same kernel, double arithmetic (rbn_lognormalize_f64);
+    # the M-step of the model above went through it (its LogProb tensors are fp64 on the GPU)
+    x64 = torch.randn(5, 7, 11, device="cuda", dtype=torch.float64)
+    x64[:, :, 3] = -float("inf")
+    x64[2, 4, 3] = 0.5                                     # a group with a single finite entry
+    ref64 = x64 - torch.logsumexp(x64, dim=(0, 1), keepdim=True)
+    out64 = em._lognormalize_(x64.clone(), (0, 1))
+    np.testing.assert_allclose(out64.cpu().numpy(), ref64.cpu().numpy(), rtol=1e-13, atol=1e-13)
+    assert all(p.dtype == torch.float64 and p.is_cuda for _, p in em.constrained_parameters(model))
 
 
 def test_length_bucketed_batches_feed_the_tensor_core_em_step():
