@@ -59,7 +59,7 @@ def _pool_take(dev, at_least):
 
 
 def _pool_give(t):
-    if t is None or not t.is_cuda:
+    if t is None or not t.is_cuda or os.environ.get("RBN_WS_POOL") == "0":      # RBN_WS_POOL=0: always go through the allocator
         return
     cur = _WS_POOL.get(t.device.index)
     if cur is None or cur.numel() < t.numel():
