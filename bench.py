@@ -616,14 +616,19 @@ def finish_ours(args, wl):
     line = run_ours(args, wl)
     if world == 1 and args.workload == "c3" and not args.no_secondary and not args.batch and line is not None:
         others = {}
-        for name in ("c1", "c2"):
-            others[name] = _brief(run_ours(args, WORKLOADS[name], secondary=True))
-        g = run_gauss(args, WORKLOADS["c4"], ret=True)
-        if g is not None:
-            others["c4"] = _brief(g)
+        for name in ("c1", "c2", "c4"):          # never let a side measurement take the headline line down with it
+            try:
+                r = run_gauss(args, WORKLOADS[name], ret=True) if WORKLOADS[name].get("gauss") else run_ours(args, WORKLOADS[name], secondary=True)
+                if r is not None:
+                    others[name] = _brief(r)
+            except Exception as e:              # noqa: BLE001
+                others[name] = dict(error=f"{type(e).__name__}: {e}"[:300])
         line["other_workloads"] = others
     if world > 1 and args.workload == "c3" and not args.no_secondary:
-        sec = run_ours(args, WORKLOADS["c5"], secondary=True)
+        try:
+            sec = run_ours(args, WORKLOADS["c5"], secondary=True)
+        except Exception as e:                  # noqa: BLE001  (deterministic failures hit every rank alike: no rank is left waiting)
+            sec = dict(error=f"{type(e).__name__}: {e}"[:300])
         if line is not None and sec is not None:
             line["secondary"] = sec
     if line is not None:
