@@ -304,9 +304,17 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     const int RB = hsplit ? 128 : NS;          // left nonterminals (rows of Y) per sub-item
     const int nsub = (N / RB) * nblk;
     const int halves = hsplit ? 1 : (NS + 127) / 128;
+    // N = 64: a span fills half of the 128-row MMA and its per-span hand-offs (barriers, TMEM drain, store) cost more
+    // issue slots than its bytes cost HBM time.  Pair mode puts TWO consecutive spans of the diagonal into one item:
+    // A = [L(t); L(t+1)] (two 64-row atoms), B = [R(t); R(t+1)], one M = 128 x N = 128 MMA chain; the diagonal blocks of
+    // the accumulator are the two split-sums (the off-diagonal blocks are never read), and the 128 x 64 staging tile is
+    // exactly Y[t], Y[t+1] -- one full-box store.  Needs all splits in one K slab (w - 1 <= 64).
+    const bool pairm = (N == 64) && (Kpad <= 64);
+    const int per = pairm ? 2 : 1;             // spans per CTA iteration
+    const int ACC = pairm ? 128 : NS;          // accumulator columns per slot
     const int a_atoms = halves * 2;            // A operand covers halves * 128 rows (zero beyond the loaded atoms)
-    const int l_atoms = RB / 64;               // left-child atoms actually loaded
-    const int b_atoms = NS / 64;
+    const int l_atoms = pairm ? 2 : RB / 64;   // left-child atoms actually loaded
+    const int b_atoms = pairm ? 2 : NS / 64;
     const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * 8192;
     uint8_t* ybuf = smem + (size_t)stages * stage_bytes;       // nbuf x 16 KB staging tiles for the Y stores
     uint8_t* tail = ybuf + (size_t)nbuf * 16384;
@@ -322,9 +330,15 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // nslots = 2: two accumulators (the halves of a span, or consecutive spans when a span has one half); nslots = 1:
     // a single accumulator (256 TMEM columns), used when this kernel shares its SM with a GEMM CTA (co-resident schedule)
-    const uint32_t TMEM_COLS = tmem_cols_pow2(nslots * NS);
+    const uint32_t TMEM_COLS = tmem_cols_pow2(nslots * ACC);
     const int nI = L - w + 1;
     const size_t C = cells_per_seq(L);
+    auto span_ok = [&](int t) {                // span t of this launch exists and lies inside its sequence
+        if (t >= cnt) return false;
+        const int m = m0 + t;
+        const int b = m / nI;
+        return (m - b * nI) + w <= lengths[b];
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -357,7 +371,30 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+            for (int t = blockIdx.x * per; t < cnt; t += gridDim.x * per) {
+                if (pairm) {
+                    const bool ok0 = span_ok(t), ok1 = span_ok(t + 1);
+                    if (!ok0 && !ok1) continue;
+                    // a span beyond its sequence borrows its partner's (finite) rows; its factors c_j are all zero
+                    int lrow[2], rrow[2];
+                    for (int sp = 0; sp < 2; ++sp) {
+                        const int ts = sp ? (ok1 ? t + 1 : t) : (ok0 ? t : t + 1);
+                        const int m = m0 + ts;
+                        const int b = m / nI, i = m - b * nI;
+                        lrow[sp] = (int)(((size_t)b * L + i) * Lp + (i + 1));
+                        rrow[sp] = (int)(((size_t)b * (L + 1) + i + w) * Lp + (i + 1));
+                    }
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sL = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sR = sL + 2 * 8192;
+                    ptx::mbar_expect_tx(&tma_full[stage], 4u * (uint32_t)Kpad * 128);
+                    ptx::tma_load_2d(sL, &tmLC, &tma_full[stage], 0, lrow[0]);
+                    ptx::tma_load_2d(sL + 8192, &tmLC, &tma_full[stage], 0, lrow[1]);
+                    ptx::tma_load_2d(sR, &tmRC, &tma_full[stage], 0, rrow[0]);
+                    ptx::tma_load_2d(sR + 8192, &tmRC, &tma_full[stage], 0, rrow[1]);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 const int m = m0 + t;
                 const int b = m / nI, i = m - b * nI, k = i + w;
                 if (k > lengths[b]) continue;
@@ -386,36 +423,39 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         const int p = threadIdx.x - 128;                // 0..127
         int stage = 0;
         uint32_t phase = 0;
-        const int chunks_per_row = RB / 8;              // 16-byte chunks per left-child slab row
+        // 16-byte chunks per left-child slab row (pair mode: the two spans' 64-column atoms side by side, chunk >> 3 = span)
+        const int chunks_per_row = pairm ? 16 : RB / 8;
+        // pair mode: threads 0-63 own the splits of span t, threads 64-127 those of span t + 1
+        const int psp = pairm ? (p >> 6) : 0, pj = pairm ? (p & 63) : p;
         // e_left + e_right of this thread's split of span t (INT_MIN: no such split / span beyond its sequence)
         // (kept as two registers and added at the point of use, so that the loads stay in flight across the iteration)
         auto fetch_sft = [&](int t, int& ea, int& eb) {
             ea = INT_MIN; eb = 0;
-            if (t >= cnt || p >= w - 1) return;
+            t += psp;
+            if (t >= cnt || pj >= w - 1) return;
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI;
             if (i + w > lengths[b]) return;
             const int* ce_seq = ce + (size_t)b * C;
-            const int u = p + 1;
+            const int u = pj + 1;
             ea = ce_seq[cell_off(u, L) + i];
             eb = ce_seq[cell_off(w - u, L) + i + u];
         };
         int ea_next, eb_next;
-        fetch_sft(blockIdx.x, ea_next, eb_next);
-        for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
+        fetch_sft(blockIdx.x * per, ea_next, eb_next);
+        for (int t = blockIdx.x * per; t < cnt; t += gridDim.x * per) {
             const int sft = (ea_next == INT_MIN) ? INT_MIN : ea_next + eb_next;
-            fetch_sft(t + gridDim.x, ea_next, eb_next);   // in flight while this span is processed (global-load latency)
-            const int m = m0 + t;
-            const int b = m / nI, i = m - b * nI, k = i + w;
-            if (k > lengths[b]) continue;
+            fetch_sft(t + gridDim.x * per, ea_next, eb_next);   // in flight while this span is processed (global-load latency)
+            if (!span_ok(t) && !(pairm && span_ok(t + 1))) continue;
             int mxs = sft;
             for (int o = 16; o > 0; o >>= 1) mxs = max(mxs, __shfl_xor_sync(0xffffffffu, mxs, o));
             ptx::named_bar_sync(1, 128);                // every fix-up thread is done with the previous span's cj / red
             if (lane == 0) red[warp - 4] = mxs;
             ptx::named_bar_sync(1, 128);
-            const int E = max(max(red[0], red[1]), max(red[2], red[3]));
-            cj[p] = (p < w - 1) ? ldexpf(1.0f, max(sft - E, -60)) : 0.f;
-            if (p == 0) item_e[t] = E;
+            // the span's scale exponent: over all four warps, or over the two warps that own the span in pair mode
+            const int E = pairm ? max(red[2 * psp], red[2 * psp + 1]) : max(max(red[0], red[1]), max(red[2], red[3]));
+            cj[p] = (sft != INT_MIN) ? ldexpf(1.0f, max(sft - E, -60)) : 0.f;
+            if (pj == 0 && E != INT_MIN) item_e[t + psp] = E;
             ptx::named_bar_sync(1, 128);
             for (int sp = 0; sp < nsub * parts; ++sp) {
                 const int part = sp % parts;
@@ -424,7 +464,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                 uint8_t* sL = smem + (size_t)stage * stage_bytes;
                 for (int idx = p; idx < Ks * chunks_per_row; idx += 128) {
                     const int r = idx / chunks_per_row, c16 = idx - r * chunks_per_row;
-                    const float c = cj[part * 64 + r];
+                    const float c = cj[pairm ? ((c16 >> 3) * 64 + r) : (part * 64 + r)];
                     if (c == 1.0f) continue;
                     uint4* ptr = reinterpret_cast<uint4*>(sL + (uint32_t)(c16 >> 3) * 8192 + (uint32_t)r * 128 +
                                                          (uint32_t)(((c16 & 7) ^ (r & 7)) << 4));
@@ -446,13 +486,11 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     } else if (warp == 9) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_f16(128, NS, true, true, 0);
+            const uint32_t idesc = ptx::make_idesc_f16(128, ACC, true, true, 0);
             int stage = 0;
             uint32_t phase = 0, nacc = 0;       // nacc: accumulators used so far; slot = n & 1, its phase = (n >> 1) & 1
-            for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
-                const int m = m0 + t;
-                const int b = m / nI, i = m - b * nI;
-                if (i + w > lengths[b]) continue;
+            for (int t = blockIdx.x * per; t < cnt; t += gridDim.x * per) {
+                if (!span_ok(t) && !(pairm && span_ok(t + 1))) continue;
                 for (int sub = 0; sub < nsub; ++sub) {
                 for (int part = 0; part < parts; ++part) {
                     const int Ks = min(64, Kpad - part * 64);
@@ -470,7 +508,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                         for (int k16 = 0; k16 < Ks / 16; ++k16) {
                             const uint64_t ad = ptx::make_smem_desc(aL + (uint32_t)(h * 2) * 8192 + k16 * 2048, 8192, 1024);
                             const uint64_t bd = ptx::make_smem_desc(aR + k16 * 2048, 8192, 1024);
-                            ptx::mma_f16_ss(tmem_base + slot * NS, ad, bd, idesc, (uint32_t)!(part == 0 && k16 == 0));
+                            ptx::mma_f16_ss(tmem_base + slot * ACC, ad, bd, idesc, (uint32_t)!(part == 0 && k16 == 0));
                         }
                         if (part == parts - 1) ptx::mma_commit(&acc_full[slot]);
                     }
@@ -495,16 +533,16 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         const int gt = grp ? (int)threadIdx.x - 320 : (int)threadIdx.x;      // thread index within the group
         const bool issuer = (gt == 0);
         uint8_t* gbuf = two_groups ? ybuf + grp * 16384 : ybuf;
-        for (int t = blockIdx.x; t < cnt; t += gridDim.x) {
-            const int m = m0 + t;
-            const int b = m / nI, i = m - b * nI;
-            if (i + w > lengths[b]) {
+        for (int t = blockIdx.x * per; t < cnt; t += gridDim.x * per) {
+            if (!span_ok(t) && !(pairm && span_ok(t + 1))) {
                 // span beyond its sequence (ragged batch): its Y rows are still read (as A rows of the rule GEMM whose
                 // output row is dropped, as K rows of the count GEMM against a zero gradient row), so they must be
-                // finite -- write zeros; nothing else ever clears these buffers
+                // finite -- write zeros; nothing else ever clears these buffers.  (Pair mode with ONE span outside: its
+                // zero factors make its block of the accumulator zero and the pair's store writes it.)
                 if (grp == 0) {
                     uint4* dst = reinterpret_cast<uint4*>(Y + (size_t)t * N * N);
-                    for (int q = gt; q < N * N / 8; q += 128) dst[q] = make_uint4(0, 0, 0, 0);
+                    const int nq = ((pairm && t + 1 < cnt) ? 2 : 1) * N * N / 8;
+                    for (int q = gt; q < nq; q += 128) dst[q] = make_uint4(0, 0, 0, 0);
                 }
                 continue;
             }
@@ -516,8 +554,10 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                     if (two_groups && (int)slot != grp) continue;        // the other group's accumulator
                     ptx::mbar_wait(&acc_full[slot], slot_phase);
                     ptx::tc_fence_after();
-                    const uint32_t taddr = tmem_base + slot * NS + ((uint32_t)(qd * 32) << 16);
-                    const bool tail_half = (h * 128 + 128 > NS);         // only 64 valid rows (N = 64 or 192)
+                    // pair mode: rows 64-127 are span t + 1, whose split-sum is columns 64-127 of the accumulator
+                    const uint32_t taddr = tmem_base + slot * ACC + (pairm ? (uint32_t)(qd >> 1) * 64 : 0u) + ((uint32_t)(qd * 32) << 16);
+                    // only 64 valid rows: N = 192's second half, or a pair whose second span is past the launch
+                    const bool tail_half = pairm ? (t + 1 >= cnt) : (h * 128 + 128 > NS);
                     for (int c0 = 0; c0 < NS; c0 += 64) {
                         float v[64];
                         ptx::tmem_ld32(taddr + c0, v);
@@ -1741,7 +1781,9 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     if (rc) return rc;
     const int NS = N > 256 ? 256 : N;
     int halves = (NS + 127) / 128;
-    size_t stage_bytes = (size_t)(halves * 2 + NS / 64) * 8192;
+    const bool pairm = (N == 64) && (Kpad <= 64);        // two spans per CTA iteration (see k_tc_splitsum)
+    const int items = pairm ? (cnt + 1) / 2 : cnt;
+    size_t stage_bytes = (size_t)(halves * 2 + (pairm ? 2 : NS / 64)) * 8192;
     // small N: a span is a few KB of operands and 8-32 KB of output, the per-span hand-offs dominate -> co-resident CTAs
     static const int k1_ctas_env = env_int("RBN_TC_K1_CTAS", 0);
     int ctas = k1_ctas_env > 0 ? (k1_ctas_env > 2 ? 2 : k1_ctas_env) : (N <= 128 ? 2 : 1);
@@ -1765,7 +1807,7 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     size_t smem = stages * stage_bytes + (size_t)nbuf * 16384 /*Y staging*/ + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
     auto kern = ctas > 1 ? k_tc_splitsum<2> : k_tc_splitsum<1>;
     RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = cnt < sms * ctas ? cnt : sms * ctas;
+    int grid = items < sms * ctas ? items : sms * ctas;
     if (half_sm && grid > sms) grid = sms;
     { ProfScope ps(KC_SPLITSUM, st);
       // measured (round 2, same box, alternating runs): two groups 157 ms of split-sum per C3 step, one group 152 -- the

@@ -76,7 +76,11 @@ def _run(N, V, L, B, ragged, seed, path, chunk=0):
     return (W, T, pr, tok, lengths, coef), lz.detach().cpu().numpy(), Wt.grad.cpu().numpy(), Tt.grad.cpu().numpy(), pt.grad.cpu().numpy()
 
 
-@pytest.mark.parametrize("N,V,L,B,ragged,chunk", [(64, 16, 8, 3, False, 0), (64, 16, 12, 5, True, 128), (128, 8, 9, 3, True, 0),
+# N = 64 runs the split-sum kernel in pair mode (two spans per MMA): odd span counts per launch (B = 3, 5; chunk 127),
+# spans beyond their sequence paired with live ones (ragged), and L = 80, whose diagonals wider than 65 fall back to
+# one span per item inside the same pass
+@pytest.mark.parametrize("N,V,L,B,ragged,chunk", [(64, 16, 8, 3, False, 0), (64, 16, 12, 5, True, 128), (64, 16, 13, 5, True, 127),
+                                                  (64, 8, 80, 3, True, 0), (128, 8, 9, 3, True, 0),
                                                   (192, 8, 6, 2, False, 0), (256, 32, 7, 2, True, 0), (256, 32, 20, 2, False, 0),
                                                   (512, 8, 6, 2, True, 0), (512, 16, 19, 3, True, 0)])
 def test_tc_path_vs_fp64_oracle(N, V, L, B, ragged, chunk):
