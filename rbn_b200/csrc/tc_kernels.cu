@@ -283,7 +283,22 @@ struct EpiCounts {
 template <int MINB>
 static constexpr int k1_threads() { return MINB == 1 ? 448 : 320; }
 
-template <int MINB>       // co-resident CTAs per SM the register budget is cut for (2 for small N)
+// Span m of a launch as (sequence b, start i), stepped without a division per item (the per-span control code is what
+// bounds this kernel at N = 64: 2742 warp instructions per span in round 2's source-level profile, two integer
+// divisions per role among them).
+struct SpanIter {
+    int b, i, sb, si, nI;
+    __device__ SpanIter(int m_first, int step, int nI_) : nI(nI_) {
+        b = m_first / nI_; i = m_first - b * nI_;
+        sb = step / nI_; si = step - sb * nI_;
+    }
+    __device__ void next() { b += sb; i += si; if (i >= nI) { i -= nI; ++b; } }
+    __device__ void succ(int& b1, int& i1) const { b1 = b; i1 = i + 1; if (i1 >= nI) { i1 = 0; ++b1; } }   // span m + 1
+};
+
+// MINB: co-resident CTAs per SM the register budget is cut for (2 for small N).  PAIR: the N = 64 pair mode below, as a
+// template parameter so that the sub-block / half / K-slab loops of the general kernel fold away.
+template <int MINB, bool PAIR>
 __global__ void __launch_bounds__(k1_threads<MINB>(), MINB)
 k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ CUtensorMap tmRC,
               const __grid_constant__ CUtensorMap tmLC1, const __grid_constant__ CUtensorMap tmRC1,   // second K-slab (rows = Kpad - 64)
@@ -293,29 +308,34 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int Kpad = ((w - 1) + 15) & ~15;
-    const int parts = (Kpad + 63) / 64;
+    const int parts = PAIR ? 1 : (Kpad + 63) / 64;
     // N > 256: the N x N split-sum is cut into (N/256)^2 sub-blocks of 256 x 256, each handled like a span of its own
-    const int NS = N > 256 ? 256 : N;          // nonterminals per sub-block side
-    const int nblk = N / NS;
+    const int NS = PAIR ? 64 : (N > 256 ? 256 : N);          // nonterminals per sub-block side
+    const int nblk = PAIR ? 1 : N / NS;
+    const int nblk_sh = nblk >> 1;             // nblk is 1 or 2: sub / nblk = sub >> nblk_sh
     // nslots == 1 (one 256-column accumulator): the two 128-row halves of a sub-block cannot accumulate side by side
     // over the K slabs, so every half becomes a sub-item of its own (its left-child slab has 128 nonterminals; the
     // right-child slab is loaded once per half)
-    const bool hsplit = (nslots == 1) && (NS == 256);
+    const bool hsplit = !PAIR && (nslots == 1) && (NS == 256);
     const int RB = hsplit ? 128 : NS;          // left nonterminals (rows of Y) per sub-item
-    const int nsub = (N / RB) * nblk;
-    const int halves = hsplit ? 1 : (NS + 127) / 128;
+    const int nsub = PAIR ? 1 : (N / RB) * nblk;
+    const int halves = (PAIR || hsplit) ? 1 : (NS + 127) / 128;
     // N = 64: a span fills half of the 128-row MMA and its per-span hand-offs (barriers, TMEM drain, store) cost more
     // issue slots than its bytes cost HBM time.  Pair mode puts TWO consecutive spans of the diagonal into one item:
     // A = [L(t); L(t+1)] (two 64-row atoms), B = [R(t); R(t+1)], one M = 128 x N = 128 MMA chain; the diagonal blocks of
     // the accumulator are the two split-sums (the off-diagonal blocks are never read), and the 128 x 64 staging tile is
     // exactly Y[t], Y[t+1] -- one full-box store.  Needs all splits in one K slab (w - 1 <= 64).
-    const bool pairm = (N == 64) && (Kpad <= 64);
-    const int per = pairm ? 2 : 1;             // spans per CTA iteration
+    constexpr bool pairm = PAIR;               // host: N == 64 and Kpad <= 64
+    constexpr int per = PAIR ? 2 : 1;          // spans per CTA iteration
     const int ACC = pairm ? 128 : NS;          // accumulator columns per slot
     const int a_atoms = halves * 2;            // A operand covers halves * 128 rows (zero beyond the loaded atoms)
     const int l_atoms = pairm ? 2 : RB / 64;   // left-child atoms actually loaded
     const int b_atoms = pairm ? 2 : NS / 64;
-    const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * 8192;
+    // an operand atom is 64 nonterminals x up to 64 splits (128 B per split row).  Pair mode packs atoms at Kpad rows
+    // instead of 64, so that the narrow diagonals (where most spans are) get a deeper ring out of the same shared memory:
+    // a pair is a ~2 us chain of load -> fix-up -> MMA, and only the ring depth overlaps consecutive pairs
+    const uint32_t atom_bytes = pairm ? (uint32_t)Kpad * 128 : 8192;
+    const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * atom_bytes;
     uint8_t* ybuf = smem + (size_t)stages * stage_bytes;       // nbuf x 16 KB staging tiles for the Y stores
     uint8_t* tail = ybuf + (size_t)nbuf * 16384;
     uint64_t* tma_full = (uint64_t*)tail;         // [stages]
@@ -333,12 +353,9 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     const uint32_t TMEM_COLS = tmem_cols_pow2(nslots * ACC);
     const int nI = L - w + 1;
     const size_t C = cells_per_seq(L);
-    auto span_ok = [&](int t) {                // span t of this launch exists and lies inside its sequence
-        if (t >= cnt) return false;
-        const int m = m0 + t;
-        const int b = m / nI;
-        return (m - b * nI) + w <= lengths[b];
-    };
+    const int step = (int)gridDim.x * per;     // spans between consecutive items of this CTA
+    // span t of this launch, at (sequence b, start i), exists and lies inside its sequence
+    auto span_ok = [&](int t, int b, int i) { return t < cnt && i + w <= lengths[b]; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -371,37 +388,34 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x * per; t < cnt; t += gridDim.x * per) {
+            SpanIter it(m0 + blockIdx.x * per, step, nI);
+            for (int t = blockIdx.x * per; t < cnt; t += step, it.next()) {
+                const int b = it.b, i = it.i, k = i + w;
                 if (pairm) {
-                    const bool ok0 = span_ok(t), ok1 = span_ok(t + 1);
+                    int b1, i1;
+                    it.succ(b1, i1);
+                    const bool ok0 = span_ok(t, b, i), ok1 = span_ok(t + 1, b1, i1);
                     if (!ok0 && !ok1) continue;
                     // a span beyond its sequence borrows its partner's (finite) rows; its factors c_j are all zero
-                    int lrow[2], rrow[2];
-                    for (int sp = 0; sp < 2; ++sp) {
-                        const int ts = sp ? (ok1 ? t + 1 : t) : (ok0 ? t : t + 1);
-                        const int m = m0 + ts;
-                        const int b = m / nI, i = m - b * nI;
-                        lrow[sp] = (int)(((size_t)b * L + i) * Lp + (i + 1));
-                        rrow[sp] = (int)(((size_t)b * (L + 1) + i + w) * Lp + (i + 1));
-                    }
+                    const int ba = ok0 ? b : b1, ia = ok0 ? i : i1, bb = ok1 ? b1 : b, ib = ok1 ? i1 : i;
+                    const int lrow0 = (int)(((size_t)ba * L + ia) * Lp + (ia + 1)), rrow0 = (int)(((size_t)ba * (L + 1) + ia + w) * Lp + (ia + 1));
+                    const int lrow1 = (int)(((size_t)bb * L + ib) * Lp + (ib + 1)), rrow1 = (int)(((size_t)bb * (L + 1) + ib + w) * Lp + (ib + 1));
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sL = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sR = sL + 2 * 8192;
+                    uint8_t* sR = sL + 2 * atom_bytes;
                     ptx::mbar_expect_tx(&tma_full[stage], 4u * (uint32_t)Kpad * 128);
-                    ptx::tma_load_2d(sL, &tmLC, &tma_full[stage], 0, lrow[0]);
-                    ptx::tma_load_2d(sL + 8192, &tmLC, &tma_full[stage], 0, lrow[1]);
-                    ptx::tma_load_2d(sR, &tmRC, &tma_full[stage], 0, rrow[0]);
-                    ptx::tma_load_2d(sR + 8192, &tmRC, &tma_full[stage], 0, rrow[1]);
+                    ptx::tma_load_2d(sL, &tmLC, &tma_full[stage], 0, lrow0);
+                    ptx::tma_load_2d(sL + atom_bytes, &tmLC, &tma_full[stage], 0, lrow1);
+                    ptx::tma_load_2d(sR, &tmRC, &tma_full[stage], 0, rrow0);
+                    ptx::tma_load_2d(sR + atom_bytes, &tmRC, &tma_full[stage], 0, rrow1);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                     continue;
                 }
-                const int m = m0 + t;
-                const int b = m / nI, i = m - b * nI, k = i + w;
                 if (k > lengths[b]) continue;
                 const int lc_row = (int)(((size_t)b * L + i) * Lp + (i + 1));
                 const int rc_row = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
                 for (int sub = 0; sub < nsub; ++sub) {
-                    const int bcol = (sub / nblk) * RB, ccol = (sub % nblk) * NS;
+                    const int bcol = (sub >> nblk_sh) * RB, ccol = (sub & (nblk - 1)) * NS;
                     for (int part = 0; part < parts; ++part) {
                         ptx::mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sL = smem + (size_t)stage * stage_bytes;
@@ -423,30 +437,87 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         const int p = threadIdx.x - 128;                // 0..127
         int stage = 0;
         uint32_t phase = 0;
-        // 16-byte chunks per left-child slab row (pair mode: the two spans' 64-column atoms side by side, chunk >> 3 = span)
-        const int chunks_per_row = pairm ? 16 : RB / 8;
-        // pair mode: threads 0-63 own the splits of span t, threads 64-127 those of span t + 1
-        const int psp = pairm ? (p >> 6) : 0, pj = pairm ? (p & 63) : p;
+        if constexpr (PAIR) {
+            // Pair mode: thread (span psp, split pj) scales ITS OWN row of its span's left-child atom, and every warp finds
+            // its span's scale exponent by itself (a thread also loads the exponents of split pj ^ 32, so the 32 lanes of
+            // a warp see all 64 splits): no shared factors and no named barrier in this role.
+            const int psp = p >> 6, pj = p & 63;
+            auto fetch2 = [&](int t, int b, int i, int& ea, int& eb, int& oa, int& ob) {     // (b, i): span t of the launch
+                ea = oa = INT_MIN; eb = ob = 0;
+                if (t >= cnt || i + w > lengths[b]) return;
+                const int* ce_seq = ce + (size_t)b * C;
+                const int u = pj + 1, v = (pj ^ 32) + 1;
+                if (u < w) { ea = ce_seq[cell_off(u, L) + i]; eb = ce_seq[cell_off(w - u, L) + i + u]; }
+                if (v < w) { oa = ce_seq[cell_off(v, L) + i]; ob = ce_seq[cell_off(w - v, L) + i + v]; }
+            };
+            SpanIter it(m0 + blockIdx.x * 2, step, nI);
+            auto my_span = [&](int& b, int& i) { b = it.b; i = it.i; if (psp) it.succ(b, i); };   // this thread's span of the item
+            int ea, eb, oa, ob, bm, im;
+            my_span(bm, im);
+            fetch2(blockIdx.x * 2 + psp, bm, im, ea, eb, oa, ob);
+            for (int t = blockIdx.x * 2; t < cnt; t += step) {
+                const int sft = (ea == INT_MIN) ? INT_MIN : ea + eb;
+                const int oft = (oa == INT_MIN) ? INT_MIN : oa + ob;
+                bool ok = span_ok(t, it.b, it.i);
+                if (!ok) { int b1, i1; it.succ(b1, i1); ok = span_ok(t + 1, b1, i1); }
+                it.next();
+                my_span(bm, im);
+                fetch2(t + step + psp, bm, im, ea, eb, oa, ob);      // in flight while this item is processed
+                if (!ok) continue;
+                int E = max(sft, oft);
+                for (int o = 16; o > 0; o >>= 1) E = max(E, __shfl_xor_sync(0xffffffffu, E, o));
+                // c_j = 2^(sft - E), exponent clamped at -60 (zero in fp16 either way); 0 for rows past the last split and
+                // for every row of a span beyond its sequence
+                const float c = (sft != INT_MIN) ? __int_as_float((max(sft - E, -60) + 127) << 23) : 0.f;
+                if (pj == 0 && E != INT_MIN) item_e[t + psp] = E;
+                ptx::mbar_wait(&tma_full[stage], phase);
+                if (pj < Kpad && c != 1.0f) {
+                    uint8_t* rowp = smem + (size_t)stage * stage_bytes + (uint32_t)psp * atom_bytes + (uint32_t)pj * 128;
+                    const __half2 sc = __float2half2_rn(c);
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint4* ptr = reinterpret_cast<uint4*>(rowp + ((ch ^ (pj & 7)) << 4));
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (c != 0.f) {
+                            v = *ptr;
+                            __half2* hv = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) hv[qd] = __hmul2(hv[qd], sc);
+                        }
+                        *ptr = v;
+                    }
+                }
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(&fix_full[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        } else {
+        // 16-byte chunks per left-child slab row
+        const int chunks_per_row = RB / 8;
+        const int psp = 0, pj = p;
         // e_left + e_right of this thread's split of span t (INT_MIN: no such split / span beyond its sequence)
         // (kept as two registers and added at the point of use, so that the loads stay in flight across the iteration)
-        auto fetch_sft = [&](int t, int& ea, int& eb) {
+        auto fetch_sft = [&](int t, int b, int i, int& ea, int& eb) {       // (b, i): span t of the launch
             ea = INT_MIN; eb = 0;
-            t += psp;
-            if (t >= cnt || pj >= w - 1) return;
-            const int m = m0 + t;
-            const int b = m / nI, i = m - b * nI;
-            if (i + w > lengths[b]) return;
+            if (t >= cnt || pj >= w - 1 || i + w > lengths[b]) return;
             const int* ce_seq = ce + (size_t)b * C;
             const int u = pj + 1;
             ea = ce_seq[cell_off(u, L) + i];
             eb = ce_seq[cell_off(w - u, L) + i + u];
         };
-        int ea_next, eb_next;
-        fetch_sft(blockIdx.x * per, ea_next, eb_next);
-        for (int t = blockIdx.x * per; t < cnt; t += gridDim.x * per) {
+        SpanIter it(m0 + blockIdx.x * per, step, nI);
+        auto my_span = [&](int& b, int& i) { b = it.b; i = it.i; if (pairm && psp) it.succ(b, i); };   // this thread's span of the item
+        int ea_next, eb_next, bm, im;
+        my_span(bm, im);
+        fetch_sft(blockIdx.x * per + psp, bm, im, ea_next, eb_next);
+        for (int t = blockIdx.x * per; t < cnt; t += step) {
             const int sft = (ea_next == INT_MIN) ? INT_MIN : ea_next + eb_next;
-            fetch_sft(t + gridDim.x * per, ea_next, eb_next);   // in flight while this span is processed (global-load latency)
-            if (!span_ok(t) && !(pairm && span_ok(t + 1))) continue;
+            bool ok = span_ok(t, it.b, it.i);
+            if (pairm && !ok) { int b1, i1; it.succ(b1, i1); ok = span_ok(t + 1, b1, i1); }
+            it.next();
+            my_span(bm, im);
+            fetch_sft(t + step + psp, bm, im, ea_next, eb_next);   // in flight while this item is processed (global-load latency)
+            if (!ok) continue;
             int mxs = sft;
             for (int o = 16; o > 0; o >>= 1) mxs = max(mxs, __shfl_xor_sync(0xffffffffu, mxs, o));
             ptx::named_bar_sync(1, 128);                // every fix-up thread is done with the previous span's cj / red
@@ -457,8 +528,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
             cj[p] = (sft != INT_MIN) ? ldexpf(1.0f, max(sft - E, -60)) : 0.f;
             if (pj == 0 && E != INT_MIN) item_e[t + psp] = E;
             ptx::named_bar_sync(1, 128);
-            for (int sp = 0; sp < nsub * parts; ++sp) {
-                const int part = sp % parts;
+            for (int sp = 0, part = 0; sp < nsub * parts; ++sp, part = (part + 1 == parts) ? 0 : part + 1) {
                 const int Ks = min(64, Kpad - part * 64);
                 ptx::mbar_wait(&tma_full[stage], phase);
                 uint8_t* sL = smem + (size_t)stage * stage_bytes;
@@ -466,7 +536,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                     const int r = idx / chunks_per_row, c16 = idx - r * chunks_per_row;
                     const float c = cj[pairm ? ((c16 >> 3) * 64 + r) : (part * 64 + r)];
                     if (c == 1.0f) continue;
-                    uint4* ptr = reinterpret_cast<uint4*>(sL + (uint32_t)(c16 >> 3) * 8192 + (uint32_t)r * 128 +
+                    uint4* ptr = reinterpret_cast<uint4*>(sL + (uint32_t)(c16 >> 3) * atom_bytes + (uint32_t)r * 128 +
                                                          (uint32_t)(((c16 & 7) ^ (r & 7)) << 4));
                     uint4 v = make_uint4(0, 0, 0, 0);
                     if (c != 0.f) {
@@ -483,21 +553,25 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
+        }
     } else if (warp == 9) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             const uint32_t idesc = ptx::make_idesc_f16(128, ACC, true, true, 0);
             int stage = 0;
             uint32_t phase = 0, nacc = 0;       // nacc: accumulators used so far; slot = n & 1, its phase = (n >> 1) & 1
-            for (int t = blockIdx.x * per; t < cnt; t += gridDim.x * per) {
-                if (!span_ok(t) && !(pairm && span_ok(t + 1))) continue;
+            SpanIter it(m0 + blockIdx.x * per, step, nI);
+            for (int t = blockIdx.x * per; t < cnt; t += step, it.next()) {
+                bool ok = span_ok(t, it.b, it.i);
+                if (pairm && !ok) { int b1, i1; it.succ(b1, i1); ok = span_ok(t + 1, b1, i1); }
+                if (!ok) continue;
                 for (int sub = 0; sub < nsub; ++sub) {
                 for (int part = 0; part < parts; ++part) {
                     const int Ks = min(64, Kpad - part * 64);
                     ptx::mbar_wait(&fix_full[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t aL = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t aR = aL + (uint32_t)a_atoms * 8192;
+                    const uint32_t aR = aL + (uint32_t)a_atoms * atom_bytes;
                     for (int h = 0; h < halves; ++h) {
                         const uint32_t na = nacc + h;
                         const uint32_t slot = nslots == 2 ? (na & 1) : 0, slot_phase = nslots == 2 ? ((na >> 1) & 1) : (na & 1);
@@ -506,8 +580,8 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                             ptx::tc_fence_after();
                         }
                         for (int k16 = 0; k16 < Ks / 16; ++k16) {
-                            const uint64_t ad = ptx::make_smem_desc(aL + (uint32_t)(h * 2) * 8192 + k16 * 2048, 8192, 1024);
-                            const uint64_t bd = ptx::make_smem_desc(aR + k16 * 2048, 8192, 1024);
+                            const uint64_t ad = ptx::make_smem_desc(aL + (uint32_t)(h * 2) * atom_bytes + k16 * 2048, atom_bytes, 1024);
+                            const uint64_t bd = ptx::make_smem_desc(aR + k16 * 2048, atom_bytes, 1024);
                             ptx::mma_f16_ss(tmem_base + slot * ACC, ad, bd, idesc, (uint32_t)!(part == 0 && k16 == 0));
                         }
                         if (part == parts - 1) ptx::mma_commit(&acc_full[slot]);
@@ -533,8 +607,11 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         const int gt = grp ? (int)threadIdx.x - 320 : (int)threadIdx.x;      // thread index within the group
         const bool issuer = (gt == 0);
         uint8_t* gbuf = two_groups ? ybuf + grp * 16384 : ybuf;
-        for (int t = blockIdx.x * per; t < cnt; t += gridDim.x * per) {
-            if (!span_ok(t) && !(pairm && span_ok(t + 1))) {
+        SpanIter it(m0 + blockIdx.x * per, step, nI);
+        for (int t = blockIdx.x * per; t < cnt; t += step, it.next()) {
+            bool ok = span_ok(t, it.b, it.i);
+            if (pairm && !ok) { int b1, i1; it.succ(b1, i1); ok = span_ok(t + 1, b1, i1); }
+            if (!ok) {
                 // span beyond its sequence (ragged batch): its Y rows are still read (as A rows of the rule GEMM whose
                 // output row is dropped, as K rows of the count GEMM against a zero gradient row), so they must be
                 // finite -- write zeros; nothing else ever clears these buffers.  (Pair mode with ONE span outside: its
@@ -547,7 +624,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                 continue;
             }
             for (int sub = 0; sub < nsub; ++sub) {
-                const int brow = (sub / nblk) * RB, ccol = (sub % nblk) * NS;
+                const int brow = (sub >> nblk_sh) * RB, ccol = (sub & (nblk - 1)) * NS;
                 for (int h = 0; h < halves; ++h) {
                     const uint32_t na = nacc + h;
                     const uint32_t slot = nslots == 2 ? (na & 1) : 0, slot_phase = nslots == 2 ? ((na >> 1) & 1) : (na & 1);
@@ -563,7 +640,9 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                         ptx::tmem_ld32(taddr + c0, v);
                         ptx::tmem_ld32(taddr + c0 + 32, v + 32);
                         ptx::tmem_ld_wait();
-                        if (two_groups)          // one staging tile per group (the two groups' stores interleave)
+                        if (PAIR)                // two co-resident CTAs: two staging tiles
+                            ptx::stage_store_tile(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
+                        else if (two_groups)     // one staging tile per group (the two groups' stores interleave)
                             ptx::stage_store_tile<1>(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3 + grp, issuer, true, y_pol);
                         else if (nbuf == 4)
                             ptx::stage_store_tile<4>(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
@@ -1783,7 +1862,7 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     int halves = (NS + 127) / 128;
     const bool pairm = (N == 64) && (Kpad <= 64);        // two spans per CTA iteration (see k_tc_splitsum)
     const int items = pairm ? (cnt + 1) / 2 : cnt;
-    size_t stage_bytes = (size_t)(halves * 2 + (pairm ? 2 : NS / 64)) * 8192;
+    size_t stage_bytes = pairm ? (size_t)4 * Kpad * 128 : (size_t)(halves * 2 + NS / 64) * 8192;
     // small N: a span is a few KB of operands and 8-32 KB of output, the per-span hand-offs dominate -> co-resident CTAs
     static const int k1_ctas_env = env_int("RBN_TC_K1_CTAS", 0);
     int ctas = k1_ctas_env > 0 ? (k1_ctas_env > 2 ? 2 : k1_ctas_env) : (N <= 128 ? 2 : 1);
@@ -1793,7 +1872,9 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     int nbuf = (nbuf_env >= 2 && nbuf_env <= 4) ? nbuf_env : (ctas == 1 && !half_sm ? 4 : 2);
     if (ctas > 1 || half_sm) nbuf = 2;
     int stages = (int)((232448 / ctas - 1024 * ctas - 2048 - nbuf * 16384) / stage_bytes);
-    if (stages > 6) stages = 6;
+    static const int k1_stages_env = env_int("RBN_TC_K1_STAGES", 0);
+    const int max_stages = k1_stages_env > 0 ? (k1_stages_env > 8 ? 8 : k1_stages_env) : (pairm ? 8 : 6);
+    if (stages > max_stages) stages = max_stages;
     if (stages < 1) { stages = 1; ctas = 1; }
     int nslots = 2;
     if (half_sm) {              // leave half of the SM (shared memory, TMEM, registers) to a co-resident GEMM CTA
@@ -1805,7 +1886,8 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
         ctas = 2;               // selects the register-capped instantiation; the grid stays one CTA per SM
     }
     size_t smem = stages * stage_bytes + (size_t)nbuf * 16384 /*Y staging*/ + 1024 /*barriers, cj*/ + 1024 /*alignment*/;
-    auto kern = ctas > 1 ? k_tc_splitsum<2> : k_tc_splitsum<1>;
+    auto kern = pairm ? (ctas > 1 ? k_tc_splitsum<2, true> : k_tc_splitsum<1, true>)
+                      : (ctas > 1 ? k_tc_splitsum<2, false> : k_tc_splitsum<1, false>);
     RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = items < sms * ctas ? items : sms * ctas;
     if (half_sm && grid > sms) grid = sms;
