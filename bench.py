@@ -538,11 +538,20 @@ def run_ours(args, wl, secondary=False):
                             frac=round(ach / peak, 3), launches_per_step=launches, avg_launch_ms=ms / launches,
                             algorithmic_per_launch=amount / launches,
                             traffic=(tr * spans * (k1_passes if cls == "split_sum" else 1.0) / launches) if tr else None)
+        # the rule / count GEMMs do 2 N^3 flops per 2 N^2 bytes of Y: N flop per byte, against a ridge point of
+        # peak flops / peak bytes (~213 flop/B on the measured peaks): HBM-bound for N <= 192, tensor-bound from N = 256
+        gemm_hbm = N < peaks["tflops"] * 1e3 / peaks["hbm"]
         entry("split_sum", "hbm", k1_passes * (y_bytes + row_bytes), peaks["hbm"], "GB/s")
-        entry("rule_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
+        if gemm_hbm:
+            entry("rule_gemm", "hbm", y_bytes, peaks["hbm"], "GB/s")
+        else:
+            entry("rule_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
         if wl["outside"]:
             entry("gy_gemm", "hbm", y_bytes, peaks["hbm"], "GB/s")
-            entry("count_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
+            if gemm_hbm:
+                entry("count_gemm", "hbm", y_bytes, peaks["hbm"], "GB/s")
+            else:
+                entry("count_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
             entry("child_grad", "hbm", y_bytes + row_bytes + 2.0 * splits * 2 * N * 4, peaks["hbm"], "GB/s")
         if per:
             top = max(per, key=lambda k: per[k]["ms_per_step"])

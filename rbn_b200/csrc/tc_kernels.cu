@@ -640,6 +640,10 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                         ptx::tmem_ld32(taddr + c0, v);
                         ptx::tmem_ld32(taddr + c0 + 32, v + 32);
                         ptx::tmem_ld_wait();
+                        if (PAIR) {              // the whole accumulator is in registers: hand it back before packing / storing
+                            ptx::tc_fence_before();
+                            ptx::mbar_arrive(&acc_empty[slot]);
+                        }
                         if (PAIR)                // two co-resident CTAs: two staging tiles
                             ptx::stage_store_tile(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
                         else if (two_groups)     // one staging tile per group (the two groups' stores interleave)
@@ -652,8 +656,10 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                             ptx::stage_store_tile(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
                         ++nstore;
                     }
-                    ptx::tc_fence_before();
-                    ptx::mbar_arrive(&acc_empty[slot]);
+                    if (!PAIR) {
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(&acc_empty[slot]);
+                    }
                 }
                 nacc += halves;
             }

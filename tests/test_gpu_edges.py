@@ -194,7 +194,8 @@ def test_batched_tokens_with_two_terminal_variables():
     lz2.sum().backward()
     for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         assert n1 == n2
-        np.testing.assert_allclose(p2.grad.cpu().numpy(), p1.grad.cpu().numpy(), rtol=1e-5, atol=1e-8)
+        # same kernels, different batch order (pack_sequences sorts): fp32 atomics add in another order
+        np.testing.assert_allclose(p2.grad.cpu().numpy(), p1.grad.cpu().numpy(), rtol=1e-4, atol=1e-6)
     bad = raw.copy()
     bad[0, 0, 0] = V0                              # valid for variable 1's alphabet, not for variable 0's
     with pytest.raises(IndexError):
