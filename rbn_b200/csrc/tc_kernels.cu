@@ -606,7 +606,8 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         const int row = qd * 32 + lane;
         const int gt = grp ? (int)threadIdx.x - 320 : (int)threadIdx.x;      // thread index within the group
         const bool issuer = (gt == 0);
-        uint8_t* gbuf = two_groups ? ybuf + grp * 16384 : ybuf;
+        // two groups: the four staging tiles are split two and two (one store in flight per group) when there are four
+        uint8_t* gbuf = two_groups ? ybuf + grp * (nbuf == 4 ? 32768 : 16384) : ybuf;
         SpanIter it(m0 + blockIdx.x * per, step, nI);
         for (int t = blockIdx.x * per; t < cnt; t += step, it.next()) {
             bool ok = span_ok(t, it.b, it.i);
@@ -646,6 +647,8 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                         }
                         if (PAIR)                // two co-resident CTAs: two staging tiles
                             ptx::stage_store_tile(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3, issuer, true, y_pol);
+                        else if (two_groups && nbuf == 4)
+                            ptx::stage_store_tile<2>(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3 + grp, issuer, true, y_pol);
                         else if (two_groups)     // one staging tile per group (the two groups' stores interleave)
                             ptx::stage_store_tile<1>(gbuf, tail_half ? &tmYtail : &tmY, ccol + c0, t * N + brow + h * 128, row, v, nstore, 3 + grp, issuer, true, y_pol);
                         else if (nbuf == 4)
@@ -1906,7 +1909,9 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     if (half_sm && grid > sms) grid = sms;
     { ProfScope ps(KC_SPLITSUM, st);
       // measured (round 2, same box, alternating runs): two groups 157 ms of split-sum per C3 step, one group 152 -- the
-      // single staging tile per group serialises on the TMA store's smem read; the second group stays selectable
+      // single staging tile per group serialises on the TMA store's smem read.  With two staging tiles per group (what
+      // RBN_TC_K1_GROUPS=2 selects now, out of the same four tiles) it is a wash: 153.4 vs 151.2 ms over three alternating
+      // runs each on a 1.5 GHz box -- the epilogue's ~960 instructions per span are not what paces this kernel.
       static const int k1_groups = env_int("RBN_TC_K1_GROUPS", 1);
       RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, (ctas > 1 || k1_groups < 2) ? k1_threads<2>() : k1_threads<1>(), smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
                                          c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y_of(u), c.e_of(u), nslots,
