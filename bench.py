@@ -387,6 +387,8 @@ def run_ours(args, wl, secondary=False):
         """One pass of the hot path over the batch, inputs resident in HBM.  Micro-batches run inside + outside back to
         back (the second pass reuses the first one's workspace); every micro-batch's count tensors go into an
         asynchronous all-reduce that overlaps the next micro-batch (N > 1), and are summed at the end of the step."""
+        if args.streams > 1:
+            return device_step_streams()
         red = CountReducer()
         outs = []
         for b0 in range(0, B, micro):
@@ -397,6 +399,34 @@ def run_ours(args, wl, secondary=False):
             del lz                           # drops the pass (its workspace goes back to the allocator for the next one)
         grads = red.result() if wl["outside"] else None
         return (outs[0] if len(outs) == 1 else torch.cat(outs)), grads
+
+    side = [torch.cuda.Stream(device=dev) for _ in range(max(0, args.streams))] if args.streams > 1 else []
+
+    def device_step_streams():
+        """Experiment (--streams S, single GPU): the micro-batches dealt over S launch streams, so that the ramp-up and the
+        last wave of one micro-batch's per-diagonal launches overlap another's."""
+        cur = torch.cuda.current_stream()
+        outs, gsum = {}, [None] * len(side)
+        for st in side:
+            st.wait_stream(cur)
+        for k, b0 in enumerate(range(0, B, micro)):
+            st = side[k % len(side)]
+            with torch.cuda.stream(st):
+                lz = inside_logZ(Wd, Td, pd, tok_d[b0:b0 + micro], len_h[b0:b0 + micro], chunk_items=args.chunk)
+                if wl["outside"]:
+                    g = torch.autograd.grad(lz.sum(), (Wd, Td, pd))
+                    j = k % len(side)
+                    gsum[j] = list(g) if gsum[j] is None else [a.add_(b) for a, b in zip(gsum[j], g)]
+                outs[k] = lz.detach()
+                del lz
+        for st in side:
+            cur.wait_stream(st)
+        grads = None
+        if wl["outside"]:
+            parts = [g for g in gsum if g is not None]
+            grads = tuple(sum(p[i] for p in parts[1:]) + parts[0][i] if len(parts) > 1 else parts[0][i] for i in range(3))
+        o = [outs[k] for k in sorted(outs)]
+        return (o[0] if len(o) == 1 else torch.cat(o)), grads
 
     def barrier():
         if world > 1:
@@ -765,6 +795,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="sequences per GPU (default: the workload's)")
     ap.add_argument("--chunk", type=int, default=0, help="spans per launch group (0 = library default)")
+    ap.add_argument("--streams", type=int, default=1, help="experiment: deal the micro-batches over this many launch streams")
     ap.add_argument("--micro", type=int, default=0, help="sequences per micro-batch (default: the workload's)")
     ap.add_argument("--no-secondary", action="store_true", help="N > 1: skip the C5 line under `secondary`")
     ap.add_argument("--profile-all", action="store_true", help="bracket the kernels of EVERY timed step with events (default: the last one)")
