@@ -45,6 +45,9 @@ WORKLOADS = {
     # configs[3]: continuous RBN, multivariate-normal transitions (separate code path: run_gauss)
     "c4": dict(D=8, L=64, B=256, outside=True, gauss=True,
                name="Gaussian RBN D=8 L=64 batch 256/GPU, inside marginal likelihood + gradient (BASELINE configs[3])"),
+    # the same with float32 charts (the reference's default dtype; csrc/gauss_kernels.cu, RBN_GAUSS_F32)
+    "c4f32": dict(D=8, L=64, B=256, outside=True, gauss=True, f32=True,
+                  name="Gaussian RBN D=8 L=64 batch 256/GPU, inside marginal likelihood + gradient, float32 charts (BASELINE configs[3] at the reference's default dtype)"),
     "tiny": dict(N=64, V=32, L=16, B=8, outside=True, name="tiny self-test"),
 }
 
@@ -655,7 +658,7 @@ def finish_ours(args, wl):
     line = run_ours(args, wl)
     if world == 1 and args.workload == "c3" and not args.no_secondary and not args.batch and line is not None:
         others = {}
-        for name in ("c1", "c2", "c4"):          # never let a side measurement take the headline line down with it
+        for name in ("c1", "c2", "c4", "c4f32"):          # never let a side measurement take the headline line down with it
             try:
                 r = run_gauss(args, WORKLOADS[name], ret=True) if WORKLOADS[name].get("gauss") else run_ours(args, WORKLOADS[name], secondary=True)
                 if r is not None:
@@ -677,10 +680,10 @@ def finish_ours(args, wl):
 
 
 def run_gauss(args, wl, ret=False):
-    """BASELINE configs[3]: fp64 Gaussian chart pass (csrc/gauss_kernels.cu).  HBM roofline per SURVEY.md 8(d): per cell
-    4 (1 + D + D^2) bytes at the reference's fp32 = 292 B (this build stores fp64: 584 B); a pass re-reads two child
-    cells per split, 2 (L^3 - L)/6 cells per sequence; inside + outside = forward reads + backward reads and adjoint
-    read-modify-writes of the same cells (3x)."""
+    """BASELINE configs[3]: Gaussian chart pass (csrc/gauss_kernels.cu), fp64 charts (584 B per cell; the parity-pinned
+    mode) or, for wl["f32"], float32 charts (296 B per cell: SURVEY.md 8(d)'s 292 B at the reference's fp32 plus the fp64
+    log weight).  HBM roofline per SURVEY.md 8(d): a pass re-reads two child cells per split, 2 (L^3 - L)/6 cells per
+    sequence; inside + outside = forward reads + backward reads and adjoint read-modify-writes of the same cells (3x)."""
     import numpy as np
     import torch
     from rbn_b200 import synth
@@ -699,11 +702,14 @@ def run_gauss(args, wl, ret=False):
     steps_g, warm_g = (5, 3) if ret else (args.steps, args.warmup)
     syn = synth.synthetic_gauss(D, B, L, seed=10 + rank)
     y_np = syn["y"]
+    f32 = bool(wl.get("f32"))
+    ydt = torch.float32 if f32 else torch.float64
     model = GaussianRBN(D, cov_term=syn["cov_term"], cov_left=syn["cov_left"], cov_right=syn["cov_right"],
-                        prior_mean=syn["prior_mean"], prior_cov=syn["prior_cov"], struct_weights=(0.4, 0.6)).to(dev)
+                        prior_mean=syn["prior_mean"], prior_cov=syn["prior_cov"], struct_weights=(0.4, 0.6),
+                        chart_dtype=ydt).to(dev)
     params = list(model.parameters())
-    y_d = torch.tensor(y_np, dtype=torch.float64, device=dev)
-    y_pin = torch.tensor(y_np, dtype=torch.float64).pin_memory()
+    y_d = torch.tensor(y_np, dtype=ydt, device=dev)
+    y_pin = torch.tensor(y_np, dtype=ydt).pin_memory()
 
     def step(y):
         for p in params:
@@ -744,7 +750,7 @@ def run_gauss(args, wl, ret=False):
     if rank != 0:
         return
     peaks = load_peaks()
-    cell_bytes = 8 * (1 + D + D * D)
+    cell_bytes = 4 * (2 + D + D * D) if f32 else 8 * (1 + D + D * D)
     splits = (L ** 3 - L) // 6
     alg_bytes = 3.0 * B * 2 * splits * cell_bytes             # child-cell reads fwd + bwd + adjoint updates
     diag_ms = prof["simt_inside"][0] + prof["simt_outside"][0]      # k_gauss_diag + k_gauss_bwd_diag
@@ -766,10 +772,12 @@ def run_gauss(args, wl, ret=False):
                    sample=f"{n_cpu} sequences of the same workload, fp64 torch restatement on rbnet.multivariate_normal's algebra, {dt:.1f}s")
     line = dict(metric="inside+gradient sequences/sec", value=world * B / (ms_step * 1e-3), unit="seq/s", n_gpus=world,
                 steps=steps_g, warmup=warm_g, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="f64", data="synthetic",
+                vs_baseline=None, dtype="f32" if f32 else "f64", data="synthetic",
                 config=workload_config(wl, B, world),
-                impl_notes=dict(l2="chart (80 MB) fits L2: latency-bound launch train, no flush"),
-                e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="seq/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(y_pin.numel() * 8),
+                impl_notes=dict(l2=f"chart + adjoint chart ({2 * B * (L * (L + 1) // 2) * cell_bytes / 1e6:.0f} MB) are larger than L2",
+                                log_weights="fp64 in both modes"),
+                e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="seq/s", ms_per_step=ms_e2e,
+                         h2d_bytes_per_step=int(y_pin.numel() * y_pin.element_size()),
                          d2h_bytes_per_step=8),
                 gpu_launches=int(sum(v[1] for v in prof.values())),
                 roofline=dict(bound="hbm", kernel="k_gauss_diag / k_gauss_bwd_diag (per-diagonal cell pass)", achieved=ach,

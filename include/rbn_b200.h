@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define RBN_ABI_VERSION 2
+#define RBN_ABI_VERSION 3
 
 /* error codes */
 #define RBN_OK            0
@@ -165,7 +165,13 @@ int rbn_lognormalize_f64(double* log_p, int64_t group_size, int64_t groups, int3
  * of a span are moment-matched as ApproximateMixture does (:502-550); prior N(x; prior_mean, prior_cov).  The
  * reference ships only these primitives, not the RBN bricks; the composition is the one of
  * oracle/gauss_oracle.py.  All arrays float64 on the device; y [B][L][D]; covariances [D][D] row-major symmetric;
- * log_struct[2] = {log p_S(terminal), log p_S(binary)}; D in {1,2,3,4,8}. */
+ * log_struct[2] = {log p_S(terminal), log p_S(binary)}; D in {1,2,3,4,8}.
+ *
+ * flags: RBN_GAUSS_F32 (ABI 3, D = 8 only) selects the _f32 entry points below: observations, the chart, the adjoint
+ * chart and g_y are float32 -- the reference's default dtype (torch.get_default_dtype(), multivariate_normal.py:150) --
+ * and the per-split algebra runs in fp32; the log weights (log c per cell), log Z, every parameter and every parameter
+ * gradient stay float64.  A descriptor and the entry point it is passed to must agree (RBN_E_BADARG otherwise). */
+#define RBN_GAUSS_F32 1
 typedef struct RbnGaussDesc {
     int32_t D, B, L, flags;
 } RbnGaussDesc;
@@ -184,6 +190,18 @@ int rbn_gauss_inside_backward(const RbnGaussDesc* desc, const double* y, const i
                               const double* coef, double* g_y, double* g_cov_term, double* g_cov_left,
                               double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
                               void* stream);
+/* The same two passes over float32 observations / charts (desc->flags & RBN_GAUSS_F32; workspace sized by
+ * rbn_gauss_workspace_bytes for that descriptor: 2 x B x L(L+1)/2 cells of 296 B). */
+int rbn_gauss_inside_forward_f32(const RbnGaussDesc* desc, const float* y, const int32_t* lengths, const double* cov_term,
+                                 const double* cov_left, const double* cov_right, const double* prior_mean,
+                                 const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
+                                 double* logZ, void* stream);
+int rbn_gauss_inside_backward_f32(const RbnGaussDesc* desc, const float* y, const int32_t* lengths, const double* cov_term,
+                                  const double* cov_left, const double* cov_right, const double* prior_mean,
+                                  const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
+                                  const double* coef, float* g_y, double* g_cov_term, double* g_cov_left,
+                                  double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
+                                  void* stream);
 
 /* Launch accounting and optional per-kernel timing.  The library counts every kernel it launches, by class; with
  * rbn_profile_enable(1) it also brackets each launch with CUDA events on the caller's stream.  rbn_profile_read

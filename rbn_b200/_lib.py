@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librbn_b200.so")
 
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
-ABI_VERSION = 2          # RBN_ABI_VERSION of include/rbn_b200.h this binding was written against
+GAUSS_F32 = 1            # RbnGaussDesc.flags: float32 observations / charts (the _f32 entry points)
+ABI_VERSION = 3          # RBN_ABI_VERSION of include/rbn_b200.h this binding was written against
 KERNEL_CLASSES = ["emission", "split_sum", "rule_gemm", "gy_gemm", "count_gemm", "child_grad", "grad_prep",
                   "simt_inside", "simt_outside", "other", "rule_finalize"]
 
@@ -53,6 +54,9 @@ _SIGNATURES = {
     "rbn_gauss_inside_forward": (ctypes.c_int, [ctypes.POINTER(GaussDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                                 ctypes.c_size_t, _P, _P]),
     "rbn_gauss_inside_backward": (ctypes.c_int, [ctypes.POINTER(GaussDesc)] + [_P] * 9 + [ctypes.c_size_t] + [_P] * 9),
+    "rbn_gauss_inside_forward_f32": (ctypes.c_int, [ctypes.POINTER(GaussDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                                    ctypes.c_size_t, _P, _P]),
+    "rbn_gauss_inside_backward_f32": (ctypes.c_int, [ctypes.POINTER(GaussDesc)] + [_P] * 9 + [ctypes.c_size_t] + [_P] * 9),
     "rbn_profile_enable": (ctypes.c_int, [ctypes.c_int32]),
     "rbn_profile_read": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
     "rbn_debug_gemm": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_int32,

@@ -28,7 +28,11 @@ int tc_forward(const RbnDesc*, const WsLayout&, char*, const float*, const float
 int tc_backward(const RbnDesc*, const WsLayout&, char*, const float*, const float*, const float*, const int*,
                 const int*, const float*, float*, float*, float*, const int*, cudaStream_t);
 int debug_gemm(int, int, int, const __half*, const __half*, float*, int, int, int, cudaStream_t);
-size_t gauss_workspace_bytes(int, int, int);
+size_t gauss_workspace_bytes(int, int, int, int);
+int gauss_backward_f32(int, int, int, const int*, const double*, const double*, const double*, const double*, const double*, const float*,
+                       float*, const double*, float*, double*, double*, double*, double*, double*, double*, cudaStream_t);
+int gauss_forward_f32(int, int, int, const float*, const int*, const double*, const double*, const double*, const double*,
+                      const double*, const double*, float*, double*, cudaStream_t);
 int gauss_backward(int, int, int, const int*, const double*, const double*, const double*, const double*, const double*, const double*,
                    double*, const double*, double*, double*, double*, double*, double*, double*, double*, cudaStream_t);
 int gauss_forward(int, int, int, const double*, const int*, const double*, const double*, const double*, const double*,
@@ -310,8 +314,21 @@ int rbn_debug_gemm(int32_t M, int32_t N, int32_t K, const void* A, const void* B
 }
 
 static bool gdesc_ok(const RbnGaussDesc* d) {
-    if (!d || d->D < 1 || d->D > 8 || d->B < 1 || d->L < 1 || d->flags != 0) {
+    if (!d || d->D < 1 || d->D > 8 || d->B < 1 || d->L < 1 || (d->flags & ~RBN_GAUSS_F32) != 0) {
         set_error("bad Gaussian descriptor");
+        return false;
+    }
+    if ((d->flags & RBN_GAUSS_F32) && d->D != 8) {
+        set_error("RBN_GAUSS_F32 (fp32 chart storage) is instantiated for D = 8 (got %d)", d->D);
+        return false;
+    }
+    return true;
+}
+// the plain entry points take fp64 charts, the _f32 ones fp32 charts: the descriptor has to say the same
+static bool gdesc_entry_ok(const RbnGaussDesc* d, int f32, const char* fn) {
+    if (!gdesc_ok(d)) return false;
+    if (((d->flags & RBN_GAUSS_F32) != 0) != (f32 != 0)) {
+        set_error("%s: RbnGaussDesc.flags %s RBN_GAUSS_F32", fn, f32 ? "must carry" : "must not carry");
         return false;
     }
     return true;
@@ -319,14 +336,14 @@ static bool gdesc_ok(const RbnGaussDesc* d) {
 
 size_t rbn_gauss_workspace_bytes(const RbnGaussDesc* desc) {
     if (!gdesc_ok(desc)) return 0;
-    return 2 * gauss_workspace_bytes(desc->D, desc->B, desc->L);     // chart + adjoint chart
+    return 2 * gauss_workspace_bytes(desc->D, desc->B, desc->L, desc->flags & RBN_GAUSS_F32);     // chart + adjoint chart
 }
 
 int rbn_gauss_inside_forward(const RbnGaussDesc* desc, const double* y, const int32_t* lengths, const double* cov_term,
                              const double* cov_left, const double* cov_right, const double* prior_mean,
                              const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
                              double* logZ, void* stream) {
-    if (!gdesc_ok(desc)) return RBN_E_BADARG;
+    if (!gdesc_entry_ok(desc, 0, "rbn_gauss_inside_forward")) return RBN_E_BADARG;
     if (!y || !lengths || !cov_term || !cov_left || !cov_right || !prior_mean || !prior_cov || !log_struct || !workspace || !logZ) {
         set_error("rbn_gauss_inside_forward: NULL pointer argument");
         return RBN_E_BADARG;
@@ -346,7 +363,7 @@ int rbn_gauss_inside_backward(const RbnGaussDesc* desc, const double* y, const i
                               double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
                               void* stream) {
     (void)y; (void)cov_term;
-    if (!gdesc_ok(desc)) return RBN_E_BADARG;
+    if (!gdesc_entry_ok(desc, 0, "rbn_gauss_inside_backward")) return RBN_E_BADARG;
     if (!lengths || !cov_left || !cov_right || !prior_mean || !prior_cov || !log_struct || !workspace || !coef || !g_y || !g_cov_term ||
         !g_cov_left || !g_cov_right || !g_prior_mean || !g_prior_cov || !g_log_struct) {
         set_error("rbn_gauss_inside_backward: NULL pointer argument");
@@ -357,10 +374,51 @@ int rbn_gauss_inside_backward(const RbnGaussDesc* desc, const double* y, const i
         return RBN_E_WORKSPACE;
     }
     double* chart = (double*)workspace;
-    double* adj = (double*)((char*)workspace + gauss_workspace_bytes(desc->D, desc->B, desc->L));
+    double* adj = (double*)((char*)workspace + gauss_workspace_bytes(desc->D, desc->B, desc->L, 0));
     return gauss_backward(desc->D, desc->B, desc->L, lengths, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, adj, coef,
                           g_y, g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct,
                           (cudaStream_t)stream);
+}
+
+int rbn_gauss_inside_forward_f32(const RbnGaussDesc* desc, const float* y, const int32_t* lengths, const double* cov_term,
+                                 const double* cov_left, const double* cov_right, const double* prior_mean,
+                                 const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
+                                 double* logZ, void* stream) {
+    if (!gdesc_entry_ok(desc, 1, "rbn_gauss_inside_forward_f32")) return RBN_E_BADARG;
+    if (!y || !lengths || !cov_term || !cov_left || !cov_right || !prior_mean || !prior_cov || !log_struct || !workspace || !logZ) {
+        set_error("rbn_gauss_inside_forward_f32: NULL pointer argument");
+        return RBN_E_BADARG;
+    }
+    if (workspace_bytes < rbn_gauss_workspace_bytes(desc)) {
+        set_error("Gaussian workspace too small");
+        return RBN_E_WORKSPACE;
+    }
+    return gauss_forward_f32(desc->D, desc->B, desc->L, y, lengths, cov_term, cov_left, cov_right, prior_mean, prior_cov,
+                             log_struct, (float*)workspace, logZ, (cudaStream_t)stream);
+}
+
+int rbn_gauss_inside_backward_f32(const RbnGaussDesc* desc, const float* y, const int32_t* lengths, const double* cov_term,
+                                  const double* cov_left, const double* cov_right, const double* prior_mean,
+                                  const double* prior_cov, const double* log_struct, void* workspace, size_t workspace_bytes,
+                                  const double* coef, float* g_y, double* g_cov_term, double* g_cov_left,
+                                  double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
+                                  void* stream) {
+    (void)y; (void)cov_term;
+    if (!gdesc_entry_ok(desc, 1, "rbn_gauss_inside_backward_f32")) return RBN_E_BADARG;
+    if (!lengths || !cov_left || !cov_right || !prior_mean || !prior_cov || !log_struct || !workspace || !coef || !g_y || !g_cov_term ||
+        !g_cov_left || !g_cov_right || !g_prior_mean || !g_prior_cov || !g_log_struct) {
+        set_error("rbn_gauss_inside_backward_f32: NULL pointer argument");
+        return RBN_E_BADARG;
+    }
+    if (workspace_bytes < rbn_gauss_workspace_bytes(desc)) {
+        set_error("Gaussian workspace too small");
+        return RBN_E_WORKSPACE;
+    }
+    const float* chart = (const float*)workspace;
+    float* adj = (float*)((char*)workspace + gauss_workspace_bytes(desc->D, desc->B, desc->L, 1));
+    return gauss_backward_f32(desc->D, desc->B, desc->L, lengths, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, adj,
+                              coef, g_y, g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct,
+                              (cudaStream_t)stream);
 }
 
 int rbn_profile_enable(int32_t on) {

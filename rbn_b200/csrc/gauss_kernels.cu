@@ -1,4 +1,5 @@
-// Continuous (multivariate-normal) RBN: inside pass over span diagonals in fp64.
+// Continuous (multivariate-normal) RBN: inside and outside passes over span diagonals, fp64 charts (default, the
+// parity-pinned mode) or, for D = 8, float32 charts with fp64 log weights (RBN_GAUSS_F32: the reference's default dtype).
 //
 // Every chart cell is a scaled Gaussian  beta(x) = exp(logc) * N(x; mu, Sigma)  stored as [logc | mu[D] | Sigma[D][D]].
 // Per split the two children are multiplied as in rbnet.multivariate_normal.PairwiseProduct
@@ -6,23 +7,37 @@
 // are collapsed by moment matching as in ApproximateMixture (multivariate_normal.py:502-550).  The composition is
 // the one of oracle/gauss_oracle.py (the reference has no Gaussian RBN bricks).
 //
-// One CTA per span, one thread per split; D x D (D <= 8) Cholesky factorisations live in registers.  The pass is
-// latency-bound (L-1 dependent diagonals of tiny dense algebra), so it runs in fp64: parity with the fp64 oracle is
-// then limited by summation order only.
+// D <= 4: one CTA per span, one thread per split; D x D Cholesky factorisations live in registers, fp64 (parity with the
+// fp64 oracle is then limited by summation order only).  D = 8: eight lanes per split (namespace g8 below).
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace rbn {
 
-template <int D>
+// Cell layout in units of the storage type T: [log c (ALWAYS one fp64, i.e. kHead slots of T) | mu[D] | Sigma[D][D]].
+// T = double: 1 + D + D^2 doubles (584 B at D = 8).  T = float (D = 8 only): 2 + 8 + 64 floats = 296 B, 8-byte aligned, so
+// the log weight keeps 53 bits while means and covariances are stored (and worked on) in fp32.
+template <int D, typename T = double>
 struct GCell {
-    static constexpr int kStride = 1 + D + D * D;
+    static constexpr int kHead = (int)(sizeof(double) / sizeof(T));
+    static constexpr int kStride = kHead + D + D * D;
 };
+template <typename T> __device__ __forceinline__ double ld_logc(const T* cell) { return *reinterpret_cast<const double*>(cell); }
+template <typename T> __device__ __forceinline__ void st_logc(T* cell, double v) { *reinterpret_cast<double*>(cell) = v; }
+__device__ __forceinline__ float tsqrt(float v) { return sqrtf(v); }
+__device__ __forceinline__ double tsqrt(double v) { return sqrt(v); }
+__device__ __forceinline__ float tlog(float v) { return logf(v); }
+__device__ __forceinline__ double tlog(double v) { return log(v); }
+__device__ __forceinline__ float texp(float v) { return expf(v); }
+__device__ __forceinline__ double texp(double v) { return exp(v); }
 
-// Register budget of the D = 8 row kernels.  Measured (C4, round 2): inside pass 21.3 ms at 252 registers (1-2 CTAs per
+// Register budget of the D = 8 row kernels.  Measured (C4, round 2, fp64): inside pass 21.3 ms at 252 registers (1-2 CTAs per
 // SM), 15.6 ms at 128 (4 CTAs per SM: the kernel is latency-bound, more warps help); outside pass 38.6 ms at 255 registers,
-// 39.1 ms at 168 (spills eat the gain).  Default: inside 128, outside 255.  RBN_GAUSS_OCC=0 / 2 select all-wide / all-narrow.
+// 39.1 ms at 168 (spills eat the gain).  fp32 charts: inside 8.4 / 7.6 / 7.35 ms at 114 / 96 / 80 registers, outside 25.2 / 23.9 /
+// 23.4 ms at 229 / 168 / 128.  Default (RBN_GAUSS_OCC=1): fp64 inside 128, outside 255; fp32 inside 80 (6 CTAs per SM, no
+// spills), outside 128 (4 CTAs per SM, 84 B of spills).  RBN_GAUSS_OCC=0: no cap; 2: the other capped variant (G8Budget).
 static int gauss_occ() {
     const char* e = getenv("RBN_GAUSS_OCC");
     return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
@@ -127,20 +142,18 @@ __device__ __forceinline__ double split_product(const double* __restrict__ l, co
     return lw;
 }
 
-template <int D>
-__global__ void k_gauss_width1(int L, const double* __restrict__ y, const int* __restrict__ lengths,
+template <int D, typename T>
+__global__ void k_gauss_width1(int L, const T* __restrict__ y, const int* __restrict__ lengths,
                                const double* __restrict__ cov_term, const double* __restrict__ log_struct,
-                               double* __restrict__ chart) {
-    constexpr int G = GCell<D>::kStride;
+                               T* __restrict__ chart) {
+    constexpr int H = GCell<D, T>::kHead, G = GCell<D, T>::kStride;
     int b = blockIdx.x / L, i = blockIdx.x % L;
     if (i >= lengths[b]) return;
-    double* cell = chart + ((size_t)b * cells_per_seq(L) + i) * G;
-    for (int t = threadIdx.x; t < G; t += blockDim.x) {
-        double v;
-        if (t == 0) v = log_struct[0];
-        else if (t <= D) v = y[((size_t)b * L + i) * D + (t - 1)];
-        else v = cov_term[t - 1 - D];
-        cell[t] = v;
+    T* cell = chart + ((size_t)b * cells_per_seq(L) + i) * G;
+    for (int t = threadIdx.x; t < 1 + D + D * D; t += blockDim.x) {
+        if (t == 0) st_logc(cell, log_struct[0]);
+        else if (t <= D) cell[H + t - 1] = y[((size_t)b * L + i) * D + (t - 1)];
+        else cell[H + t - 1] = (T)cov_term[t - 1 - D];
     }
 }
 
@@ -244,31 +257,31 @@ namespace g8 {
 static constexpr int D8 = 8;
 static constexpr double kLog2Pi = 1.8378770664093454836;
 
-__device__ __forceinline__ double gshfl(unsigned mask, double v, int src) { return __shfl_sync(mask, v, src, 8); }
-__device__ __forceinline__ double gsum(unsigned mask, double v) {
+template <typename T> __device__ __forceinline__ T gshfl(unsigned mask, T v, int src) { return __shfl_sync(mask, v, src, 8); }
+template <typename T> __device__ __forceinline__ T gsum(unsigned mask, T v) {
     v += __shfl_xor_sync(mask, v, 1, 8);
     v += __shfl_xor_sync(mask, v, 2, 8);
     v += __shfl_xor_sync(mask, v, 4, 8);
     return v;
 }
 // element r (lane-dependent) of a register array
-__device__ __forceinline__ double sel8(const double (&v)[8], int r) {
-    double x = v[0];
+template <typename T> __device__ __forceinline__ T sel8(const T (&v)[8], int r) {
+    T x = v[0];
 #pragma unroll
     for (int k = 1; k < 8; ++k) x = (r == k) ? v[k] : x;
     return x;
 }
 
 // In place: row r of the symmetric S -> row r of its lower Cholesky factor (entries k <= r).  Returns L[r][r].
-__device__ __forceinline__ double chol_rows(unsigned mask, int r, double (&s)[8]) {
-    double mydiag = 1.0;
+template <typename T> __device__ __forceinline__ T chol_rows(unsigned mask, int r, T (&s)[8]) {
+    T mydiag = T(1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        double t = s[j];
+        T t = s[j];
 #pragma unroll
         for (int k = 0; k < j; ++k) t -= s[k] * s[k];
-        const double ljj = gshfl(mask, sqrt(t), j);            // lane j's value is the meaningful one
-        double acc = s[j];
+        const T ljj = gshfl(mask, tsqrt(t), j);               // lane j's value is the meaningful one
+        T acc = s[j];
 #pragma unroll
         for (int k = 0; k < j; ++k) acc -= s[k] * gshfl(mask, s[k], j);
         if (r > j) s[j] = acc / ljj;
@@ -279,8 +292,9 @@ __device__ __forceinline__ double chol_rows(unsigned mask, int r, double (&s)[8]
 
 // Forward substitution L Y = X for 8 right-hand-side columns and one extra vector: lane r holds row r of X in x[] and
 // entry r of the vector in xv; on return row r of L^-1 X and entry r of L^-1 v.
-__device__ __forceinline__ void fwd_subst(unsigned mask, int r, const double (&s)[8], double mydiag, double (&x)[8], double& xv) {
-    const double inv = 1.0 / mydiag;
+template <typename T>
+__device__ __forceinline__ void fwd_subst(unsigned mask, int r, const T (&s)[8], T mydiag, T (&x)[8], T& xv) {
+    const T inv = T(1) / mydiag;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (r == k) {
@@ -288,22 +302,25 @@ __device__ __forceinline__ void fwd_subst(unsigned mask, int r, const double (&s
             for (int c = 0; c < 8; ++c) x[c] *= inv;
             xv *= inv;
         }
-        const double lrk = s[k];                                // L[r][k] (meaningful for r > k)
+        const T lrk = s[k];                                     // L[r][k] (meaningful for r > k)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const double yk = gshfl(mask, x[c], k);
+            const T yk = gshfl(mask, x[c], k);
             if (r > k) x[c] -= lrk * yk;
         }
-        const double yv = gshfl(mask, xv, k);
+        const T yv = gshfl(mask, xv, k);
         if (r > k) xv -= lrk * yv;
     }
 }
 
-template <int MINB>      // CTAs per SM the register budget is cut for
+// T = storage and working type of means / covariances (double, or float = the reference's default dtype); log weights
+// are fp64 in both (they reach -1e3 at L = 64: a float there is 6e-5 coarse, which the softmax over splits turns into a
+// 6e-5 relative error per level).
+template <typename T, int MINB>      // MINB: CTAs per SM the register budget is cut for
 __global__ void __launch_bounds__(128, MINB)
 k_gauss_diag8(int L, int w, int B, const int* __restrict__ lengths, const double* __restrict__ cov_left,
-              const double* __restrict__ cov_right, const double* __restrict__ log_struct, double* __restrict__ chart) {
-    constexpr int G = 1 + D8 + D8 * D8;
+              const double* __restrict__ cov_right, const double* __restrict__ log_struct, T* __restrict__ chart) {
+    constexpr int H = GCell<D8, T>::kHead, G = GCell<D8, T>::kStride;
     const int nI = L - w + 1;
     const int span = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (span >= B * nI) return;
@@ -311,55 +328,56 @@ k_gauss_diag8(int L, int w, int B, const int* __restrict__ lengths, const double
     if (i + w > lengths[b]) return;
     const int lane = threadIdx.x & 31, g = lane >> 3, r = lane & 7;
     const unsigned mask = 0xFFu << (lane & 24);
-    const double* seq = chart + (size_t)b * cells_per_seq(L) * G;
-    double cl[8], cr[8];
+    const T* seq = chart + (size_t)b * cells_per_seq(L) * G;
+    T cl[8], cr[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { cl[c] = cov_left[r * 8 + c]; cr[c] = cov_right[r * 8 + c]; }
+    for (int c = 0; c < 8; ++c) { cl[c] = (T)cov_left[r * 8 + c]; cr[c] = (T)cov_right[r * 8 + c]; }
     // running moment-matching state of this group: max log weight, sum of weights, first moment (entry r), second moment (row r)
-    double mx = -INFINITY, se = 0.0, a1 = 0.0, a2[8];
+    double mx = -INFINITY;
+    T se = T(0), a1 = T(0), a2[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a2[c] = 0.0;
+    for (int c = 0; c < 8; ++c) a2[c] = T(0);
     for (int u = 1 + g; u < w; u += 4) {
-        const double* lc = seq + (size_t)(cell_off(u, L) + i) * G;
-        const double* rc = seq + (size_t)(cell_off(w - u, L) + i + u) * G;
-        double A[8], s[8], x[8];
-        const double mul = lc[1 + r];
-        double dv = rc[1 + r] - mul;
+        const T* lc = seq + (size_t)(cell_off(u, L) + i) * G;
+        const T* rc = seq + (size_t)(cell_off(w - u, L) + i + u) * G;
+        T A[8], s[8], x[8];
+        const T mul = lc[H + r];
+        T dv = rc[H + r] - mul;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            A[c] = lc[1 + D8 + r * 8 + c] + cl[c];
-            s[c] = A[c] + rc[1 + D8 + r * 8 + c] + cr[c];
+            A[c] = lc[H + D8 + r * 8 + c] + cl[c];
+            s[c] = A[c] + rc[H + D8 + r * 8 + c] + cr[c];
             x[c] = A[c];
         }
-        const double diag = chol_rows(mask, r, s);
+        const T diag = chol_rows(mask, r, s);
         fwd_subst(mask, r, s, diag, x, dv);                     // x = row r of Y = L^-1 A, dv = (L^-1 d)[r]
-        const double quad = gsum(mask, dv * dv);
-        const double logdet = 2.0 * gsum(mask, log(diag));
-        const double lw = lc[0] + rc[0] - 0.5 * (quad + logdet + D8 * kLog2Pi);
+        const T quad = gsum(mask, dv * dv);
+        const T logdet = T(2) * gsum(mask, tlog(diag));
+        const double lw = ld_logc(lc) + ld_logc(rc) - 0.5 * ((double)quad + (double)logdet + D8 * kLog2Pi);
         // cov = A - Y^T Y (row r), mean = mu_l + Y^T (L^-1 d) (entry r)
-        double C[8], m = mul;
+        T C[8], m = mul;
 #pragma unroll
         for (int c = 0; c < 8; ++c) C[c] = A[c];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            double yk[8];
+            T yk[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) yk[c] = gshfl(mask, x[c], k);
-            const double ya = sel8(yk, r);                       // Y[k][r]
-            const double dk = gshfl(mask, dv, k);
+            const T ya = sel8(yk, r);                            // Y[k][r]
+            const T dk = gshfl(mask, dv, k);
 #pragma unroll
             for (int c = 0; c < 8; ++c) C[c] -= ya * yk[c];
             m += ya * dk;
         }
         // online moment matching
         const double nmx = fmax(mx, lw);
-        const double sc = (mx == -INFINITY) ? 0.0 : exp(mx - nmx);
-        const double wt = exp(lw - nmx);
+        const T sc = (mx == -INFINITY) ? T(0) : texp((T)(mx - nmx));
+        const T wt = texp((T)(lw - nmx));
         se = se * sc + wt;
         a1 = a1 * sc + wt * m;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const double mc = gshfl(mask, m, c);
+            const T mc = gshfl(mask, m, c);
             a2[c] = a2[c] * sc + wt * (C[c] + m * mc);
         }
         mx = nmx;
@@ -368,51 +386,51 @@ k_gauss_diag8(int L, int w, int B, const int* __restrict__ lengths, const double
 #pragma unroll
     for (int o = 8; o <= 16; o <<= 1) {
         const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
-        const double ose = __shfl_xor_sync(0xffffffffu, se, o);
-        const double oa1 = __shfl_xor_sync(0xffffffffu, a1, o);
+        const T ose = __shfl_xor_sync(0xffffffffu, se, o);
+        const T oa1 = __shfl_xor_sync(0xffffffffu, a1, o);
         const double nmx = fmax(mx, omx);
-        const double s0 = (mx == -INFINITY) ? 0.0 : exp(mx - nmx), s1 = (omx == -INFINITY) ? 0.0 : exp(omx - nmx);
+        const T s0 = (mx == -INFINITY) ? T(0) : texp((T)(mx - nmx)), s1 = (omx == -INFINITY) ? T(0) : texp((T)(omx - nmx));
         se = se * s0 + ose * s1;
         a1 = a1 * s0 + oa1 * s1;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const double oa = __shfl_xor_sync(0xffffffffu, a2[c], o);
+            const T oa = __shfl_xor_sync(0xffffffffu, a2[c], o);
             a2[c] = a2[c] * s0 + oa * s1;
         }
         mx = nmx;
     }
-    const double log_norm = mx + log(se);
-    const double inv = 1.0 / se;
-    const double mean = a1 * inv;
-    double* out = chart + ((size_t)b * cells_per_seq(L) + cell_off(w, L) + i) * G;
+    const double log_norm = mx + log((double)se);
+    const T inv = T(1) / se;
+    const T mean = a1 * inv;
+    T* out = chart + ((size_t)b * cells_per_seq(L) + cell_off(w, L) + i) * G;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const double mc = __shfl_sync(0xffffffffu, mean, c, 8);
-        if (g == 0) out[1 + D8 + r * 8 + c] = a2[c] * inv - mean * mc;
+        const T mc = __shfl_sync(0xffffffffu, mean, c, 8);
+        if (g == 0) out[H + D8 + r * 8 + c] = a2[c] * inv - mean * mc;
     }
     if (g == 0) {
-        out[1 + r] = mean;
-        if (r == 0) out[0] = log_norm + log_struct[1];
+        out[H + r] = mean;
+        if (r == 0) st_logc(out, log_norm + log_struct[1]);
     }
 }
 
 }  // namespace g8
 
-template <int D>
+template <int D, typename T>
 __global__ void k_gauss_root(int L, int B, const int* __restrict__ lengths, const double* __restrict__ prior_mean,
-                             const double* __restrict__ prior_cov, const double* __restrict__ chart,
+                             const double* __restrict__ prior_cov, const T* __restrict__ chart,
                              double* __restrict__ logZ) {
-    constexpr int G = GCell<D>::kStride;
+    constexpr int H = GCell<D, T>::kHead, G = GCell<D, T>::kStride;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int n = lengths[b];
-    const double* cell = chart + ((size_t)b * cells_per_seq(L) + cell_off(n, L)) * G;
+    const T* cell = chart + ((size_t)b * cells_per_seq(L) + cell_off(n, L)) * G;
     double S[D][D], d[D];
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        d[a] = cell[1 + a] - prior_mean[a];
+        d[a] = (double)cell[H + a] - prior_mean[a];
 #pragma unroll
-        for (int c = 0; c < D; ++c) S[a][c] = cell[1 + D + a * D + c] + prior_cov[a * D + c];
+        for (int c = 0; c < D; ++c) S[a][c] = (double)cell[H + D + a * D + c] + prior_cov[a * D + c];
     }
     const double logdet = chol_inplace<D>(S);
     double z[D];
@@ -422,42 +440,53 @@ __global__ void k_gauss_root(int L, int B, const int* __restrict__ lengths, cons
     double quad = 0.0;
 #pragma unroll
     for (int a = 0; a < D; ++a) quad += d[a] * z[a];
-    logZ[b] = cell[0] - 0.5 * (quad + logdet + D * 1.8378770664093454836);
+    logZ[b] = ld_logc(cell) - 0.5 * (quad + logdet + D * 1.8378770664093454836);
 }
 
-template <int D>
-static int gauss_forward_t(int B, int L, const double* y, const int* lengths, const double* cov_term,
+// Register budgets of the D = 8 row kernels per storage type (see gauss_occ()).
+template <typename T> struct G8Budget;
+// kFwd / kBwd: CTAs per SM of the default budget; kFwd2 / kBwd2: of the narrow one (RBN_GAUSS_OCC=2).
+template <> struct G8Budget<double> { static constexpr int kFwd = 4, kFwd2 = 4, kBwd = 1, kBwd2 = 3; };
+template <> struct G8Budget<float> { static constexpr int kFwd = 6, kFwd2 = 5, kBwd = 4, kBwd2 = 3; };
+
+template <int D, typename T>
+static int gauss_forward_t(int B, int L, const T* y, const int* lengths, const double* cov_term,
                            const double* cov_left, const double* cov_right, const double* prior_mean,
-                           const double* prior_cov, const double* log_struct, double* chart, double* logZ,
+                           const double* prior_cov, const double* log_struct, T* chart, double* logZ,
                            cudaStream_t st) {
-    { ProfScope ps(KC_EMISSION, st); k_gauss_width1<D><<<B * L, 96, 0, st>>>(L, y, lengths, cov_term, log_struct, chart); }
+    constexpr bool kF64 = std::is_same<T, double>::value;
+    { ProfScope ps(KC_EMISSION, st); k_gauss_width1<D, T><<<B * L, 96, 0, st>>>(L, y, lengths, cov_term, log_struct, chart); }
     RBN_LAUNCH_CHECK("k_gauss_width1");
-    size_t smem = ((size_t)L + D + 3 * D * D) * sizeof(double);
     static const bool rows8 = gauss_rows8();
     for (int w = 2; w <= L; ++w) {
         { ProfScope ps(KC_SIMT_INSIDE, st);
-          if (D == 8 && rows8) {
+          if (D == 8 && (rows8 || !kF64)) {
               static const int occ = gauss_occ();
-              if (occ >= 1) g8::k_gauss_diag8<4><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
-              else g8::k_gauss_diag8<1><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
-          }
-          else
-              k_gauss_diag<D><<<B * (L - w + 1), 64, smem, st>>>(L, w, lengths, cov_left, cov_right, log_struct, chart); }
+              const int grid = (B * (L - w + 1) + 3) / 4;
+              if (occ >= 2) g8::k_gauss_diag8<T, G8Budget<T>::kFwd2><<<grid, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
+              else if (occ == 1) g8::k_gauss_diag8<T, G8Budget<T>::kFwd><<<grid, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
+              else g8::k_gauss_diag8<T, 1><<<grid, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart);
+          } else if constexpr (kF64) {
+              const size_t smem = ((size_t)L + D + 3 * D * D) * sizeof(double);
+              k_gauss_diag<D><<<B * (L - w + 1), 64, smem, st>>>(L, w, lengths, cov_left, cov_right, log_struct, chart);
+          } }
         RBN_LAUNCH_CHECK("k_gauss_diag");
     }
-    { ProfScope ps(KC_OTHER, st); k_gauss_root<D><<<(B + 63) / 64, 64, 0, st>>>(L, B, lengths, prior_mean, prior_cov, chart, logZ); }
+    { ProfScope ps(KC_OTHER, st); k_gauss_root<D, T><<<(B + 63) / 64, 64, 0, st>>>(L, B, lengths, prior_mean, prior_cov, chart, logZ); }
     RBN_LAUNCH_CHECK("k_gauss_root");
     return RBN_OK;
 }
 
-size_t gauss_workspace_bytes(int D, int B, int L) {
-    return align_up((size_t)B * cells_per_seq(L) * (1 + D + D * D) * sizeof(double), 1024);
+// bytes of ONE chart (the adjoint chart has the same layout); f32 != 0: fp32 storage (D = 8 only)
+size_t gauss_workspace_bytes(int D, int B, int L, int f32) {
+    const size_t cell = f32 ? (size_t)(2 + D + D * D) * sizeof(float) : (size_t)(1 + D + D * D) * sizeof(double);
+    return align_up((size_t)B * cells_per_seq(L) * cell, 1024);
 }
 
 int gauss_forward(int D, int B, int L, const double* y, const int* lengths, const double* cov_term,
                   const double* cov_left, const double* cov_right, const double* prior_mean, const double* prior_cov,
                   const double* log_struct, double* chart, double* logZ, cudaStream_t st) {
-#define RBN_G(DD) case DD: return gauss_forward_t<DD>(B, L, y, lengths, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, logZ, st)
+#define RBN_G(DD) case DD: return gauss_forward_t<DD, double>(B, L, y, lengths, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, logZ, st)
     switch (D) {
         RBN_G(1); RBN_G(2); RBN_G(3); RBN_G(4); RBN_G(8);
         default:
@@ -465,6 +494,16 @@ int gauss_forward(int D, int B, int L, const double* y, const int* lengths, cons
             return RBN_E_UNSUPPORTED;
     }
 #undef RBN_G
+}
+
+int gauss_forward_f32(int D, int B, int L, const float* y, const int* lengths, const double* cov_term,
+                      const double* cov_left, const double* cov_right, const double* prior_mean, const double* prior_cov,
+                      const double* log_struct, float* chart, double* logZ, cudaStream_t st) {
+    if (D != 8) {
+        set_error("fp32 chart storage is instantiated for D = 8 (got %d); other D run through the fp64 entry points", D);
+        return RBN_E_UNSUPPORTED;
+    }
+    return gauss_forward_t<8, float>(B, L, y, lengths, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, logZ, st);
 }
 
 }  // namespace rbn
@@ -478,34 +517,34 @@ namespace rbn {
 
 #define SMAT(M, r, c) M[(r) * D + (c)]
 
-template <int D>
+template <int D, typename T>
 __global__ void k_gauss_bwd_root(int L, int B, const int* __restrict__ lengths, const double* __restrict__ prior_mean,
-                                 const double* __restrict__ prior_cov, const double* __restrict__ chart,
-                                 const double* __restrict__ coef, double* __restrict__ adj,
+                                 const double* __restrict__ prior_cov, const T* __restrict__ chart,
+                                 const double* __restrict__ coef, T* __restrict__ adj,
                                  double* __restrict__ g_prior_mean, double* __restrict__ g_prior_cov) {
-    constexpr int G = GCell<D>::kStride;
+    constexpr int H = GCell<D, T>::kHead, G = GCell<D, T>::kStride;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double c = coef[b];
     if (c == 0.0) return;
     const int n = lengths[b];
     const size_t cidx = (size_t)b * cells_per_seq(L) + cell_off(n, L);
-    const double* cell = chart + cidx * G;
-    double* out = adj + cidx * G;
+    const T* cell = chart + cidx * G;
+    T* out = adj + cidx * G;
     double S[D][D], d[D], z[D];
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        d[a] = cell[1 + a] - prior_mean[a];
+        d[a] = (double)cell[H + a] - prior_mean[a];
         z[a] = d[a];
 #pragma unroll
-        for (int e = 0; e < D; ++e) S[a][e] = cell[1 + D + a * D + e] + prior_cov[a * D + e];
+        for (int e = 0; e < D; ++e) S[a][e] = (double)cell[H + D + a * D + e] + prior_cov[a * D + e];
     }
     chol_inplace<D>(S);
     chol_solve<D>(S, z);
-    out[0] += c;
+    st_logc(out, ld_logc(out) + c);
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        out[1 + a] += -c * z[a];
+        out[H + a] += (T)(-c * z[a]);
         atomicAdd(&g_prior_mean[a], c * z[a]);
     }
 #pragma unroll
@@ -517,7 +556,7 @@ __global__ void k_gauss_bwd_root(int L, int B, const int* __restrict__ lengths, 
 #pragma unroll
         for (int a = 0; a < D; ++a) {
             const double sb = 0.5 * c * (z[a] * z[e] - x[a]);
-            out[1 + D + a * D + e] += sb;
+            out[H + D + a * D + e] += (T)sb;
             atomicAdd(&g_prior_cov[a * D + e], sb);
         }
     }
@@ -748,13 +787,14 @@ k_gauss_bwd_diag(int L, int w, const int* __restrict__ lengths, const double* __
 // load; gauss_backward_t symmetrises the parameter gradients once at the end).
 namespace g8 {
 
-template <int MINB>
+// Storage type T as in k_gauss_diag8: log weights, the adjoint of log c and every PARAMETER gradient stay fp64.
+template <typename T, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_gauss_bwd_diag8(int L, int w, int B, const int* __restrict__ lengths, const double* __restrict__ cov_left,
                   const double* __restrict__ cov_right, const double* __restrict__ log_struct,
-                  const double* __restrict__ chart, double* __restrict__ adj, double* __restrict__ g_cov_left,
+                  const T* __restrict__ chart, T* __restrict__ adj, double* __restrict__ g_cov_left,
                   double* __restrict__ g_cov_right, double* __restrict__ g_log_struct) {
-    constexpr int G = 1 + D8 + D8 * D8;
+    constexpr int H = GCell<D8, T>::kHead, G = GCell<D8, T>::kStride;
     const int nI = L - w + 1;
     const int span = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (span >= B * nI) return;
@@ -763,146 +803,150 @@ k_gauss_bwd_diag8(int L, int w, int B, const int* __restrict__ lengths, const do
     const int lane = threadIdx.x & 31, g = lane >> 3, r = lane & 7;
     const unsigned mask = 0xFFu << (lane & 24);
     const size_t seq_off = (size_t)b * cells_per_seq(L);
-    const double* seq = chart + seq_off * G;
-    double* aseq = adj + seq_off * G;
+    const T* seq = chart + seq_off * G;
+    T* aseq = adj + seq_off * G;
     const size_t pcell = cell_off(w, L) + i;
-    const double* pa = aseq + pcell * G;
+    const T* pa = aseq + pcell * G;
+    const double abar_d = ld_logc(pa);
     {   // skip spans that no gradient reaches
-        double any = 0.0;
-        for (int t = lane; t < G; t += 32) any += fabs(pa[t]);
+        T any = (lane == 0) ? (T)fabs(abar_d) : T(0);
+        for (int t = H + lane; t < G; t += 32) any += fabs(pa[t]);
         for (int o = 16; o > 0; o >>= 1) any += __shfl_xor_sync(0xffffffffu, any, o);
-        if (any == 0.0) return;
+        if (any == T(0) && abar_d == 0.0) return;
     }
-    const double abar = pa[0];
-    double M2b[8];
+    const T abar = (T)abar_d;
+    T M2b[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) M2b[c] = 0.5 * (pa[1 + D8 + r * 8 + c] + pa[1 + D8 + c * 8 + r]);
-    const double pm = seq[pcell * G + 1 + r];
-    double g1 = pa[1 + r], swo;
+    for (int c = 0; c < 8; ++c) M2b[c] = T(0.5) * (pa[H + D8 + r * 8 + c] + pa[H + D8 + c * 8 + r]);
+    const T pm = seq[pcell * G + H + r];
+    T g1 = pa[H + r], swo;
     {
-        double t = 0.0, q = 0.0;
+        T t = T(0), q = T(0);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const double pmc = gshfl(mask, pm, c);
+            const T pmc = gshfl(mask, pm, c);
             t += M2b[c] * pmc;                                                   // (M2_bar mu_p)[r]
-            q += M2b[c] * seq[pcell * G + 1 + D8 + r * 8 + c];                  // <M2_bar, Sigma_p>, row r
+            q += M2b[c] * seq[pcell * G + H + D8 + r * 8 + c];                  // <M2_bar, Sigma_p>, row r
         }
-        g1 -= 2.0 * t;                                                           // mu_bar_tot = mu_bar - 2 Sigma_bar mu_p
+        g1 -= T(2) * t;                                                          // mu_bar_tot = mu_bar - 2 Sigma_bar mu_p
         swo = gsum(mask, g1 * pm + q + pm * t);
     }
-    const double log_norm = seq[pcell * G] - log_struct[1];
-    if (lane == 0) atomicAdd(&g_log_struct[1], abar);
-    double tL[8], tR[8];
+    const double log_norm = ld_logc(seq + pcell * G) - log_struct[1];
+    if (lane == 0) atomicAdd(&g_log_struct[1], abar_d);
+    T tL[8], tR[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) tL[c] = tR[c] = 0.0;
+    for (int c = 0; c < 8; ++c) tL[c] = tR[c] = T(0);
 
     for (int u = 1 + g; u < w; u += 4) {
         const size_t lcell = cell_off(u, L) + i, rcell = cell_off(w - u, L) + i + u;
-        const double* lc = seq + lcell * G;
-        const double* rc = seq + rcell * G;
-        double A[8], s[8], x[8];
-        const double mul = lc[1 + r];
-        double yd = rc[1 + r] - mul;
+        const T* lc = seq + lcell * G;
+        const T* rc = seq + rcell * G;
+        T A[8], s[8], x[8];
+        const T mul = lc[H + r];
+        T yd = rc[H + r] - mul;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            A[c] = lc[1 + D8 + r * 8 + c] + cov_left[r * 8 + c];
-            s[c] = A[c] + rc[1 + D8 + r * 8 + c] + cov_right[r * 8 + c];
-            x[c] = (c == r) ? 1.0 : 0.0;
+            A[c] = lc[H + D8 + r * 8 + c] + (T)cov_left[r * 8 + c];
+            s[c] = A[c] + rc[H + D8 + r * 8 + c] + (T)cov_right[r * 8 + c];
+            x[c] = (c == r) ? T(1) : T(0);
         }
-        const double diag = chol_rows(mask, r, s);
+        const T diag = chol_rows(mask, r, s);
         fwd_subst(mask, r, s, diag, x, yd);                      // x = row r of W = L^-1, yd = (L^-1 d)[r]
-        const double quad = gsum(mask, yd * yd);
-        const double logdet = 2.0 * gsum(mask, log(diag));
-        const double lw = lc[0] + rc[0] - 0.5 * (quad + logdet + D8 * kLog2Pi);
-        const double om = exp(lw - log_norm);
+        const T quad = gsum(mask, yd * yd);
+        const T logdet = T(2) * gsum(mask, tlog(diag));
+        const double lw = ld_logc(lc) + ld_logc(rc) - 0.5 * ((double)quad + (double)logdet + D8 * kLog2Pi);
+        const T om = texp((T)(lw - log_norm));
         // P = W^T W (row r), z = W^T (L^-1 d) (entry r)
-        double P[8], z = 0.0;
+        T P[8], z = T(0);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) P[c] = 0.0;
+        for (int c = 0; c < 8; ++c) P[c] = T(0);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            double wk[8];
+            T wk[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) wk[c] = gshfl(mask, x[c], k);
-            const double wa = sel8(wk, r);
-            const double ydk = gshfl(mask, yd, k);
+            const T wa = sel8(wk, r);
+            const T ydk = gshfl(mask, yd, k);
 #pragma unroll
             for (int c = 0; c < 8; ++c) P[c] += wa * wk[c];
             z += wa * ydk;
         }
         // K = A P (row r)
-        double K[8];
+        T K[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) K[c] = 0.0;
+        for (int c = 0; c < 8; ++c) K[c] = T(0);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) K[c] += A[k] * gshfl(mask, P[c], k);
         }
-        double zc[8], m = mul;
+        T zc[8], m = mul;
 #pragma unroll
         for (int c = 0; c < 8; ++c) { zc[c] = gshfl(mask, z, c); m += A[c] * zc[c]; }    // m = mu_l + A z
         // Q = M2_bar K (row r)
-        double Q[8];
+        T Q[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) Q[c] = 0.0;
+        for (int c = 0; c < 8; ++c) Q[c] = T(0);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) Q[c] += M2b[k] * gshfl(mask, K[c], k);
         }
-        double t = 0.0, part = 0.0;
+        T t = T(0), part = T(0);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             t += M2b[c] * gshfl(mask, m, c);                                     // (M2_bar m)[r]
             part += (M2b[c] - Q[c]) * A[c];                                      // <M2_bar, C> = <M2_bar - Q, A>
         }
-        const double ob = gsum(mask, g1 * m + part + m * t);
-        const double lwb = om * (ob - swo + abar);
-        const double mb = om * (g1 + 2.0 * t);
+        const T ob = gsum(mask, g1 * m + part + m * t);
+        const T lwb = om * (ob - swo + abar);
+        const T mb = om * (g1 + T(2) * t);
         // K^T Q (row r) and row r of Q^T
-        double KtQ[8], QT[8];
+        T KtQ[8], QT[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) KtQ[c] = 0.0;
+        for (int c = 0; c < 8; ++c) KtQ[c] = T(0);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            double kk[8], qk[8];
+            T kk[8], qk[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) { kk[c] = gshfl(mask, K[c], k); qk[c] = gshfl(mask, Q[c], k); }
-            const double ka = sel8(kk, r);
+            const T ka = sel8(kk, r);
             QT[k] = sel8(qk, r);
 #pragma unroll
             for (int c = 0; c < 8; ++c) KtQ[c] += ka * qk[c];
         }
-        double zb = 0.0, pz = 0.0;
+        T zb = T(0), pz = T(0);
 #pragma unroll
         for (int c = 0; c < 8; ++c) zb += A[c] * gshfl(mask, mb, c);              // z_bar = A m_bar
 #pragma unroll
         for (int c = 0; c < 8; ++c) pz += P[c] * gshfl(mask, zb, c);              // P z_bar
-        const double db = -lwb * z + pz;
-        double* la = aseq + lcell * G;
-        double* ra = aseq + rcell * G;
-        if (r == 0) { atomicAdd(&la[0], lwb); atomicAdd(&ra[0], lwb); }
-        atomicAdd(&la[1 + r], mb - db);
-        atomicAdd(&ra[1 + r], db);
+        const T db = -lwb * z + pz;
+        T* la = aseq + lcell * G;
+        T* ra = aseq + rcell * G;
+        if (r == 0) {
+            atomicAdd(reinterpret_cast<double*>(la), (double)lwb);
+            atomicAdd(reinterpret_cast<double*>(ra), (double)lwb);
+        }
+        atomicAdd(&la[H + r], mb - db);
+        atomicAdd(&ra[H + r], db);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const double sb = 0.5 * lwb * (z * zc[c] - P[c]) - pz * zc[c] + om * KtQ[c];
-            const double ab = mb * zc[c] + om * (M2b[c] - Q[c] - QT[c]) + sb;
-            atomicAdd(&la[1 + D8 + r * 8 + c], ab);
-            atomicAdd(&ra[1 + D8 + r * 8 + c], sb);
+            const T sb = T(0.5) * lwb * (z * zc[c] - P[c]) - pz * zc[c] + om * KtQ[c];
+            const T ab = mb * zc[c] + om * (M2b[c] - Q[c] - QT[c]) + sb;
+            atomicAdd(&la[H + D8 + r * 8 + c], ab);
+            atomicAdd(&ra[H + D8 + r * 8 + c], sb);
             tL[c] += ab;
             tR[c] += sb;
         }
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        double vl = tL[c], vr = tR[c];
+        T vl = tL[c], vr = tR[c];
         vl += __shfl_xor_sync(0xffffffffu, vl, 8);  vr += __shfl_xor_sync(0xffffffffu, vr, 8);
         vl += __shfl_xor_sync(0xffffffffu, vl, 16); vr += __shfl_xor_sync(0xffffffffu, vr, 16);
         if (g == 0) {
-            if (vl != 0.0) atomicAdd(&g_cov_left[r * 8 + c], vl);
-            if (vr != 0.0) atomicAdd(&g_cov_right[r * 8 + c], vr);
+            if (vl != T(0)) atomicAdd(&g_cov_left[r * 8 + c], (double)vl);
+            if (vr != T(0)) atomicAdd(&g_cov_right[r * 8 + c], (double)vr);
         }
     }
 }
@@ -918,36 +962,36 @@ __global__ void k_sym8(double* __restrict__ a, double* __restrict__ b) {
 
 }  // namespace g8
 
-template <int D>
-__global__ void k_gauss_bwd_width1(int L, const int* __restrict__ lengths, const double* __restrict__ adj,
-                                   double* __restrict__ g_y, double* __restrict__ g_cov_term,
+template <int D, typename T>
+__global__ void k_gauss_bwd_width1(int L, const int* __restrict__ lengths, const T* __restrict__ adj,
+                                   T* __restrict__ g_y, double* __restrict__ g_cov_term,
                                    double* __restrict__ g_log_struct) {
-    constexpr int G = GCell<D>::kStride;
+    constexpr int H = GCell<D, T>::kHead, G = GCell<D, T>::kStride;
     int b = blockIdx.x / L, i = blockIdx.x % L;
     if (i >= lengths[b]) return;
-    const double* cell = adj + ((size_t)b * cells_per_seq(L) + i) * G;
-    for (int t = threadIdx.x; t < G; t += blockDim.x) {
-        const double v = cell[t];
-        if (t == 0) { if (v != 0.0) atomicAdd(&g_log_struct[0], v); }
-        else if (t <= D) g_y[((size_t)b * L + i) * D + (t - 1)] = v;
+    const T* cell = adj + ((size_t)b * cells_per_seq(L) + i) * G;
+    for (int t = threadIdx.x; t < 1 + D + D * D; t += blockDim.x) {
+        if (t == 0) { const double v = ld_logc(cell); if (v != 0.0) atomicAdd(&g_log_struct[0], v); }
+        else if (t <= D) g_y[((size_t)b * L + i) * D + (t - 1)] = cell[H + t - 1];
         else {
             const int a = (t - 1 - D) / D, c = (t - 1 - D) % D;
-            const double s = 0.5 * (v + cell[1 + D + c * D + a]);
+            const double s = 0.5 * ((double)cell[H + t - 1] + (double)cell[H + D + c * D + a]);
             if (s != 0.0) atomicAdd(&g_cov_term[a * D + c], s);
         }
     }
 }
 
-template <int D>
+template <int D, typename T>
 static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_left, const double* cov_right,
-                            const double* prior_mean, const double* prior_cov, const double* log_struct, const double* chart, double* adj,
-                            const double* coef, double* g_y, double* g_cov_term, double* g_cov_left,
+                            const double* prior_mean, const double* prior_cov, const double* log_struct, const T* chart, T* adj,
+                            const double* coef, T* g_y, double* g_cov_term, double* g_cov_left,
                             double* g_cov_right, double* g_prior_mean, double* g_prior_cov, double* g_log_struct,
                             cudaStream_t st) {
-    constexpr int G = GCell<D>::kStride;
+    constexpr bool kF64 = std::is_same<T, double>::value;
+    constexpr int G = GCell<D, T>::kStride;
     constexpr int DD = D * D;
-    RBN_CUDA_CHECK(cudaMemsetAsync(adj, 0, (size_t)B * cells_per_seq(L) * G * sizeof(double), st));
-    RBN_CUDA_CHECK(cudaMemsetAsync(g_y, 0, (size_t)B * L * D * sizeof(double), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(adj, 0, (size_t)B * cells_per_seq(L) * G * sizeof(T), st));
+    RBN_CUDA_CHECK(cudaMemsetAsync(g_y, 0, (size_t)B * L * D * sizeof(T), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(g_cov_term, 0, DD * sizeof(double), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(g_cov_left, 0, DD * sizeof(double), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(g_cov_right, 0, DD * sizeof(double), st));
@@ -955,29 +999,36 @@ static int gauss_backward_t(int B, int L, const int* lengths, const double* cov_
     RBN_CUDA_CHECK(cudaMemsetAsync(g_prior_cov, 0, DD * sizeof(double), st));
     RBN_CUDA_CHECK(cudaMemsetAsync(g_log_struct, 0, 2 * sizeof(double), st));
     { ProfScope ps(KC_OTHER, st);
-      k_gauss_bwd_root<D><<<(B + 63) / 64, 64, 0, st>>>(L, B, lengths, prior_mean, prior_cov, chart, coef, adj, g_prior_mean, g_prior_cov); }
+      k_gauss_bwd_root<D, T><<<(B + 63) / 64, 64, 0, st>>>(L, B, lengths, prior_mean, prior_cov, chart, coef, adj, g_prior_mean, g_prior_cov); }
     RBN_LAUNCH_CHECK("k_gauss_bwd_root");
-    size_t smem = ((size_t)2 * L + G + D + 4 * DD) * sizeof(double);
-    RBN_CUDA_CHECK(cudaFuncSetAttribute(k_gauss_bwd_diag<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const bool rows8 = gauss_rows8();
+    const bool use8 = (D == 8) && (rows8 || !kF64);
+    size_t smem = 0;
+    if constexpr (kF64) {
+        smem = ((size_t)2 * L + G + D + 4 * DD) * sizeof(double);
+        RBN_CUDA_CHECK(cudaFuncSetAttribute(k_gauss_bwd_diag<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     for (int w = L; w >= 2; --w) {
         { ProfScope ps(KC_SIMT_OUTSIDE, st);
-          if (D == 8 && rows8) {
+          if (use8) {
               static const int occ = gauss_occ();
-              if (occ >= 2) g8::k_gauss_bwd_diag8<3><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
-                                                                                      g_cov_left, g_cov_right, g_log_struct);
-              else g8::k_gauss_bwd_diag8<1><<<(B * (L - w + 1) + 3) / 4, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
-                                                                                  g_cov_left, g_cov_right, g_log_struct);
-          }
-          else
-              k_gauss_bwd_diag<D><<<B * (L - w + 1), 32, smem, st>>>(L, w, lengths, cov_left, cov_right, chart, adj, g_cov_left, g_cov_right, g_log_struct); }
+              const int grid = (B * (L - w + 1) + 3) / 4;
+              if (occ >= 2) g8::k_gauss_bwd_diag8<T, G8Budget<T>::kBwd2><<<grid, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
+                                                                                   g_cov_left, g_cov_right, g_log_struct);
+              else if (occ == 1) g8::k_gauss_bwd_diag8<T, G8Budget<T>::kBwd><<<grid, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
+                                                                                       g_cov_left, g_cov_right, g_log_struct);
+              else g8::k_gauss_bwd_diag8<T, 1><<<grid, 128, 0, st>>>(L, w, B, lengths, cov_left, cov_right, log_struct, chart, adj,
+                                                                    g_cov_left, g_cov_right, g_log_struct);
+          } else if constexpr (kF64) {
+              k_gauss_bwd_diag<D><<<B * (L - w + 1), 32, smem, st>>>(L, w, lengths, cov_left, cov_right, chart, adj, g_cov_left, g_cov_right, g_log_struct);
+          } }
         RBN_LAUNCH_CHECK("k_gauss_bwd_diag");
     }
-    if (D == 8 && rows8) {
+    if (use8) {
         { ProfScope ps(KC_OTHER, st); g8::k_sym8<<<2, 64, 0, st>>>(g_cov_left, g_cov_right); }
         RBN_LAUNCH_CHECK("k_sym8");
     }
-    { ProfScope ps(KC_EMISSION, st); k_gauss_bwd_width1<D><<<B * L, 96, 0, st>>>(L, lengths, adj, g_y, g_cov_term, g_log_struct); }
+    { ProfScope ps(KC_EMISSION, st); k_gauss_bwd_width1<D, T><<<B * L, 96, 0, st>>>(L, lengths, adj, g_y, g_cov_term, g_log_struct); }
     RBN_LAUNCH_CHECK("k_gauss_bwd_width1");
     return RBN_OK;
 }
@@ -986,7 +1037,7 @@ int gauss_backward(int D, int B, int L, const int* lengths, const double* cov_le
                    const double* prior_mean, const double* prior_cov, const double* log_struct, const double* chart, double* adj,
                    const double* coef, double* g_y, double* g_cov_term, double* g_cov_left, double* g_cov_right,
                    double* g_prior_mean, double* g_prior_cov, double* g_log_struct, cudaStream_t st) {
-#define RBN_G(DD_) case DD_: return gauss_backward_t<DD_>(B, L, lengths, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, adj, coef, g_y, g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct, st)
+#define RBN_G(DD_) case DD_: return gauss_backward_t<DD_, double>(B, L, lengths, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, adj, coef, g_y, g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct, st)
     switch (D) {
         RBN_G(1); RBN_G(2); RBN_G(3); RBN_G(4); RBN_G(8);
         default:
@@ -994,6 +1045,18 @@ int gauss_backward(int D, int B, int L, const int* lengths, const double* cov_le
             return RBN_E_UNSUPPORTED;
     }
 #undef RBN_G
+}
+
+int gauss_backward_f32(int D, int B, int L, const int* lengths, const double* cov_left, const double* cov_right,
+                       const double* prior_mean, const double* prior_cov, const double* log_struct, const float* chart, float* adj,
+                       const double* coef, float* g_y, double* g_cov_term, double* g_cov_left, double* g_cov_right,
+                       double* g_prior_mean, double* g_prior_cov, double* g_log_struct, cudaStream_t st) {
+    if (D != 8) {
+        set_error("fp32 chart storage is instantiated for D = 8 (got %d); other D run through the fp64 entry points", D);
+        return RBN_E_UNSUPPORTED;
+    }
+    return gauss_backward_t<8, float>(B, L, lengths, cov_left, cov_right, prior_mean, prior_cov, log_struct, chart, adj, coef, g_y,
+                                      g_cov_term, g_cov_left, g_cov_right, g_prior_mean, g_prior_cov, g_log_struct, st);
 }
 
 }  // namespace rbn

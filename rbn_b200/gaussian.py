@@ -9,6 +9,12 @@ Covariances are parametrised by lower-triangular factors (Sigma = L L^T), the pa
 
 All chart arithmetic runs in librbn_b200.so (rbn_gauss_inside_forward / rbn_gauss_inside_backward); there is no CPU
 fallback.
+
+Chart precision: float64 by default (what the reference's tests use, tests/test_multivariate_normal.py:89-91, and what the
+parity tests pin).  `chart_dtype=torch.float32` stores observations, means and covariances in float32 and runs the
+per-split algebra in fp32 -- the reference's DEFAULT dtype (multivariate_normal.py:150 builds its tensors with
+torch.get_default_dtype()) -- through rbn_gauss_inside_*_f32; log weights, log Z, parameters and parameter gradients
+stay float64.  Instantiated for D = 8; other D keep the float64 kernels.
 """
 import ctypes
 
@@ -26,16 +32,18 @@ class _GaussFn(torch.autograd.Function):
     """(y, Sigma_T, Sigma_L, Sigma_R, mu_P, Sigma_P, log_struct) -> log Z [B]."""
 
     @staticmethod
-    def forward(ctx, y, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct, lengths):
+    def forward(ctx, y, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct, lengths, f32):
         lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.RbnError("rbn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         dev = y.device if y.is_cuda else torch.device("cuda", torch.cuda.current_device())
         f64 = lambda t: t.detach().to(device=dev, dtype=torch.float64).contiguous()
-        args = [f64(t) for t in (y, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct)]
+        args = [f64(t) for t in (cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct)]
+        args.insert(0, y.detach().to(device=dev, dtype=torch.float32 if f32 else torch.float64).contiguous())
         B, L, D = args[0].shape
         lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
-        desc = _lib.GaussDesc(D=D, B=B, L=L, flags=0)
+        desc = _lib.GaussDesc(D=D, B=B, L=L, flags=_lib.GAUSS_F32 if f32 else 0)
+        fwd = lib.rbn_gauss_inside_forward_f32 if f32 else lib.rbn_gauss_inside_forward
         nbytes = lib.rbn_gauss_workspace_bytes(ctypes.byref(desc))
         if nbytes == 0:
             _lib.check(-1, "rbn_gauss_workspace_bytes")
@@ -43,45 +51,58 @@ class _GaussFn(torch.autograd.Function):
         logZ = torch.empty(B, dtype=torch.float64, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
-            rc = lib.rbn_gauss_inside_forward(ctypes.byref(desc), *[_ptr(a) for a in args[:1]], _ptr(lengths),
-                                              *[_ptr(a) for a in args[1:]], _ptr(ws), nbytes, _ptr(logZ), stream)
+            rc = fwd(ctypes.byref(desc), *[_ptr(a) for a in args[:1]], _ptr(lengths),
+                     *[_ptr(a) for a in args[1:]], _ptr(ws), nbytes, _ptr(logZ), stream)
         _lib.check(rc, "rbn_gauss_inside_forward")
-        ctx.state = (desc, args, lengths, ws, nbytes)
+        ctx.state = (desc, args, lengths, ws, nbytes, f32)
         ctx.meta = [(t.dtype, t.device) for t in (y, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct)]
         return logZ.to(y.device)
 
     @staticmethod
     def backward(ctx, grad_logZ):
         lib = _lib.load()
-        desc, args, lengths, ws, nbytes = ctx.state
+        desc, args, lengths, ws, nbytes, f32 = ctx.state
         dev = args[0].device
         coef = grad_logZ.to(device=dev, dtype=torch.float64).contiguous()
         grads = [torch.zeros_like(a) for a in args]
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        bwd = lib.rbn_gauss_inside_backward_f32 if f32 else lib.rbn_gauss_inside_backward
         with torch.cuda.device(dev):
-            rc = lib.rbn_gauss_inside_backward(ctypes.byref(desc), _ptr(args[0]), _ptr(lengths),
-                                               *[_ptr(a) for a in args[1:]], _ptr(ws), nbytes, _ptr(coef),
-                                               *[_ptr(g) for g in grads], stream)
+            rc = bwd(ctypes.byref(desc), _ptr(args[0]), _ptr(lengths),
+                     *[_ptr(a) for a in args[1:]], _ptr(ws), nbytes, _ptr(coef),
+                     *[_ptr(g) for g in grads], stream)
         _lib.check(rc, "rbn_gauss_inside_backward")
         outs = [g.to(device=dv, dtype=dt) for g, (dt, dv) in zip(grads, ctx.meta)]
-        return (*outs, None)
+        return (*outs, None, None)
 
 
-def gauss_logZ(y, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct, lengths=None):
-    """Functional entry point: log Z [B] for observations y [B, L, D]."""
+def _use_f32(chart_dtype, dim):
+    if chart_dtype in (None, torch.float64):
+        return False
+    if chart_dtype != torch.float32:
+        raise ValueError(f"chart_dtype must be torch.float64 or torch.float32 (got {chart_dtype})")
+    return dim == 8          # the fp32 row kernels exist for D = 8; other D run the float64 kernels
+
+
+def gauss_logZ(y, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct, lengths=None, chart_dtype=None):
+    """Functional entry point: log Z [B] (float64) for observations y [B, L, D].  `chart_dtype=torch.float32`: fp32
+    charts and per-split algebra (module docstring)."""
     y = torch.as_tensor(y)
     if lengths is None:
         lengths = torch.full((y.shape[0],), y.shape[1], dtype=torch.int32)
-    return _GaussFn.apply(y, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct, torch.as_tensor(lengths))
+    return _GaussFn.apply(y, cov_term, cov_left, cov_right, prior_mean, prior_cov, log_struct, torch.as_tensor(lengths),
+                          _use_f32(chart_dtype, y.shape[-1]))
 
 
 class GaussianRBN(torch.nn.Module):
     """Sequential RBN with one continuous D-dimensional non-terminal variable and Gaussian transitions."""
 
     def __init__(self, dim, cov_term=None, cov_left=None, cov_right=None, prior_mean=None, prior_cov=None,
-                 struct_weights=(0.5, 0.5)):
+                 struct_weights=(0.5, 0.5), chart_dtype=torch.float64):
         super().__init__()
         self.dim = dim
+        _use_f32(chart_dtype, dim)              # validates
+        self.chart_dtype = chart_dtype
         eye = np.eye(dim)
 
         def tril(c):
@@ -124,7 +145,7 @@ class GaussianRBN(torch.nn.Module):
         log_struct = self.struct_log_p - torch.logsumexp(self.struct_log_p, dim=0)
         return gauss_logZ(y, self._cov(self.term_scale_tril), self._cov(self.left_scale_tril),
                           self._cov(self.right_scale_tril), self.prior_mean, self._cov(self.prior_scale_tril),
-                          log_struct, lengths)
+                          log_struct, lengths, chart_dtype=self.chart_dtype)
 
     def inside(self, sequence):
         """Marginal likelihood (linear space) of one sequence [L, D], the RBN.inside contract (base.py:93-121)."""

@@ -229,7 +229,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"librbn_b200.so does not export {name}"
     assert declared == set(_lib.exported_symbols())
-    assert lib.rbn_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.rbn_abi_version() == _lib.ABI_VERSION == 3
     # descriptor validation happens without touching a device
     bad = _lib.RbnDesc(N=0, V=1, B=1, L=1, n_tvars=1, path=0, chunk_items=0, flags=0)
     assert lib.rbn_workspace_bytes(ctypes.byref(bad)) == 0

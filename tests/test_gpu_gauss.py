@@ -111,3 +111,67 @@ def test_full_size_config4_properties():
     with torch.no_grad():
         sub = f({k: (C[k][[4, 1]] if k == "y" else C[k]) for k in names})
     np.testing.assert_allclose(sub.cpu().numpy(), lz.detach().cpu().numpy()[[4, 1]], rtol=1e-12)
+
+
+# ---- float32 charts (RBN_GAUSS_F32): the reference's default dtype ---------------------------------------------------
+# Tolerances: the SAME algebra (oracle/gauss_oracle.py, i.e. rbnet.multivariate_normal's formulas) evaluated by torch in
+# float32 against float64 differs by 2e-6 relative on log Z and 1.8e-3 (max-norm) on the gradients at D = 8, L = 64
+# (4e-7 / 1.7e-4 at L = 24); the fp32 kernels keep the log weights in fp64 and have to stay inside those figures.
+@pytest.mark.parametrize("B,L,ragged,tol_lz,tol_g", [(4, 12, True, 2e-6, 2e-4), (3, 24, False, 2e-6, 5e-4), (2, 64, False, 5e-6, 3e-3)])
+def test_gauss_float32_charts_vs_fp64_oracle(B, L, ragged, tol_lz, tol_g):
+    from oracle import gauss_oracle as G
+    from rbn_b200.gaussian import gauss_logZ
+    D = 8
+    g, lengths = _case(D, B, L, seed=100 + L, ragged=ragged)
+    coef = np.random.default_rng(2).uniform(0.5, 1.5, B)
+    names = ["y", "cov_term", "cov_left", "cov_right", "prior_mean", "prior_cov", "log_struct"]
+    T = {k: torch.tensor(g[k], requires_grad=True) for k in names}
+    ref = G.gauss_inside(T["y"], torch.tensor(lengths), T["cov_term"], T["cov_left"], T["cov_right"], T["prior_mean"],
+                         T["prior_cov"], T["log_struct"])
+    (ref * torch.tensor(coef)).sum().backward()
+    C = {k: torch.tensor(g[k], device="cuda", requires_grad=True) for k in names}
+    lz = gauss_logZ(C["y"], C["cov_term"], C["cov_left"], C["cov_right"], C["prior_mean"], C["prior_cov"],
+                    C["log_struct"], torch.tensor(lengths), chart_dtype=torch.float32)
+    assert lz.dtype == torch.float64
+    (lz * torch.tensor(coef, device="cuda")).sum().backward()
+    rel = np.abs(lz.detach().cpu().numpy() - ref.detach().numpy()) / np.abs(ref.detach().numpy())
+    assert rel.max() <= tol_lz, rel
+    for k in names:
+        got, want = C[k].grad.cpu().numpy(), T[k].grad.numpy()
+        assert got.dtype == np.float64
+        if k.startswith("cov") or k == "prior_cov":
+            want = 0.5 * (want + want.T)
+            got = 0.5 * (got + got.T)
+        if k == "y":
+            for b in range(B):
+                want[b, lengths[b]:] = 0
+        scale = max(np.abs(want).max(), 1e-12)
+        assert np.abs(got - want).max() <= tol_g * scale, (k, np.abs(got - want).max() / scale)
+    # the structural gradients count rule uses: exact in any precision up to the softmax normalisation
+    n = np.asarray(lengths, dtype=np.float64)
+    assert abs(float(C["log_struct"].grad[0]) - float((coef * n).sum())) < 1e-4 * float((coef * n).sum())
+
+
+def test_gauss_float32_descriptor_and_entry_point_must_agree():
+    """RBN_GAUSS_F32 on the fp64 entry point (or the reverse) is refused; D != 8 has no fp32 instantiation and the Python
+    layer runs it through the float64 kernels."""
+    import ctypes
+    from oracle import gauss_oracle as G
+    from rbn_b200 import _lib
+    from rbn_b200.gaussian import gauss_logZ
+    lib = _lib.load()
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    p = ctypes.c_void_p(ws.data_ptr())
+    d32 = _lib.GaussDesc(D=8, B=1, L=4, flags=_lib.GAUSS_F32)
+    d64 = _lib.GaussDesc(D=8, B=1, L=4, flags=0)
+    assert 0 < lib.rbn_gauss_workspace_bytes(ctypes.byref(d32)) < lib.rbn_gauss_workspace_bytes(ctypes.byref(d64))
+    assert lib.rbn_gauss_inside_forward(ctypes.byref(d32), *([p] * 9), 1 << 20, p, None) == -1
+    assert lib.rbn_gauss_inside_forward_f32(ctypes.byref(d64), *([p] * 9), 1 << 20, p, None) == -1
+    assert lib.rbn_gauss_workspace_bytes(ctypes.byref(_lib.GaussDesc(D=4, B=1, L=4, flags=_lib.GAUSS_F32))) == 0
+    g = G.synthetic_gauss(4, 2, 6, seed=1)
+    T = {k: torch.tensor(v) for k, v in g.items()}
+    ref = G.gauss_inside(T["y"], torch.tensor([6, 6]), T["cov_term"], T["cov_left"], T["cov_right"], T["prior_mean"],
+                         T["prior_cov"], T["log_struct"])
+    lz = gauss_logZ(T["y"].cuda(), T["cov_term"], T["cov_left"], T["cov_right"], T["prior_mean"], T["prior_cov"],
+                    T["log_struct"], chart_dtype=torch.float32)
+    np.testing.assert_allclose(lz.cpu().numpy(), ref.numpy(), rtol=1e-9)
