@@ -92,6 +92,8 @@ struct TcTune {
     int bwd_sms0;       // RBN_TC_BWD_SMS0  SMs of the {split-sum, prep, gY} partition in the outside pass (even)
     int nslot;          // RBN_TC_SLOTS     per-chunk buffer copies
     int k3_stream;      // RBN_TC_K3_STREAM 0: gY GEMM beside the split-sum, 1: beside the child-gradient kernel
+    int pdl;            // RBN_PDL          1: the per-diagonal kernels of the tensor-core path are launched with programmatic stream
+                        //                  serialisation (tc_ptx.cuh grid_dep_sync): a kernel's prologue overlaps its predecessor's tail
     float kappa;        // RBN_TC_KAPPA     tcgen05 accumulator-truncation bias per k-block of a chain (compensated in the rule GEMM)
     int hints;          // RBN_TC_HINTS     L2 eviction-priority hints on the bulk tensor copies (bit mask): 1 outside-chart
                         //                  reduce-adds evict_last (the second contribution to a cell of a diagonal should find the
@@ -100,6 +102,25 @@ struct TcTune {
 };
 const TcTune& tc_tune();
 int device_sm_count();
+
+// kern<<<grid, block, smem, st>>>(args...) with, under RBN_PDL, the programmatic-stream-serialisation attribute.  Only for
+// kernels that call ptx::grid_dep_sync() before they touch global memory.
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    if (tc_tune().pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // ---- per-kernel-class launch accounting (always) and CUDA-event timing (when enabled) ------------------------------
 enum KernelClass { KC_EMISSION = 0, KC_SPLITSUM, KC_RULE, KC_GY, KC_COUNTS, KC_CHILD, KC_PREP, KC_SIMT_INSIDE,

@@ -147,6 +147,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_sync();                        // nothing above reads or writes global memory
 
     const int total_tiles = shape.m_tiles * shape.n_tiles;
 
@@ -338,6 +339,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     ptx::cluster_sync();                         // peer barriers are initialised before any remote arrive / multicast
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_sync();                        // nothing above reads or writes global memory
 
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;     // (m_tiles counts 256-row tiles here)
     const bool short_mode = SEG > 0 && shape.short_units != 0;
@@ -489,7 +491,7 @@ int launch_tc_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape sh
     }
     if (tiles < pairs) pairs = tiles;
     if (pairs < 1) return RBN_OK;
-    { ProfScope ps(kclass, st); kern<<<2 * pairs, 256, S::TOTAL, st>>>(tmA, tmB, shape, epi); }
+    { ProfScope ps(kclass, st); launch_pdl(kern, dim3(2 * pairs), dim3(256), S::TOTAL, st, tmA, tmB, shape, epi); }
     RBN_LAUNCH_CHECK(name);
     return RBN_OK;
 }
@@ -520,7 +522,7 @@ int launch_tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape sha
     int tiles = shape.m_tiles * shape.n_tiles;
     int grid = tiles < num_sms ? tiles : num_sms;
     if (grid < 1) return RBN_OK;
-    { ProfScope ps(kclass, st); kern<<<grid, 256, S::TOTAL, st>>>(tmA, tmB, shape, epi); }
+    { ProfScope ps(kclass, st); launch_pdl(kern, dim3(grid), dim3(256), S::TOTAL, st, tmA, tmB, shape, epi); }
     RBN_LAUNCH_CHECK(name);
     return RBN_OK;
 }

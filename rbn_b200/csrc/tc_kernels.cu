@@ -382,6 +382,7 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_sync();                        // nothing above reads or writes global memory
 
     if (warp == 8) {
         // ---------------- TMA producer ----------------
@@ -736,6 +737,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_sync();                        // nothing above reads or writes global memory
     const uint32_t b_bytes = (uint32_t)Npad * 128;
 
     if (warp == 0) {
@@ -945,6 +947,7 @@ k_tc_gy(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_sync();                        // nothing above reads or writes global memory
     const int units = supertiles * ranges;
 
     if (warp == 0) {
@@ -1092,6 +1095,7 @@ k_tc_gy2(const __grid_constant__ CUtensorMap tmG,     // Ghat [cnt rows][N], box
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_sync();                        // nothing above reads or writes global memory
     const int units = supertiles * ranges;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
@@ -1238,6 +1242,7 @@ k_tc_gy3(const __grid_constant__ CUtensorMap tmW,     // Wk [N*N rows][N], box {
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_sync();                        // nothing above reads or writes global memory
     const uint32_t acc_base = tmem_base + (uint32_t)(N / 2);
     const int units = supertiles * ranges;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -1424,6 +1429,7 @@ k_rule_finalize(int N, int L, int Lp, int w, int m0, int t_begin, int cnt, const
                 const float* __restrict__ wscale, const int* __restrict__ item_e,
                 const float* __restrict__ acc, float* __restrict__ cv, int* __restrict__ ce,
                 __half* __restrict__ lc, __half* __restrict__ rc, const float* __restrict__ wdens, float kc) {
+    ptx::grid_dep_sync();
     const int lane = threadIdx.x & 31;
     const int t = t_begin + blockIdx.x * kFinWarps + (threadIdx.x >> 5);
     if (t >= cnt) return;
@@ -1518,6 +1524,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32)
 k_prep_g(int N, int L, int Lp, int w, int m0, int cnt, int rows, int gabs_rows, const int* __restrict__ lengths, const int* __restrict__ ce,
          const int* __restrict__ item_e, const int* __restrict__ wexp, const float* __restrict__ alpha,
          __half* __restrict__ ghat, float* __restrict__ g32, int* __restrict__ gmax_bits, int* __restrict__ gexp) {
+    ptx::grid_dep_sync();
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);
     if (t >= rows) return;                          // rows = cnt rounded up to 64: the pad rows are written as zeros
@@ -1627,6 +1634,7 @@ const TcTune& tc_tune() {
         t.nslot = env_int("RBN_TC_SLOTS", 3);
         t.k3_stream = env_int("RBN_TC_K3_STREAM", 0) != 0;
         t.hints = env_int("RBN_TC_HINTS", kDefaultHints);
+        t.pdl = env_int("RBN_PDL", 0) != 0;
         const char* ek = getenv("RBN_TC_KAPPA");
         t.kappa = (ek && *ek) ? (float)atof(ek) : kTruncPerKBlock;
         if (t.groups < 1) t.groups = 1;
@@ -1824,20 +1832,27 @@ template <class... KArgs, class... Args>
 static cudaError_t launch_maybe_paired(void (*kern)(KArgs...), bool paired, int grid, int threads, size_t smem, cudaStream_t st,
                                        Args&&... args) {
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
+    unsigned na = 0;
     if (paired) grid = (grid + 1) & ~1;
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     if (paired) {
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 2;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
     }
+    if (tc_tune().pdl) {               // both kernels launched through here call ptx::grid_dep_sync() after their prologue
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
@@ -1977,7 +1992,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
         rc = launch_tc_gemm2<false, false, BN, 3, 0, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule,half>", KC_RULE);
         if (rc) return rc;
         { ProfScope ps(KC_RULE_FIN, st);
-          k_rule_finalize<<<(cnt + kFinWarps - 1) / kFinWarps, kFinWarps * 32, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
+          launch_pdl(k_rule_finalize, dim3((cnt + kFinWarps - 1) / kFinWarps), dim3(kFinWarps * 32), 0, st, c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
         RBN_LAUNCH_CHECK("k_rule_finalize");
         return RBN_OK;
     }
@@ -2006,7 +2021,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
                 rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
                 if (rc) return rc;
                 { ProfScope ps(KC_RULE_FIN, st);
-                  k_rule_finalize<<<(cnt + kFinWarps - 1) / kFinWarps, kFinWarps * 32, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(per)); }
+                  launch_pdl(k_rule_finalize, dim3((cnt + kFinWarps - 1) / kFinWarps), dim3(kFinWarps * 32), 0, st, c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(per)); }
                 RBN_LAUNCH_CHECK("k_rule_finalize");
                 return RBN_OK;
             }
@@ -2019,7 +2034,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
-              k_rule_finalize<<<(cnt + kFinWarps - 1) / kFinWarps, kFinWarps * 32, 0, st>>>(c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
+              launch_pdl(k_rule_finalize, dim3((cnt + kFinWarps - 1) / kFinWarps), dim3(kFinWarps * 32), 0, st, c.N, c.L, c.Lp, w, m0, 0, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc(kSegBlocks)); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
@@ -2032,7 +2047,7 @@ static int launch_k2_bn(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool 
             rc = launch_tc_gemm2<false, false, BN, kK2Stages, kSegBlocks, EpiRule>(tmA, tmB2, shape2, epi, sms, st, "k_tc_gemm2<rule>", KC_RULE);
             if (rc) return rc;
             { ProfScope ps(KC_RULE_FIN, st);
-              k_rule_finalize<<<(cnt - t_begin + kFinWarps - 1) / kFinWarps, kFinWarps * 32, 0, st>>>(c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc((shape2.k_blocks + splits - 1) / splits)); }
+              launch_pdl(k_rule_finalize, dim3((cnt - t_begin + kFinWarps - 1) / kFinWarps), dim3(kFinWarps * 32), 0, st, c.N, c.L, c.Lp, w, m0, t_begin, cnt, c.lengths, c.wscale, c.e_of(u), c.acc(u.slot), c.cv, c.ce, c.lc, c.rc, c.wdens, chain_kc((shape2.k_blocks + splits - 1) / splits)); }
             RBN_LAUNCH_CHECK("k_rule_finalize");
             return RBN_OK;
         }
@@ -2076,7 +2091,7 @@ static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
         RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gy3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         int units3 = supertiles * ranges3;
         int np = units3 < pairs ? units3 : pairs;
-        { ProfScope ps(KC_GY, st); k_tc_gy3<<<2 * np, 384, smem3, st>>>(tmW64, tmOut, c.ghat(u.slot), cnt, c.N, supertiles, ranges3); }
+        { ProfScope ps(KC_GY, st); launch_pdl(k_tc_gy3, dim3(2 * np), dim3(384), smem3, st, tmW64, tmOut, c.ghat(u.slot), cnt, c.N, supertiles, ranges3); }
         RBN_LAUNCH_CHECK("k_tc_gy3");
         return RBN_OK;
     }
@@ -2105,7 +2120,7 @@ static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
         RBN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         int units2 = supertiles * ranges2;
         int np = units2 < pairs ? units2 : pairs;
-        { ProfScope ps(KC_GY, st); kern<<<2 * np, 384, smem2, st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges2,
+        { ProfScope ps(KC_GY, st); launch_pdl(kern, dim3(2 * np), dim3(384), smem2, st, tmG, tmW, tmOut, c.N, supertiles, ranges2,
                                                                      (uint64_t)((tc_tune().hints & 2) ? ptx::kEvictFirst : ptx::kEvictNormal),
                                                                      (uint64_t)((tc_tune().hints & 4) ? ptx::kEvictLast : ptx::kEvictNormal)); }
         RBN_LAUNCH_CHECK("k_tc_gy2");
@@ -2118,7 +2133,7 @@ static int launch_k3(TcCtx& c, const Unit& u, cudaStream_t st, int sms) {
     RBN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int units = supertiles * ranges;
     int grid = units < sms ? units : sms;
-    { ProfScope ps(KC_GY, st); k_tc_gy<<<grid, 256, smem, st>>>(tmG, tmW, tmOut, c.N, supertiles, ranges); }
+    { ProfScope ps(KC_GY, st); launch_pdl(k_tc_gy, dim3(grid), dim3(256), smem, st, tmG, tmW, tmOut, c.N, supertiles, ranges); }
     RBN_LAUNCH_CHECK("k_tc_gy");
     return RBN_OK;
 }
@@ -2325,7 +2340,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
             int pg = (cnt + 63) / 64 * 64;      // pad rows are written as zeros
             if (u.coff < 0) RBN_CUDA_CHECK(cudaMemsetAsync(c.gmax(1 + u.slot), 0, sizeof(int), S.st[0]));
             { ProfScope ps(KC_PREP, S.st[0]);
-              k_prep_g<<<(pg + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, S.st[0]>>>(N, L, c.Lp, u.w, u.m0, cnt, pg, u.coff >= 0 ? cnt : pg, lengths, c.ce, c.e_of(u), c.wexp, c.alpha,
+              launch_pdl(k_prep_g, dim3((pg + kPrepWarps - 1) / kPrepWarps), dim3(kPrepWarps * 32), 0, S.st[0], N, L, c.Lp, u.w, u.m0, cnt, pg, u.coff >= 0 ? cnt : pg, lengths, c.ce, c.e_of(u), c.wexp, c.alpha,
                                              c.ghat(u.slot), c.g32_of(u), c.gmax(u.coff >= 0 ? 0 : 1 + u.slot), c.gexp(u.slot)); }
             RBN_LAUNCH_CHECK("k_prep_g");
             S.wait(1, S.record(0));

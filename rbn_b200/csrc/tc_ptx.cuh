@@ -53,6 +53,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
 
 // L2 eviction-priority policies for the .L2::cache_hint operand of bulk tensor copies (the fixed encodings
 // createpolicy.fractional.L2::evict_{normal,first,last} with fraction 1.0 produces)
+// Programmatic dependent launch (griddepcontrol): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (barrier init, TMEM allocation, descriptor prefetch) while the kernel before it on the stream is still draining;
+// grid_dep_sync() then waits until that kernel has completed and its writes are visible, and lets the NEXT kernel of the
+// stream do the same with this one.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void grid_dep_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 static constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;    // streamed once: do not displace what is reused
 static constexpr uint64_t kEvictLast = 0x14F0000000000000ull;     // reused soon: keep
