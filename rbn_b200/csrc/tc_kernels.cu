@@ -1634,7 +1634,7 @@ const TcTune& tc_tune() {
         t.nslot = env_int("RBN_TC_SLOTS", 3);
         t.k3_stream = env_int("RBN_TC_K3_STREAM", 0) != 0;
         t.hints = env_int("RBN_TC_HINTS", kDefaultHints);
-        t.pdl = env_int("RBN_PDL", 0) != 0;
+        t.pdl = env_int("RBN_PDL", 1) != 0;
         const char* ek = getenv("RBN_TC_KAPPA");
         t.kappa = (ek && *ek) ? (float)atof(ek) : kTruncPerKBlock;
         if (t.groups < 1) t.groups = 1;
