@@ -580,7 +580,12 @@ def run_ours(args, wl, secondary=False):
         else:
             entry("rule_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
         if wl["outside"]:
-            entry("gy_gemm", "hbm", y_bytes, peaks["hbm"], "GB/s")
+            # gY is write-only output: N flop per byte WRITTEN, and pure writes reach ~0.6 of the copy bandwidth on this part
+            # (memset 3.9 TB/s against 6.5): HBM-bound up to N ~ 355, tensor-bound at N = 512
+            if N < peaks["tflops"] * 1e3 / (0.6 * peaks["hbm"]):
+                entry("gy_gemm", "hbm", y_bytes, peaks["hbm"], "GB/s")
+            else:
+                entry("gy_gemm", "tensor", f_rule_fwd, peaks["tflops"], "TFLOP/s")
             if gemm_hbm:
                 entry("count_gemm", "hbm", y_bytes, peaks["hbm"], "GB/s")
             else:

@@ -79,9 +79,10 @@ static bool desc_ok(const RbnDesc* d) {
     return true;
 }
 
-// The split-sum and child-gradient kernels hold the splits of a span in two K-slabs of 64 (128 fix-up threads, 128-row
-// stage buffers): a span has at most 128 splits, i.e. L <= 129.
-static constexpr int kTcMaxL = 129;
+// The split-sum and child-gradient kernels hold 128 splits of a span per launch (two K-slabs of 64, 128 fix-up threads,
+// 128-row stage buffers); wider spans take one launch per window of 128 splits (tc_kernels.cu launch_k1 / launch_k5).
+// The cap only bounds the window count (8) and keeps row indices of the chart copies far inside 32 bits.
+static constexpr int kTcMaxL = 1025;
 static bool tc_shape_ok(const RbnDesc* d) {
     return ((d->N % 64 == 0 && d->N >= 64 && d->N <= 256) || d->N == 512) && d->L >= 2 && d->L <= kTcMaxL;
 }
@@ -145,6 +146,10 @@ bool make_layout(const RbnDesc* d, WsLayout* o) {
         o->gmax = take(32 * sizeof(int));
         o->gexp = take(ns * chunk * sizeof(int));
         o->acc = take(ns * chunk * N * sizeof(float));
+        size_t wide = L > 129 ? B * (L - 129) : 0;             // spans of the widest-but-one window count: diagonal w = 130
+        if (wide > chunk) wide = chunk;
+        o->ywin = take(wide * N * N * sizeof(__half));
+        o->ywin_e = take(wide * sizeof(int));
         // split-sum cache: whole spans only, never more than the batch has, off in the two-stream schedules (their
         // forward and backward passes cut the diagonals differently)
         const size_t per_span = N * N * sizeof(__half) + sizeof(int) + N * sizeof(__half) + N * sizeof(float);

@@ -67,6 +67,9 @@ struct WsLayout {
     size_t gmax;        // int32 [16] running max |G| (float bits) per scale group + float [16] the groups' inverse scales
     size_t gexp;        // int32 [nslot][chunk]
     size_t acc;         // float [nslot][chunk][N]  K-split partial sums of the rule GEMM's tail tiles
+    // spans wider than 129 tokens (more than 128 splits): partial split-sum of one window of splits, before k_y_combine
+    size_t ywin;        // half [wide_items][N*N]   (wide_items = most spans a unit of a diagonal w > 129 can have; 0 if L <= 129)
+    size_t ywin_e;      // int32 [wide_items]
     // split-sum cache (RbnDesc.cache_bytes): the inside pass writes the Y of `cache_spans` spans here (widest diagonals
     // first) and the outside pass reads them back instead of recomputing them; E_m of the same spans beside it
     size_t ycache;      // half [cache_spans][N*N]

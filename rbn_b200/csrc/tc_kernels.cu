@@ -304,10 +304,14 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
               const __grid_constant__ CUtensorMap tmLC1, const __grid_constant__ CUtensorMap tmRC1,   // second K-slab (rows = Kpad - 64)
               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYtail,
               int N, int L, int Lp, int w, int m0, int cnt, int stages, const int* __restrict__ lengths,
-              const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e, int nslots, uint64_t y_pol, int nbuf) {
+              const int* __restrict__ ce, __half* __restrict__ Y, int* __restrict__ item_e, int nslots, uint64_t y_pol, int nbuf,
+              int j0, int ns) {
+    // [j0, j0 + ns): the window of a span's w - 1 splits this launch sums (ns <= 128: two K slabs of 64).  Spans of up to
+    // 129 tokens are one window (j0 = 0, ns = w - 1); wider spans take one launch per window, each with its own scale
+    // exponent, folded together by k_y_combine (launch_split_sum).  Pair mode: always the whole span.
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int Kpad = ((w - 1) + 15) & ~15;
+    const int Kpad = (ns + 15) & ~15;
     const int parts = PAIR ? 1 : (Kpad + 63) / 64;
     // N > 256: the N x N split-sum is cut into (N/256)^2 sub-blocks of 256 x 256, each handled like a span of its own
     const int NS = PAIR ? 64 : (N > 256 ? 256 : N);          // nonterminals per sub-block side
@@ -413,8 +417,8 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
                     continue;
                 }
                 if (k > lengths[b]) continue;
-                const int lc_row = (int)(((size_t)b * L + i) * Lp + (i + 1));
-                const int rc_row = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
+                const int lc_row = (int)(((size_t)b * L + i) * Lp + (i + 1) + j0);
+                const int rc_row = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1) + j0);
                 for (int sub = 0; sub < nsub; ++sub) {
                     const int bcol = (sub >> nblk_sh) * RB, ccol = (sub & (nblk - 1)) * NS;
                     for (int part = 0; part < parts; ++part) {
@@ -500,9 +504,9 @@ k_tc_splitsum(const __grid_constant__ CUtensorMap tmLC, const __grid_constant__ 
         // (kept as two registers and added at the point of use, so that the loads stay in flight across the iteration)
         auto fetch_sft = [&](int t, int b, int i, int& ea, int& eb) {       // (b, i): span t of the launch
             ea = INT_MIN; eb = 0;
-            if (t >= cnt || pj >= w - 1 || i + w > lengths[b]) return;
+            if (t >= cnt || pj >= ns || i + w > lengths[b]) return;
             const int* ce_seq = ce + (size_t)b * C;
-            const int u = pj + 1;
+            const int u = j0 + pj + 1;
             ea = ce_seq[cell_off(u, L) + i];
             eb = ce_seq[cell_off(w - u, L) + i + u];
         };
@@ -697,10 +701,12 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                const __grid_constant__ CUtensorMap tmALt,   // same views, tail_rows instead of 32: last chunk of a span's splits
                const __grid_constant__ CUtensorMap tmARt,
                const int* __restrict__ ce, const int* __restrict__ item_e, const int* __restrict__ gexp,
-               uint64_t red_pol, uint64_t gy2_pol, int stages) {
+               uint64_t red_pol, uint64_t gy2_pol, int stages, int j0, int ns) {
+    // [j0, j0 + ns): the window of a span's w - 1 splits whose children this launch serves (ns <= 128; wider spans take one
+    // launch per window: the windows' child gradients are independent outputs, gY is read once per window)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int stage_bytes = 16384 + ((((w - 1) + 15) & ~15) * 128);
+    const int stage_bytes = 16384 + (((ns + 15) & ~15) * 128);
     uint8_t* rbuf = smem + stages * stage_bytes;        // [2 groups][2] x 16 KB tiles [32 splits][128 nonterminals] fp32
     uint64_t* full = (uint64_t*)(rbuf + 65536);
     uint64_t* empty = full + kK5MaxStages;
@@ -710,7 +716,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
     float* fac = (float*)(tmem_slot + 2);    // [2 groups][2][128] split factors c_j * 2^eG of the current / next span
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int Npad = ((w - 1) + 15) & ~15;
+    const int Npad = (ns + 15) & ~15;
     const int halves = (N + 127) / 128;
     const int units = 2 * halves;            // unit = kind * halves + h ; kind 0 = left-child, 1 = right-child gradient
     const int kblocks = N / 64;
@@ -748,8 +754,8 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                 const int m = m0 + t;
                 const int b = m / nI, i = m - b * nI, k = i + w;
                 if (k > lengths[b]) continue;
-                const int rc_row = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1));
-                const int lc_row = (int)(((size_t)b * L + i) * Lp + (i + 1));
+                const int rc_row = (int)(((size_t)b * (L + 1) + k) * Lp + (i + 1) + j0);
+                const int lc_row = (int)(((size_t)b * L + i) * Lp + (i + 1) + j0);
                 for (int u = 0; u < units; ++u) {
                     const int kind = u / halves, h = u - kind * halves;
                     for (int kb = 0; kb < kblocks; ++kb) {
@@ -830,12 +836,12 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
         // combined at the point of use so that the loads stay in flight (INT_MIN: padding split, factor 0)
         auto fetch_fac = [&](int t, int& e0, int& e1, int& e2, int& e3) {
             e0 = INT_MIN; e1 = e2 = e3 = 0;
-            if (t >= cnt || p >= w - 1) return;
+            if (t >= cnt || p >= ns) return;
             const int m = m0 + t;
             const int b = m / nI, i = m - b * nI;
             if (i + w > lengths[b]) return;
             const int* ce_seq = ce + (size_t)b * C;
-            const int us = p + 1;
+            const int us = j0 + p + 1;
             e0 = ce_seq[cell_off(us, L) + i];
             e1 = ce_seq[cell_off(w - us, L) + i + us];
             e2 = item_e[t];
@@ -852,7 +858,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
             float* facb = fac + (grp * 2 + fbuf) * 128;
             facb[p] = f_cur;
             ptx::named_bar_sync(2 + grp, 128);
-            const int rowL = (int)(((size_t)b * L + i) * Lp + (i + 1));
+            const int rowL = (int)(((size_t)b * L + i) * Lp + (i + 1) + j0);
             for (int u = grp; u < units; u += 2) {
                 const int kind = u / halves, h = u - kind * halves;
                 const uint32_t slot = (nunit0 + u) & 3, slot_phase = ((nunit0 + u) >> 2) & 1;
@@ -860,7 +866,7 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                 ptx::tc_fence_after();
                 const int xl = q * 32 + lane;                    // row of the 128-wide tile
                 const uint32_t taddr = tmem_base + slot * 128 + ((uint32_t)(q * 32) << 16);
-                for (int c0 = 0; c0 < w - 1; c0 += 32) {
+                for (int c0 = 0; c0 < ns; c0 += 32) {
                     float v[32];
                     ptx::tmem_ld32(taddr + c0, v);
                     float* tile = reinterpret_cast<float*>(mybuf + (nred & 1) * 16384);
@@ -872,12 +878,12 @@ k_tc_childgrad(const __grid_constant__ CUtensorMap tmGYk,   // gY as [rows=(t,b)
                     ptx::fence_proxy_async_smem();
                     ptx::named_bar_sync(2 + grp, 128);
                     if (issuer) {
-                        const bool last = (c0 + 32 >= w - 1);       // the tail box covers only the rows that hold splits
+                        const bool last = (c0 + 32 >= ns);          // the tail box covers only the rows that hold splits
                         // left children (i, j): consecutive rows of start i.  Right children (j, k): row `end = k` of the
                         // consecutive starts j -- both land in ONE chart, so the two contributions a cell receives per
                         // diagonal meet in L2 (they are issued within a few microseconds of each other)
                         if (kind == 0) ptx::tma_reduce_add_2d(last ? &tmALt : &tmAL, tile, h * 128, rowL + c0, red_pol);
-                        else ptx::tma_reduce_add_3d(last ? &tmARt : &tmAR, tile, h * 128, k, b * L + (i + 1) + c0, red_pol);
+                        else ptx::tma_reduce_add_3d(last ? &tmARt : &tmAR, tile, h * 128, k, b * L + (i + 1) + j0 + c0, red_pol);
                         ptx::bulk_commit();
                     }
                     ++nred;
@@ -1421,6 +1427,36 @@ __global__ void k_copy_width1(int N, int L, int Lp, const int* __restrict__ leng
     }
 }
 // max-shift epilogue of the K-split tail tiles of the rule GEMM: acc[t][a] (fp32 sums) -> chart, exponents, fp16 copies.
+// Splits per split-sum / child-gradient launch (two K slabs of 64 chart rows; 128 fix-up threads, 128 factors).
+static constexpr int kMaxWindow = 128;
+
+// Y[t] <- Y[t] 2^(E[t] - E') + Yp[t] 2^(Ep[t] - E'),  E[t] <- E' = max(E[t], Ep[t]): folds the partial split-sum of one more
+// window of splits (spans wider than 129 tokens) into the span's split-sum.  One CTA per span, 16-byte accesses.
+__global__ void __launch_bounds__(256)
+k_y_combine(int N, int L, int w, int m0, const int* __restrict__ lengths, __half* __restrict__ Y, int* __restrict__ E,
+            const __half* __restrict__ Yp, const int* __restrict__ Ep) {
+    const int t = blockIdx.x;
+    const int nI = L - w + 1;
+    const int m = m0 + t;
+    const int b = m / nI, i = m - b * nI;
+    if (i + w > lengths[b]) return;                 // span beyond its sequence: both parts are zeros, no exponent was written
+    const int ea = E[t], eb = Ep[t];
+    const int e = max(ea, eb);
+    const __half2 sa = __float2half2_rn(ldexpf(1.0f, max(ea - e, -60))), sb = __float2half2_rn(ldexpf(1.0f, max(eb - e, -60)));
+    uint4* y = reinterpret_cast<uint4*>(Y + (size_t)t * N * N);
+    const uint4* yp = reinterpret_cast<const uint4*>(Yp + (size_t)t * N * N);
+    for (int idx = threadIdx.x; idx < N * N / 8; idx += blockDim.x) {
+        uint4 a = y[idx], p = yp[idx];
+        __half2* ha = reinterpret_cast<__half2*>(&a);
+        const __half2* hp = reinterpret_cast<const __half2*>(&p);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ha[q] = __hfma2(ha[q], sa, __hmul2(hp[q], sb));
+        y[idx] = a;
+    }
+    __syncthreads();                                // every thread has read E[t]
+    if (threadIdx.x == 0) E[t] = e;
+}
+
 // One WARP per span (8 spans per CTA, N / 32 values per lane, float4 accesses): no block-level synchronisation and an
 // eighth of the CTAs of the former one-CTA-per-span version (20 -> ~8 us per diagonal of 16 k spans; 508 launches per step).
 static constexpr int kFinWarps = 8;
@@ -1870,10 +1906,12 @@ static int prep_weights(TcCtx& c, const float* W, cudaStream_t st) {
     return RBN_OK;
 }
 
-static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired, bool half_sm = false) {
+// Split-sum launch over the window [j0, j0 + ns) of every span's splits; Y / exponents go to (Ydst, Edst).
+static int launch_k1_window(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired, bool half_sm, int j0, int ns,
+                            __half* Ydst, int* Edst) {
     int N = c.N, L = c.L, B = c.B;
     const int w = u.w, m0 = u.m0, cnt = u.cnt;
-    const int Kpad = ((w - 1) + 15) & ~15;
+    const int Kpad = (ns + 15) & ~15;
     const uint32_t rows0 = (uint32_t)(Kpad < 64 ? Kpad : 64), rows1 = (uint32_t)(Kpad > 64 ? Kpad - 64 : 16);
     CUtensorMap tmLC, tmRC, tmLC1, tmRC1;
     int rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, rows0);
@@ -1885,13 +1923,13 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     rc = make_tmap_2d(&tmRC1, c.rc, (uint64_t)N, (uint64_t)B * (L + 1) * c.Lp, (uint64_t)N * 2, rows1);
     if (rc) return rc;
     CUtensorMap tmY, tmYtail;
-    rc = make_tmap_2d(&tmY, c.y_of(u), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
+    rc = make_tmap_2d(&tmY, Ydst, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmYtail, c.y_of(u), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
+    rc = make_tmap_2d(&tmYtail, Ydst, (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 64);
     if (rc) return rc;
     const int NS = N > 256 ? 256 : N;
     int halves = (NS + 127) / 128;
-    const bool pairm = (N == 64) && (Kpad <= 64);        // two spans per CTA iteration (see k_tc_splitsum)
+    const bool pairm = (N == 64) && (Kpad <= 64) && (ns == w - 1);      // two spans per CTA iteration (see k_tc_splitsum)
     const int items = pairm ? (cnt + 1) / 2 : cnt;
     size_t stage_bytes = pairm ? (size_t)4 * Kpad * 128 : (size_t)(halves * 2 + NS / 64) * 8192;
     // small N: a span is a few KB of operands and 8-32 KB of output, the per-span hand-offs dominate -> co-resident CTAs
@@ -1929,10 +1967,29 @@ static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
       // runs each on a 1.5 GHz box -- the epilogue's ~960 instructions per span are not what paces this kernel.
       static const int k1_groups = env_int("RBN_TC_K1_GROUPS", 1);
       RBN_CUDA_CHECK(launch_maybe_paired(kern, paired, grid, (ctas > 1 || k1_groups < 2) ? k1_threads<2>() : k1_threads<1>(), smem, st, tmLC, tmRC, tmLC1, tmRC1, tmY, tmYtail, N, L,
-                                         c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, c.y_of(u), c.e_of(u), nslots,
-                                         (uint64_t)((tc_tune().hints & 2) ? ptx::kEvictFirst : ptx::kEvictNormal), nbuf)); }
+                                         c.Lp, w, m0, cnt, stages, c.lengths, (const int*)c.ce, Ydst, Edst, nslots,
+                                         (uint64_t)((tc_tune().hints & 2) ? ptx::kEvictFirst : ptx::kEvictNormal), nbuf, j0, ns)); }
     RBN_LAUNCH_CHECK("k_tc_splitsum");
     return RBN_OK;
+}
+
+// Spans wider than 129 tokens have more than the 128 splits one split-sum launch holds (two K slabs of 64): the launch is
+// repeated per window of 128 splits into a scratch buffer of the workspace (WsLayout::ywin) and the partial sums, each
+// under its own scale exponent, are folded into the unit's Y.
+static int launch_k1(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired, bool half_sm = false) {
+    const int S = u.w - 1;
+    if (S <= kMaxWindow) return launch_k1_window(c, u, st, sms, paired, half_sm, 0, S, c.y_of(u), c.e_of(u));
+    int rc = launch_k1_window(c, u, st, sms, paired, half_sm, 0, kMaxWindow, c.y_of(u), c.e_of(u));
+    __half* yw = (__half*)(c.base + c.ws->ywin);
+    int* ew = (int*)(c.base + c.ws->ywin_e);
+    for (int j0 = kMaxWindow; j0 < S && !rc; j0 += kMaxWindow) {
+        const int ns = S - j0 < kMaxWindow ? S - j0 : kMaxWindow;
+        if ((rc = launch_k1_window(c, u, st, sms, paired, half_sm, j0, ns, yw, ew))) break;
+        { ProfScope ps(KC_SPLITSUM, st);
+          k_y_combine<<<u.cnt, 256, 0, st>>>(c.N, c.L, u.w, u.m0, c.lengths, c.y_of(u), c.e_of(u), (const __half*)yw, (const int*)ew); }
+        RBN_LAUNCH_CHECK("k_y_combine");
+    }
+    return rc;
 }
 
 // K-split factor of the partial last wave of a 2-CTA GEMM: r tiles left for `pairs` CTA pairs.  Splitting each into s
@@ -2191,10 +2248,10 @@ static int launch_k4(TcCtx& c, const Unit& u, float* gW, cudaStream_t st, int sm
     }
 }
 
-static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired) {
+static int launch_k5_window(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired, int j0, int ns) {
     int N = c.N, L = c.L, B = c.B;
     const int w = u.w, m0 = u.m0, cnt = u.cnt;
-    int Npad = ((w - 1) + 15) & ~15;
+    int Npad = (ns + 15) & ~15;
     CUtensorMap tmGYk, tmGYm, tmRC, tmLC;
     int rc = make_tmap_2d(&tmGYk, c.gy(u.slot), (uint64_t)N, (uint64_t)cnt * N, (uint64_t)N * 2, 128);
     if (rc) return rc;
@@ -2205,7 +2262,7 @@ static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
     rc = make_tmap_2d(&tmLC, c.lc, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 2, (uint32_t)Npad);
     if (rc) return rc;
     CUtensorMap tmAL, tmAR, tmALt, tmARt;
-    const uint32_t tail_rows = (uint32_t)(((w - 1) % 32) ? ((w - 1) % 32) : 32);
+    const uint32_t tail_rows = (uint32_t)((ns % 32) ? (ns % 32) : 32);
     rc = make_tmap_2d_f32(&tmAL, c.alpha, (uint64_t)N, (uint64_t)B * L * c.Lp, (uint64_t)N * 4, 128, 32);
     if (rc) return rc;
     rc = make_tmap_3d_f32(&tmAR, c.alpha, (uint64_t)N, (uint64_t)c.Lp, (uint64_t)B * L, 128, 32);
@@ -2228,9 +2285,17 @@ static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool pai
                                          c.lengths, tmAL, tmAR, tmALt, tmARt, (const int*)c.ce, (const int*)c.e_of(u),
                                          (const int*)c.gexp(u.slot),
                                          (uint64_t)((tc_tune().hints & 1) ? ptx::kEvictLast : ptx::kEvictNormal),
-                                         (uint64_t)((tc_tune().hints & 8) ? ptx::kEvictFirst : ptx::kEvictNormal), stages)); }
+                                         (uint64_t)((tc_tune().hints & 8) ? ptx::kEvictFirst : ptx::kEvictNormal), stages, j0, ns)); }
     RBN_LAUNCH_CHECK("k_tc_childgrad");
     return RBN_OK;
+}
+
+static int launch_k5(TcCtx& c, const Unit& u, cudaStream_t st, int sms, bool paired) {
+    const int S = u.w - 1;
+    int rc = RBN_OK;
+    for (int j0 = 0; j0 < S && !rc; j0 += kMaxWindow)
+        rc = launch_k5_window(c, u, st, sms, paired, j0, S - j0 < kMaxWindow ? S - j0 : kMaxWindow);
+    return rc;
 }
 
 // Inside pass.  Stream 0 runs the split-sums (HBM-write bound), stream 1 the rule GEMMs (tensor / HBM-read bound).
@@ -2254,7 +2319,8 @@ int tc_forward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W,
     { ProfScope ps(KC_EMISSION, st); k_copy_width1<<<B * L, 128, 0, st>>>(N, L, c.Lp, lengths, c.cv, c.lc, c.rc); }
     RBN_LAUNCH_CHECK("k_copy_width1");
 
-    const int mode = (tune.overlap && ws.nslot >= 2 && B >= 2 * tune.groups) ? tune.overlap : 0;
+    // (spans wider than 129 tokens share ONE scratch buffer for their split windows: single-stream schedule only)
+    const int mode = (tune.overlap && ws.nslot >= 2 && B >= 2 * tune.groups && L <= kMaxWindow + 1) ? tune.overlap : 0;
     const bool overlap = mode != 0, half_sm = (mode == 2);
     const int groups = overlap ? tune.groups : 1;
     Sched S;
@@ -2312,7 +2378,7 @@ int tc_backward(const RbnDesc* d, const WsLayout& ws, char* base, const float* W
     RBN_LAUNCH_CHECK("k_tc_outside_seed");
 
     // co-resident mode (2): inside pass only so far
-    const int mode = ((tune.overlap == 1 || tune.overlap == 3) && ws.nslot >= 2 && B >= 2 * tune.groups) ? tune.overlap : 0;
+    const int mode = ((tune.overlap == 1 || tune.overlap == 3) && ws.nslot >= 2 && B >= 2 * tune.groups && L <= kMaxWindow + 1) ? tune.overlap : 0;
     const bool overlap = mode != 0;
     const int groups = overlap ? tune.groups : 1;
     Sched S;

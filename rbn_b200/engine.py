@@ -251,7 +251,7 @@ class _InsideFn(torch.autograd.Function):
         return outs[0], outs[1], outs[2], None, None, None, None, None, None, None
 
 
-TC_MAX_L = 129        # tensor-core path: at most 128 splits per span (csrc/api.cu kTcMaxL)
+TC_MAX_L = 1025       # tensor-core path: spans wider than 129 tokens run in windows of 128 splits (csrc/api.cu kTcMaxL)
 
 
 def _padded_cardinality(N, batch_spans, L=2):

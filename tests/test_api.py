@@ -303,11 +303,12 @@ def test_batched_tokens_are_per_variable_values_and_range_checked():
         inside_logZ(W, T, pr, torch.tensor([[0, 1, 1]]), lengths=torch.tensor([4]))
 
 
-def test_long_sequences_are_not_padded_onto_the_tensor_core_path():
+def test_very_long_sequences_are_not_padded_onto_the_tensor_core_path():
     from rbn_b200 import engine
     assert engine._padded_cardinality(40, 100000, L=128) == 64
-    assert engine._padded_cardinality(40, 100000, L=130) == 40   # tensor-core kernels take at most 128 splits per span
-    big = _lib.RbnDesc(N=64, V=4, B=2, L=130, n_tvars=1, path=_lib.PATH_TCGEN05, chunk_items=0, flags=0)
+    assert engine._padded_cardinality(40, 100000, L=130) == 64   # spans wider than 129 tokens: windows of 128 splits
+    assert engine._padded_cardinality(40, 100000, L=1026) == 40  # beyond the cap of the tensor-core path
+    big = _lib.RbnDesc(N=64, V=4, B=2, L=1026, n_tvars=1, path=_lib.PATH_TCGEN05, chunk_items=0, flags=0)
     lib = _lib.load()
     assert lib.rbn_resolve_path(ctypes.byref(big)) == -4         # RBN_E_UNSUPPORTED
     big.path = _lib.PATH_AUTO

@@ -127,24 +127,55 @@ def test_split_sum_cache_does_not_change_results(monkeypatch, N, L, B, chunk):
     assert metrics(res[0][1], gW.numpy())["max_rel"] <= GRAD_RTOL
 
 
-@pytest.mark.parametrize("L", [130, 200])
-def test_sequences_longer_than_the_tensor_core_path_takes(L):
-    """The tensor-core kernels hold at most 128 splits per span (L <= 129).  Longer input: PATH_AUTO runs the CUDA-core
-    path (correct, checked against the oracle), an explicit PATH_TCGEN05 request is refused with RBN_E_UNSUPPORTED."""
+@pytest.mark.parametrize("N,L,B,cache_gb,against", [(64, 130, 2, None, "oracle"), (64, 200, 2, "0", "oracle"),
+                                                   (128, 150, 3, None, "simt"), (64, 300, 1, None, "simt"),
+                                                   (128, 260, 2, "0.02", "simt"), (64, 513, 1, None, "simt")])
+def test_sequences_longer_than_129_tokens_on_the_tensor_core_path(monkeypatch, N, L, B, cache_gb, against):
+    """A split-sum / child-gradient launch holds 128 splits of a span; spans wider than 129 tokens run one launch per window
+    of 128 splits, the partial split-sums (each under its own scale exponent) are folded by k_y_combine (L >= 130
+    used to be refused on this path).  Whole / partial / no split-sum cache, ragged batch, NaN-poisoned workspace; two to
+    four windows.  Reference: the fp64 oracle where it is affordable on the GPU box's host, else the CUDA-core path (itself
+    checked against the oracle at these lengths, tests/test_gpu_parity.py and the first two cases here)."""
     from oracle import inside_oracle as O
     from rbn_b200 import inside_logZ, _lib
-    N, V, B = 64, 8, 2
+    V = 8
     W, T, pr = O.synthetic_grammar(N, V, seed=11)
-    tok, lengths = O.synthetic_tokens(B, L, V, seed=12)
-    Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
-    lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths))
-    lz.sum().backward()
-    ref, gW, gT, gP = O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths)
-    assert np.abs(lz.detach().cpu().numpy() - ref.numpy()).max() <= LOGZ_RTOL * np.abs(ref.numpy()).max()
-    assert metrics(Wt.grad.cpu().numpy(), gW.numpy())["max_rel"] <= GRAD_RTOL
-    assert metrics(Tt.grad.cpu().numpy(), gT.numpy())["max_rel"] <= GRAD_RTOL
-    with pytest.raises(_lib.RbnError, match="L <= 129|129"):
-        inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), path=_lib.PATH_TCGEN05)
+    tok, lengths = O.synthetic_tokens(B, L, V, seed=12, ragged=B > 2)
+    lengths[0] = L
+    tok[0] = np.random.default_rng(5).integers(0, V, L)
+    monkeypatch.setenv("RBN_DEBUG_POISON", "1")
+    if cache_gb is not None:
+        monkeypatch.setenv("RBN_Y_CACHE_GB", cache_gb)
+
+    def run(path):
+        Wt, Tt, pt = (torch.tensor(x, device="cuda", requires_grad=True) for x in (W, T, pr))
+        lz = inside_logZ(Wt, Tt, pt, torch.tensor(tok), torch.tensor(lengths), path=path)
+        lz.sum().backward()
+        return lz.detach().cpu().numpy(), Wt.grad.cpu().numpy(), Tt.grad.cpu().numpy(), pt.grad.cpu().numpy()
+
+    lz, gW_, gT_, gP_ = run(_lib.PATH_TCGEN05)
+    if against == "oracle":
+        ref, gW, gT, gP = (x.numpy() for x in O.flat_inside_with_grads(W, T, pr, tok[:, :, None], lengths))
+    else:
+        ref, gW, gT, gP = run(_lib.PATH_SIMT)
+    assert np.abs(lz - ref).max() <= LOGZ_RTOL * np.abs(ref).max()
+    for got, want in ((gW_, gW), (gT_, gT), (gP_, gP)):
+        m = metrics(got, want)
+        assert m["max_rel"] <= GRAD_RTOL and m["l2_rel"] <= GRAD_RTOL, m
+    assert abs(float((gW_.astype(np.float64) * W).sum()) - float((lengths - 1).sum())) <= 1e-3 * float((lengths - 1).sum())
+
+
+def test_tensor_core_path_length_cap():
+    """Beyond the cap (1025 tokens) PATH_AUTO runs the CUDA-core path and an explicit PATH_TCGEN05 request is refused."""
+    import ctypes
+    from rbn_b200 import _lib
+    lib = _lib.load()
+    d = _lib.RbnDesc(N=64, V=8, B=1, L=1026, n_tvars=1, path=_lib.PATH_AUTO, chunk_items=0, flags=0, cache_bytes=0)
+    assert lib.rbn_resolve_path(ctypes.byref(d)) == _lib.PATH_SIMT
+    d.path = _lib.PATH_TCGEN05
+    assert lib.rbn_resolve_path(ctypes.byref(d)) == -4
+    d.L = 1025
+    assert lib.rbn_resolve_path(ctypes.byref(d)) == _lib.PATH_TCGEN05
 
 
 @pytest.mark.parametrize("N,L", [(10, 64), (64, 64), (10, 120)])
