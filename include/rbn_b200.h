@@ -45,10 +45,11 @@ extern "C" {
 #define RBN_E_UNSUPPORTED -4  /* shape outside what the selected path supports */
 
 /* RbnDesc.path */
-#define RBN_PATH_AUTO     0   /* tensor-core path when N is 64, 128, 192, 256 or 512 and 2 <= L <= 129, else the shared-memory path */
+#define RBN_PATH_AUTO     0   /* tensor-core path when N is 64, 128, 192, 256 or 512 and 2 <= L <= 1025, else the shared-memory path */
 #define RBN_PATH_SIMT     1   /* shared-memory / CUDA-core path, fp32 end to end (small nonterminal counts) */
-#define RBN_PATH_TCGEN05  2   /* span-diagonal tcgen05 tensor-core path (fp16 operands, fp32 accumulate); L <= 129 (at most 128
-                                 splits per span), longer inputs: RBN_E_UNSUPPORTED here, the shared-memory path under AUTO */
+#define RBN_PATH_TCGEN05  2   /* span-diagonal tcgen05 tensor-core path (fp16 operands, fp32 accumulate); L <= 1025 (spans wider
+                                 than 129 tokens: one split-sum / child-gradient launch per window of 128 splits); longer
+                                 inputs: RBN_E_UNSUPPORTED here, the shared-memory path under AUTO */
 
 typedef struct RbnDesc {
     int32_t N;            /* number of (flattened) nonterminal values */
