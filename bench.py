@@ -224,7 +224,8 @@ def run_reference_gauss(args, wl):
     torch.set_num_threads(os.cpu_count() or 1)
     D, L = wl["D"], wl["L"]
     syn = GO.synthetic_gauss(D, 4, L, seed=10)
-    tt = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != "y")) for k, v in syn.items()}
+    dt = torch.float32 if wl.get("f32") else torch.float64          # c4f32: the reference's default dtype
+    tt = {k: torch.tensor(v, dtype=dt, requires_grad=(k != "y")) for k, v in syn.items()}
     times = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -236,10 +237,10 @@ def run_reference_gauss(args, wl):
     t = sum(times) / len(times)
     v = 1.0 / t
     cores = torch.get_num_threads()
-    sample = f"1 sequence per step, D={D}, L={L}, fp64 torch composition of rbnet.multivariate_normal + autograd"
+    sample = f"1 sequence per step, D={D}, L={L}, {'fp32' if wl.get('f32') else 'fp64'} torch composition of rbnet.multivariate_normal + autograd"
     print(json.dumps(dict(metric="inside+gradient sequences/sec", value=v, unit="seq/s", n_gpus=args.gpus, steps=args.steps,
                           warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                          dtype="f64", data="synthetic", impl="reference",
+                          dtype="f32" if wl.get("f32") else "f64", data="synthetic", impl="reference",
                           config=workload_config(wl, args.batch or wl["B"], int(os.environ.get("WORLD_SIZE", "1"))),
                           cpu_baseline=dict(value=v, unit="seq/s", cores=cores, kind="port", sample=sample),
                           e2e=dict(value=v, unit="seq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)), flush=True)
